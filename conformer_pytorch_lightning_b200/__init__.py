@@ -1,0 +1,16 @@
+"""B200-native (sm_100a) Conformer encoder: drop-in for the encoder of
+Lingeng56/conformer-pytorch-lightning (src/encoder.py, encoder_layer.py, attention.py,
+convolution.py, feedforward.py, utils.py mask helpers), executed by hand-written CUDA kernels
+behind the C-ABI in include/cfm_b200.h.  No CPU fallback: CPU tensors raise."""
+from .attention import (MultiHeadSelfAttentionModule, PositionalEncoding, RelativeMultiHeadSelfAttentionModule,
+                        RelativePositionalEncoding)
+from .convolution import ConvolutionModule, ConvolutionSubSampling
+from .encoder import ConformerEncoder
+from .encoder_layer import ConformerEncoderLayer
+from .feedforward import PositionwiseFeedForwardModule
+from .utils import make_attn_mask, make_pad_mask, subsequent_chunk_mask
+
+__all__ = ["ConformerEncoder", "ConformerEncoderLayer", "RelativeMultiHeadSelfAttentionModule",
+           "MultiHeadSelfAttentionModule", "RelativePositionalEncoding", "PositionalEncoding", "ConvolutionModule",
+           "ConvolutionSubSampling", "PositionwiseFeedForwardModule", "make_pad_mask", "make_attn_mask",
+           "subsequent_chunk_mask"]

@@ -1,0 +1,82 @@
+"""ctypes binding of libcfm_b200.so (the C-ABI declared in include/cfm_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails this module
+raises.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C conformer_pytorch_lightning_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfm_b200.so")
+
+F32, BF16 = 0, 1
+EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_GLU, EPI_RESIDUAL = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+
+# every symbol include/cfm_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm",
+    "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu",
+]
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+
+_p, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+
+def _declare(lib):
+    lib.cfm_abi_version.restype = _i
+    lib.cfm_last_error.restype = ctypes.c_char_p
+    lib.cfm_init.argtypes = [_i]
+    lib.cfm_launch_count.restype = _i64
+    lib.cfm_layernorm.argtypes = [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _f, _p]
+    lib.cfm_gemm.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _p, _i, _p]
+    lib.cfm_attention.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i, _i, _i, _i,
+                                  _p, _i64, _i64, _p, _f, _i, _i, _p]
+    lib.cfm_relpos_keys.argtypes = [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _p]
+    lib.cfm_dwconv.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]
+    lib.cfm_bn_stats.argtypes = [_p, _i, _i, _p, _p, _p]
+    lib.cfm_bn_apply_silu.argtypes = [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version"):
+            fn.restype = _i
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the extension is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback).")
+                handle = ctypes.CDLL(LIB_PATH)
+                _declare(handle)
+                if handle.cfm_abi_version() != 1:
+                    raise RuntimeError("libcfm_b200.so ABI version mismatch")
+                _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("cfm_b200: " + lib().cfm_last_error().decode("utf-8", "replace"))
+
+
+def init(device_index):
+    if device_index not in _inited_devices:
+        check(lib().cfm_init(int(device_index)))
+        _inited_devices.add(device_index)
+
+
+def launch_count():
+    return int(lib().cfm_launch_count())

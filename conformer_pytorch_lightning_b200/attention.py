@@ -1,0 +1,132 @@
+"""Drop-in for the reference's src/attention.py: positional-encoding tables and the two
+multi-head self-attention modules, executed by the native QKV GEMM + flash-attention kernels."""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import engine
+
+
+def _sincos_table(max_len, d_model):
+    # attention.py:12-16 / 111-115 of the reference: interleaved sin/cos, no sqrt(d) scaling
+    pos = torch.arange(max_len).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, 1, d_model)
+    pe[:, 0, 0::2] = torch.sin(pos * div)
+    pe[:, 0, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class _PositionTable(nn.Module):
+    """The reference keeps ``pe`` as a plain attribute and re-casts it *in place* to the dtype of
+    every input, so one bf16 call permanently degrades the table.  Here the fp32
+    master table is immutable and per-(device,dtype) casts are cached."""
+
+    def __init__(self, d_model, dropout, max_len, table_dtype):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        self.pe = _sincos_table(max_len, d_model).to(table_dtype)
+        self._cast = {}
+
+    def _table(self, like):
+        key = (like.device, like.dtype)
+        t = self._cast.get(key)
+        if t is None:
+            t = self._cast[key] = self.pe.to(like.device).to(like.dtype)
+        return t
+
+    def position_encoding(self, offset, size, apply_dropout=True):
+        ref = getattr(self, "_last_like", self.pe)
+        pos_embed = self._table(ref)[offset: offset + size]
+        if apply_dropout:
+            pos_embed = self.dropout(pos_embed)
+        return pos_embed
+
+
+class RelativePositionalEncoding(_PositionTable):
+    """attention.py:6-29.  NB: the table is sliced by ``inputs.size(0)`` = batch size."""
+
+    def __init__(self, d_model, dropout, max_len=5000):
+        super().__init__(d_model, dropout, max_len, torch.float32)
+
+    def forward(self, inputs, offset=0):
+        self._last_like = inputs
+        pos_embed = self.position_encoding(offset, inputs.size(0), False)
+        return self.dropout(inputs), self.dropout(pos_embed)
+
+
+class PositionalEncoding(_PositionTable):
+    """attention.py:105-127: absolute variant; the reference builds this table in float16."""
+
+    def __init__(self, d_model, dropout, max_len=5000):
+        super().__init__(d_model, dropout, max_len, torch.float16)
+
+    def forward(self, inputs, offset=0):
+        self._last_like = inputs
+        pos_embed = self.position_encoding(offset, inputs.size(0), False)
+        x = inputs + pos_embed
+        return self.dropout(x), self.dropout(pos_embed)
+
+
+class _MHSABase(nn.Module):
+    def _run(self, query, key, value, inputs_attn_mask, pos_embed, cache, out_dropout):
+        if key is not query or value is not query:
+            if not (torch.equal(key, query) and torch.equal(value, query)):
+                raise NotImplementedError("native attention implements self-attention (query is key is value), "
+                                          "the only way the reference encoder calls it (encoder_layer.py:60)")
+        engine.check_inference_only(self, self.dropout.p)
+        dtype = engine.resolve_dtype(self)
+        B, T, d = query.shape
+        y = query.reshape(B * T, d).to(dtype).contiguous()
+        x = torch.zeros((B * T, d), dtype=torch.float32, device=y.device)
+        new_cache = engine.mhsa_into(x, y, B, T, self.num_heads, self.derived_weights(dtype), inputs_attn_mask,
+                                     pos_embed, cache, True, engine.thread_workspace())
+        return x.view(B, T, d).to(query.dtype), new_cache.to(query.dtype)
+
+    def derived_weights(self, dtype):
+        return self._derived.get(self, dtype, lambda dt: engine.mhsa_weights(self, dt))
+
+
+class RelativeMultiHeadSelfAttentionModule(_MHSABase):
+    """attention.py:34-100.  matrix_ac + matrix_bd without rel_shift:
+    (q+u).k_j + (q+v).p_j = (q+u).(k_j+p_j) + (v-u).p_j, i.e. flash attention over shifted keys plus a
+    per-key bias; with one position row per batch element (batched forward, D2) the bd term is
+    constant along keys and drops out of the softmax."""
+
+    def __init__(self, encoder_dim, num_heads, dropout):
+        super().__init__()
+        self.d_k = encoder_dim // num_heads
+        self.num_heads = num_heads
+        self.linear_pos = nn.Linear(encoder_dim, encoder_dim, bias=False)
+        self.linear_k = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_q = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_v = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_out = nn.Linear(encoder_dim, encoder_dim)
+        self.pos_bias_u = nn.Parameter(torch.Tensor(self.num_heads, self.d_k))
+        self.pos_bias_v = nn.Parameter(torch.Tensor(self.num_heads, self.d_k))
+        self.dropout = nn.Dropout(dropout)
+        nn.init.xavier_uniform_(self.pos_bias_u)
+        nn.init.xavier_uniform_(self.pos_bias_v)
+        self._derived = engine.Derived()
+
+    def forward(self, query, key, value, inputs_attn_mask, pos_embed=None, cache=torch.zeros((0, 0, 0, 0))):
+        return self._run(query, key, value, inputs_attn_mask, pos_embed, cache, False)
+
+
+class MultiHeadSelfAttentionModule(_MHSABase):
+    """attention.py:130-179 (use_relative=False)."""
+
+    def __init__(self, encoder_dim, num_heads, dropout):
+        super().__init__()
+        self.d_k = encoder_dim // num_heads
+        self.num_heads = num_heads
+        self.linear_k = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_q = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_v = nn.Linear(encoder_dim, encoder_dim)
+        self.linear_out = nn.Linear(encoder_dim, encoder_dim)
+        self.dropout = nn.Dropout(dropout)
+        self._derived = engine.Derived()
+
+    def forward(self, query, key, value, inputs_attn_mask, pos_embed=None, cache=torch.zeros((0, 0, 0, 0))):
+        return self._run(query, key, value, inputs_attn_mask, None, cache, True)

@@ -1,0 +1,63 @@
+"""Drop-in for the reference's src/convolution.py."""
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+
+
+class ConvolutionModule(nn.Module):
+    """convolution.py:5-49: pointwise conv -> GLU -> depthwise conv -> BatchNorm -> SiLU -> pointwise
+    conv with the padding mask applied before and after.  Native execution: GEMM+GLU epilogue,
+    one memory-bound depthwise+BN(folded)+SiLU kernel, GEMM+mask epilogue.  ``bias`` receives
+    ``hidden_dim`` from the reference's layer constructor -> any truthy value."""
+
+    def __init__(self, input_dim, kernel_size, bias=True):
+        super().__init__()
+        bias = bool(bias)
+        self.pointwise_conv1 = nn.Conv1d(input_dim, input_dim * 2, kernel_size=1, stride=1, padding=0, bias=bias)
+        self.glu = nn.GLU(dim=1)
+        self.depthwise_conv = nn.Conv1d(input_dim, input_dim, kernel_size, stride=1, padding=(kernel_size - 1) // 2,
+                                        groups=input_dim, bias=bias)
+        self.norm = nn.BatchNorm1d(input_dim)
+        self.activation = nn.SiLU()
+        self.pointwise_conv2 = nn.Conv1d(input_dim, input_dim, kernel_size=1, stride=1, padding=0)
+        self._derived = engine.Derived()
+
+    def derived_weights(self, dtype):
+        return self._derived.get(self, dtype, lambda dt: engine.conv_weights(self, dt))
+
+    def forward(self, inputs, inputs_pad_mask, cache=torch.zeros((0, 0, 0, 0))):
+        engine.check_inference_only(self, 0.0)
+        dtype = engine.resolve_dtype(self)
+        B, T, d = inputs.shape
+        row_valid = engine._row_valid(inputs_pad_mask, B, T)
+        y = inputs.reshape(B * T, d)
+        if row_valid is not None:
+            y = y * row_valid.view(-1, 1).to(y.dtype)            # convolution.py:36-37
+        y = y.to(dtype).contiguous()
+        x = torch.zeros((B * T, d), dtype=torch.float32, device=y.device)
+        engine.conv_into(x, y, B, T, self.derived_weights(dtype), row_valid, self, engine.thread_workspace())
+        new_cache = torch.zeros((0, 0, 0), dtype=inputs.dtype, device=inputs.device)   # convolution.py:39 (stub)
+        return x.view(B, T, d).to(inputs.dtype), new_cache
+
+
+class ConvolutionSubSampling(nn.Module):
+    """convolution.py:52-79: Conv2d x2 (stride 2) + Linear + positional encoding.  Stays in PyTorch,
+    outside the measured path (BASELINE.json north_star); part of the state_dict contract."""
+
+    def __init__(self, input_dim, output_dim, pos_enc):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(1, output_dim, 3, 2), nn.ReLU(),
+                                  nn.Conv2d(output_dim, output_dim, 3, 2), nn.ReLU())
+        self.out = nn.Sequential(nn.Linear(output_dim * (((input_dim - 1) // 2 - 1) // 2), output_dim))
+        self.pos_enc = pos_enc
+
+    def forward(self, inputs, inputs_pad_mask, offset=0):
+        outputs = self.conv(inputs.unsqueeze(1))
+        b, c, t, f = outputs.size()
+        outputs = self.out(outputs.transpose(1, 2).contiguous().view(b, t, c * f))
+        outputs, pos_embed = self.pos_enc(outputs, offset)
+        return outputs, pos_embed, inputs_pad_mask[:, :, 2::2][:, :, 2::2]
+
+    def position_encoding(self, offset, size):
+        return self.pos_enc.position_encoding(offset, size)

@@ -1,0 +1,80 @@
+// C-ABI surface of libcfm_b200.so: argument validation, engine dispatch, error reporting.
+#include "cfm_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace cfm {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace cfm
+
+extern "C" int cfm_abi_version(void) { return CFM_ABI_VERSION; }
+extern "C" const char* cfm_last_error(void) { return cfm::g_err; }
+extern "C" int64_t cfm_launch_count(void) { return cfm::g_launches.load(); }
+
+extern "C" int cfm_init(int device) {
+  using namespace cfm;
+  CFM_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CFM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  CFM_CHECK_ARG(prop.major == 10, "cfm_init: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  int rc = gemm_tc_init();
+  if (rc != 0) return rc;
+  return attention_tc_init();
+}
+
+extern "C" int cfm_gemm(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N,
+                        int K, int dtype, int epilogue, const float* residual, float alpha,
+                        const uint8_t* row_valid, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(A && W && C, "cfm_gemm: null A/W/C");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_gemm: bad dtype %d", dtype);
+  CFM_CHECK_ARG(epilogue >= CFM_EPI_BIAS && epilogue <= CFM_EPI_RESIDUAL, "cfm_gemm: bad epilogue %d", epilogue);
+  CFM_CHECK_ARG(epilogue != CFM_EPI_RESIDUAL || residual != nullptr, "cfm_gemm: EPI_RESIDUAL needs residual");
+  CFM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lda >= K && ldc >= N, "cfm_gemm: bad shape M=%d N=%d K=%d lda=%d ldc=%d",
+                M, N, K, lda, ldc);
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = gemm_tc_supported(lda, ldc, M, N, K, dtype, epilogue);
+  if (engine == CFM_ENGINE_TC) {
+    CFM_CHECK_ARG(tc_ok, "cfm_gemm: tcgen05 engine does not support M=%d N=%d K=%d dtype=%d epi=%d", M, N, K, dtype,
+                  epilogue);
+    return gemm_tc(A, lda, W, bias, C, ldc, M, N, K, dtype, epilogue, residual, alpha, row_valid, st);
+  }
+  if (engine == CFM_ENGINE_AUTO && tc_ok)
+    return gemm_tc(A, lda, W, bias, C, ldc, M, N, K, dtype, epilogue, residual, alpha, row_valid, st);
+  return gemm_simt(A, lda, W, bias, C, ldc, M, N, K, dtype, epilogue, residual, alpha, row_valid, st);
+}
+
+extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
+                             const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
+                             const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,
+                             float scale, int dtype, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(q && k && v && out, "cfm_attention: null q/k/v/out");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_attention: bad dtype %d", dtype);
+  CFM_CHECK_ARG(B >= 0 && H > 0 && Tq >= 0 && Tk >= 0, "cfm_attention: bad shape");
+  if (B == 0 || Tq == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = attention_tc_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, dtype);
+  if (engine == CFM_ENGINE_TC) {
+    CFM_CHECK_ARG(tc_ok, "cfm_attention: tcgen05 engine does not support this shape/dtype");
+    return attention_tc(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
+                        key_bias, scale, dtype, st);
+  }
+  if (engine == CFM_ENGINE_AUTO && tc_ok)
+    return attention_tc(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
+                        key_bias, scale, dtype, st);
+  return attention_simt(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
+                        key_bias, scale, dtype, st);
+}

@@ -1,0 +1,138 @@
+// Shared device/host helpers for the cfm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/cfm_b200.h"
+
+namespace cfm {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define CFM_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::cfm::set_error(__VA_ARGS__);             \
+      return -1;                                 \
+    }                                            \
+  } while (0)
+
+#define CFM_CUDA_OK(expr)                                                            \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::cfm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                       __FILE__, __LINE__);                                          \
+      return -2;                                                                     \
+    }                                                                                \
+  } while (0)
+
+// every kernel launch goes through this so that bench.py can report `gpu_launches`
+#define CFM_LAUNCHED()                                  \
+  do {                                                  \
+    ::cfm::g_launches.fetch_add(1);                     \
+    CFM_CUDA_OK(cudaPeekAtLastError());                 \
+  } while (0)
+
+// ---------------------------------------------------------------- dtype helpers
+template <typename T> struct Act;
+template <> struct Act<float> {
+  static constexpr int kId = CFM_F32;
+  static constexpr int kVec = 4;  // elements per 16 bytes
+};
+template <> struct Act<__nv_bfloat16> {
+  static constexpr int kId = CFM_BF16;
+  static constexpr int kVec = 8;
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// exact-ish activations for the fp32 path (match ATen's expf-based SiLU / sigmoid to ~1 ulp)
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// fast variants for the bf16 path: one MUFU (tanh.approx) per element; rel. error ~2^-11,
+// far below bf16's 2^-9 output rounding.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ float silu_fast(float x) {
+  float h = 0.5f * x;
+  return fmaf(h, tanh_fast(h), h);
+}
+
+template <typename T> __device__ __forceinline__ float act_silu(float x);
+template <> __device__ __forceinline__ float act_silu<float>(float x) { return silu_f(x); }
+template <> __device__ __forceinline__ float act_silu<__nv_bfloat16>(float x) { return silu_fast(x); }
+template <typename T> __device__ __forceinline__ float act_sigmoid(float x);
+template <> __device__ __forceinline__ float act_sigmoid<float>(float x) { return sigmoid_f(x); }
+template <> __device__ __forceinline__ float act_sigmoid<__nv_bfloat16>(float x) { return sigmoid_fast(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------- engine entry points (defined per .cu)
+int gemm_simt(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N,
+              int K, int dtype, int epilogue, const float* residual, float alpha,
+              const uint8_t* row_valid, cudaStream_t st);
+// returns 1 when the shape/dtype is handled by the tcgen05 kernel
+bool gemm_tc_supported(int lda, int ldc, int M, int N, int K, int dtype, int epilogue);
+int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N,
+            int K, int dtype, int epilogue, const float* residual, float alpha,
+            const uint8_t* row_valid, cudaStream_t st);
+int gemm_tc_init();
+
+int attention_simt(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
+                   const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
+                   const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,
+                   float scale, int dtype, cudaStream_t st);
+bool attention_tc_supported(int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
+                            int64_t v_ts, int B, int H, int Tq, int Tk, int dtype);
+int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
+                 const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
+                 const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,
+                 float scale, int dtype, cudaStream_t st);
+int attention_tc_init();
+
+}  // namespace cfm

@@ -1,0 +1,115 @@
+"""Drop-in for the reference's src/encoder.py (ConformerEncoder, :9-153)."""
+import torch
+import torch.nn as nn
+
+from . import engine
+from .attention import PositionalEncoding, RelativePositionalEncoding
+from .convolution import ConvolutionSubSampling
+from .encoder_layer import ConformerEncoderLayer
+from .utils import make_attn_mask, make_pad_mask
+
+
+class ConformerEncoder(nn.Module):
+    """Same constructor arguments, forward / forward_chunk / forward_chunk_by_chunk signatures,
+    return tuples and state_dict layout as the reference; the layer stack + after_norm
+    (encoder.py:72-74) run as native sm_100a kernels.  CMVN, Conv2d sub-sampling and mask
+    construction stay in PyTorch (outside the measured path)."""
+
+    def __init__(self, input_dim, kernel_size, encoder_dim, dropout, attention_dropout, pos_enc_dropout,
+                 hidden_dim, num_heads, encoder_num_layers, cmvn=None, max_len=5000, use_relative=False,
+                 use_dynamic_chunk_size=False, use_dynamic_left_chunk=False, static_chunk_size=-1):
+        super().__init__()
+        pos_cls = RelativePositionalEncoding if use_relative else PositionalEncoding
+        self.position_encoding = pos_cls(encoder_dim, pos_enc_dropout, max_len)
+        self.embed = ConvolutionSubSampling(input_dim=input_dim, output_dim=encoder_dim,
+                                            pos_enc=self.position_encoding)
+        self.encoders = nn.ModuleList([
+            ConformerEncoderLayer(encoder_dim, kernel_size, dropout, attention_dropout, hidden_dim, num_heads,
+                                  use_relative) for _ in range(encoder_num_layers)])
+        self.encoder_dim = encoder_dim
+        self.after_norm = nn.LayerNorm(encoder_dim, eps=1e-5)
+        self.global_cmvn = cmvn
+        self.use_dynamic_chunk_size = use_dynamic_chunk_size
+        self.use_dynamic_left_chunk = use_dynamic_left_chunk
+        self.static_chunk_size = static_chunk_size
+        self.compute_dtype = None
+
+    # ------------------------------------------------------------------ B200-specific knobs
+    def set_compute_dtype(self, dtype):
+        """torch.float32 (default, exact-parity path) or torch.bfloat16 (tcgen05 path).  Parameters and
+        the state_dict stay fp32 either way; ``None`` follows torch.autocast."""
+        if dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("compute dtype must be torch.float32, torch.bfloat16 or None")
+        for m in self.modules():
+            m.compute_dtype = dtype
+        return self
+
+    def encode_layers(self, outputs, inputs_attn_mask, pos_embed, inputs_pad_mask):
+        """The measured path: layer loop + after_norm (encoder.py:72-74)."""
+        engine.check_inference_only(self, self._max_dropout())
+        out, _ = engine.run_layers(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask, pos_embed,
+                                   inputs_pad_mask, None, False, engine.resolve_dtype(self))
+        return out
+
+    def _max_dropout(self):
+        return max([m.p for m in self.modules() if isinstance(m, nn.Dropout)] + [0.0])
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, inputs, input_lengths, decoding_chunk_size=0, num_decoding_chunk_size=-1):
+        if self.global_cmvn is not None:
+            inputs = self.global_cmvn(inputs)
+        max_seq_len = inputs.size(1)
+        inputs_pad_mask = ~make_pad_mask(input_lengths, max_seq_len).unsqueeze(1)
+        outputs, pos_embed, inputs_pad_mask = self.embed(inputs, inputs_pad_mask)
+        inputs_attn_mask = make_attn_mask(outputs, inputs_pad_mask, self.use_dynamic_chunk_size,
+                                          self.use_dynamic_left_chunk, decoding_chunk_size, self.static_chunk_size,
+                                          num_decoding_chunk_size)
+        out = self.encode_layers(outputs, inputs_attn_mask, pos_embed, inputs_pad_mask)
+        return out.to(outputs.dtype), inputs_pad_mask
+
+    def forward_chunk(self, inputs, offset, required_cache_size, attn_cache, cnn_cache,
+                      inputs_attn_mask=torch.ones((0, 0, 0))):
+        attn_cache = attn_cache.to(inputs.device)
+        cnn_cache = cnn_cache.to(inputs.device)
+        tmp_masks = torch.ones(1, inputs.size(1), device=inputs.device, dtype=torch.bool).unsqueeze(1)
+        if self.global_cmvn is not None:
+            inputs = self.global_cmvn(inputs)
+        outputs, pos_embed, _ = self.embed(inputs, tmp_masks, offset)
+        num_layers, cache_size = attn_cache.size(0), attn_cache.size(2)
+        chunk_size = outputs.size(1)
+        attention_key_size = cache_size + chunk_size
+        pos_embed = self.embed.position_encoding(offset=offset - cache_size, size=attention_key_size)
+        if required_cache_size < 0:
+            next_cache_start = 0
+        elif required_cache_size == 0:
+            next_cache_start = attention_key_size
+        else:
+            next_cache_start = max(attention_key_size - required_cache_size, 0)
+        engine.check_inference_only(self, self._max_dropout())
+        caches = [attn_cache[i:i + 1] for i in range(len(self.encoders))] if num_layers > 0 else None
+        out, new_caches = engine.run_layers(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask,
+                                            pos_embed, None, caches, True, engine.resolve_dtype(self))
+        r_attn_cache = torch.cat([c[:, :, next_cache_start:, :] for c in new_caches], dim=0).to(outputs.dtype)
+        r_cnn_cache = torch.zeros((len(self.encoders), 0, 0, 0), dtype=outputs.dtype, device=outputs.device)
+        return out.to(outputs.dtype), r_attn_cache, r_cnn_cache
+
+    def forward_chunk_by_chunk(self, inputs, decoding_chunk_size, num_decoding_left_chunks=-1):
+        subsampling_rate, context = 4, 7
+        stride = subsampling_rate * decoding_chunk_size
+        decoding_window = (decoding_chunk_size - 1) * subsampling_rate + context
+        num_frames = inputs.size(1)
+        attn_cache = torch.zeros((0, 0, 0, 0), device=inputs.device)
+        cnn_cache = torch.zeros((0, 0, 0, 0), device=inputs.device)
+        outputs = []
+        offset = 0
+        required_cache_size = decoding_chunk_size * num_decoding_left_chunks
+        for cur in range(0, num_frames - context + 1, stride):
+            end = min(cur + decoding_window, num_frames)
+            chunk_outputs, attn_cache, cnn_cache = self.forward_chunk(
+                inputs=inputs[:, cur:end, :], offset=offset, required_cache_size=required_cache_size,
+                attn_cache=attn_cache, cnn_cache=cnn_cache)
+            outputs.append(chunk_outputs)
+            offset += chunk_outputs.size(1)
+        outputs = torch.cat(outputs, 1)
+        masks = torch.ones((1, 1, outputs.size(1)))
+        return outputs, masks

@@ -1,0 +1,296 @@
+"""Kernel chains of the Conformer encoder layer on top of the C-ABI ops.
+
+This is the host-side schedule of the hot path (reference: encoder_layer.py:49-71 and the
+modules it calls).  All tensors handled here are 2-D ``(N = B*T, channels)`` row-major
+device buffers; the residual stream ``x`` is fp32 and is updated *in place* by GEMM
+epilogues, GEMM operands are in the compute dtype (fp32 or bf16).  Per layer the
+schedule is 15 native launches:
+
+    LN | W1+SiLU | W2+0.5*res | LN | QKV | flash-attn | Wo+res | LN+mask | PW1+GLU |
+    dwconv+BN+SiLU | PW2+mask+res | LN | W1+SiLU | W2+0.5*res | LN_final(+LN of next layer)
+
+Derived weights (bf16 copies, fused QKV with pos_bias_u folded into the q bias, the
+BatchNorm-folded depthwise filter) are caches keyed on parameter versions; the
+``state_dict`` keeps the reference layout untouched.
+"""
+from __future__ import annotations
+
+import math
+import threading
+
+import torch
+
+from . import _native as N
+from . import ops
+
+_LN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------- compute dtype
+def resolve_dtype(module):
+    """fp32 unless the module was switched with ``set_compute_dtype`` or bf16 autocast is on."""
+    dt = getattr(module, "compute_dtype", None)
+    if dt is None and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        dt = torch.bfloat16
+    return dt or torch.float32
+
+
+def check_inference_only(module, dropout_p):
+    """Round-1 scope: forward kernels only.  Eval always runs; training-mode forward (BatchNorm batch
+    statistics) runs under torch.no_grad() when all dropouts are 0; autograd is not wired yet."""
+    if module.training:
+        if dropout_p > 0.0:
+            raise NotImplementedError("native training-mode dropout is not implemented; set dropouts to 0 or call eval()")
+        if torch.is_grad_enabled():
+            raise NotImplementedError("backward kernels are not implemented yet: call under torch.no_grad()")
+
+
+# --------------------------------------------------------------------------- workspace
+class Workspace:
+    """Named scratch buffers, re-used across calls on the same thread (no hidden allocation
+    inside the native ops; the buffers live in PyTorch's caching allocator)."""
+
+    def __init__(self):
+        self._t = {}
+
+    def get(self, name, shape, dtype, device):
+        key = (name, tuple(shape), dtype, device)
+        t = self._t.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._t[key] = t
+        return t
+
+
+_tls = threading.local()
+
+
+def thread_workspace():
+    ws = getattr(_tls, "ws", None)
+    if ws is None:
+        ws = _tls.ws = Workspace()
+    return ws
+
+
+# --------------------------------------------------------------------------- derived weights
+class Derived:
+    """Cache of tensors derived from a module's parameters.  Rebuilt (in place when shapes
+    allow, so captured CUDA graphs stay valid) whenever a parameter version, storage,
+    the training flag or the compute dtype changes."""
+
+    def __init__(self):
+        self.key = None
+        self.t = None
+
+    def get(self, module, dtype, build):
+        tensors = list(module.parameters(recurse=True)) + list(module.buffers(recurse=True))
+        key = (dtype, module.training) + tuple((p.data_ptr(), p._version) for p in tensors)
+        if key != self.key:
+            with torch.no_grad():
+                new = build(dtype)
+            old = self.t
+            if old is not None and old.keys() == new.keys() and all(
+                    old[k].shape == new[k].shape and old[k].dtype == new[k].dtype and old[k].device == new[k].device
+                    for k in new):
+                for k in new:
+                    if old[k].data_ptr() != new[k].data_ptr():
+                        old[k].copy_(new[k])
+            else:
+                self.t = new
+            self.key = key
+        return self.t
+
+
+def _act(w, dtype):
+    w = w.detach()
+    return w.contiguous() if w.dtype == dtype else w.to(dtype).contiguous()
+
+
+def _f32(w):
+    return w.detach().float().contiguous()
+
+
+def ffn_weights(m, dtype):
+    return {"w1": _act(m.w_1.weight, dtype), "b1": _f32(m.w_1.bias),
+            "w2": _act(m.w_2.weight, dtype), "b2": _f32(m.w_2.bias)}
+
+
+def mhsa_weights(m, dtype):
+    rel = hasattr(m, "pos_bias_u")
+    bq = m.linear_q.bias.detach().float()
+    if rel:
+        bq = bq + m.pos_bias_u.detach().float().reshape(-1)     # (q + u) folded into the q bias
+    d = {"wqkv": _act(torch.cat([m.linear_q.weight, m.linear_k.weight, m.linear_v.weight], 0), dtype),
+         "bqkv": torch.cat([bq, m.linear_k.bias.detach().float(), m.linear_v.bias.detach().float()]).contiguous(),
+         "wo": _act(m.linear_out.weight, dtype), "bo": _f32(m.linear_out.bias)}
+    if rel:
+        d["wpos"] = _act(m.linear_pos.weight, dtype)
+        d["u"] = _f32(m.pos_bias_u)
+        d["vb"] = _f32(m.pos_bias_v)
+    return d
+
+
+def conv_weights(m, dtype):
+    dd = m.pointwise_conv2.weight.shape[0]
+    k = m.depthwise_conv.weight.shape[-1]
+    w1 = m.pointwise_conv1.weight.detach().reshape(2 * dd, dd)
+    b1 = m.pointwise_conv1.bias
+    b1 = _f32(b1) if b1 is not None else torch.zeros(2 * dd, device=w1.device)
+    dw = m.depthwise_conv.weight.detach().float().reshape(dd, k)
+    db = m.depthwise_conv.bias
+    db = db.detach().float() if db is not None else torch.zeros(dd, device=w1.device)
+    if not m.training:
+        # eval: fold BatchNorm running statistics + conv bias (convolution.py:43-44)
+        scale = m.norm.weight.detach().float() * torch.rsqrt(m.norm.running_var.float() + m.norm.eps)
+        dw = dw * scale[:, None]
+        db = (db - m.norm.running_mean.float()) * scale + m.norm.bias.detach().float()
+    return {"w1": _act(w1, dtype), "b1": b1, "dw_w": dw.t().contiguous(), "dw_b": db.contiguous(),
+            "w2": _act(m.pointwise_conv2.weight.detach().reshape(dd, dd), dtype), "b2": _f32(m.pointwise_conv2.bias),
+            "gamma": _f32(m.norm.weight), "beta": _f32(m.norm.bias)}
+
+
+# --------------------------------------------------------------------------- module chains
+def ffn_into(x, y, W, alpha, ws):
+    """x += alpha * (w_2 silu(w_1 y + b1) + b2)   (feedforward.py:16-21 + encoder_layer.py:58,69)."""
+    n = y.shape[0]
+    h = ws.get("ffn_h", (n, W["w1"].shape[0]), y.dtype, y.device)
+    ops.gemm(y, W["w1"], W["b1"], h, N.EPI_BIAS_SILU)
+    ops.gemm(h, W["w2"], W["b2"], x, N.EPI_RESIDUAL, residual=x, alpha=alpha)
+
+
+def _mask_u8(mask):
+    """Reference semantics are ``mask.eq(0)`` on any dtype (attention.py:90)."""
+    if mask is None or mask.dim() != 3 or mask.size(2) == 0:
+        return None
+    if mask.dtype not in (torch.bool, torch.uint8):
+        mask = mask != 0
+    if mask.stride(2) != 1:
+        mask = mask.contiguous()
+    return mask
+
+
+def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws):
+    """x += linear_out(attn(...))  (attention.py:54-100 / 148-179 + encoder_layer.py:60-62).
+    Returns new_cache (B,H,Tk,128) fp32 when want_cache else None."""
+    n, d = y.shape
+    dev, dt = y.device, y.dtype
+    qkv = ws.get("qkv", (n, 3 * d), dt, dev)
+    ops.gemm(y, W["wqkv"], W["bqkv"], qkv, N.EPI_BIAS)
+    q5 = qkv.view(B, T, 3, H, 64)
+    q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
+    if cache is not None and cache.dim() == 4 and cache.size(0) > 0:
+        # caller-held streaming cache (B,H,C,2*dk) (attention.py:70-74): PyTorch plumbing, tiny tensors
+        kc = cache[..., :64].permute(0, 2, 1, 3).to(dt)
+        vc = cache[..., 64:].permute(0, 2, 1, 3).to(dt)
+        k = torch.cat([kc, k], dim=1)
+        v = torch.cat([vc, v], dim=1)
+    Tk = k.shape[1]
+    new_cache = None
+    if want_cache:
+        new_cache = torch.cat([k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)], dim=-1).float()
+    key_bias = None
+    k_use = k
+    if "wpos" in W and pos_embed is not None:
+        rows = pos_embed.numel() // d
+        if rows % B != 0:
+            raise RuntimeError(f"pos_embed with {rows} rows cannot be viewed as (B={B}, -1, H, d_k)")
+        P = rows // B
+        if P == Tk and Tk > 1:
+            # streaming position term: fold into keys + per-key bias
+            pe = pos_embed.reshape(rows, d).to(dt).contiguous()
+            p = ws.get("pos_p", (rows, d), dt, dev)
+            ops.gemm(pe, W["wpos"], None, p, N.EPI_BIAS)
+            k_use = ws.get("k_fold", (B, Tk, H, 64), dt, dev)
+            key_bias = ws.get("key_bias", (B, H, Tk), torch.float32, dev)
+            ops.relpos_keys(k, p.view(B, P, d), W["u"], W["vb"], k_use, key_bias)
+        elif P != 1:
+            raise RuntimeError(f"pos_embed gives {P} position rows per batch element; expected 1 or Tk={Tk}")
+        # P == 1 (batched forward): matrix_bd is constant along keys -> softmax-invariant
+    ctx = ws.get("attn_ctx", (n, d), dt, dev)
+    ops.attention(q, k_use, v, ctx.view(B, T, d), mask=_mask_u8(attn_mask), key_bias=key_bias,
+                  scale=1.0 / math.sqrt(64.0))
+    ops.gemm(ctx, W["wo"], W["bo"], x, N.EPI_RESIDUAL, residual=x, alpha=1.0)
+    return new_cache
+
+
+def conv_into(x, y, B, T, W, row_valid, module, ws):
+    """x += mask(pw2(silu(bn(dw(glu(pw1(y)))))))  (convolution.py:34-49 + encoder_layer.py:64-66).
+    ``y`` must already be zeroed on padded rows (done by the LayerNorm kernel's row mask)."""
+    n, d = y.shape
+    dev, dt = y.device, y.dtype
+    g = ws.get("conv_glu", (n, d), dt, dev)
+    ops.gemm(y, W["w1"], W["b1"], g, N.EPI_BIAS_GLU)
+    c = ws.get("conv_dw", (n, d), dt, dev)
+    if not module.training:
+        ops.dwconv(g.view(B, T, d), W["dw_w"], W["dw_b"], c.view(B, T, d), apply_silu=True)
+    else:
+        # BatchNorm batch statistics over all B*T rows, unmasked (convolution.py:44) + running update
+        raw = ws.get("conv_raw", (n, d), torch.float32, dev)
+        ops.dwconv(g.view(B, T, d), W["dw_w"], W["dw_b"], raw.view(B, T, d), apply_silu=False)
+        st = ws.get("bn_st", (2, d), torch.float32, dev)
+        st.zero_()
+        ops.bn_stats(raw, st[0], st[1])
+        mean = st[0] / n
+        var = (st[1] / n - mean * mean).clamp_min_(0.0)
+        bn = module.norm
+        with torch.no_grad():
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+            bn.num_batches_tracked += 1
+        ops.bn_apply_silu(raw, mean.contiguous(), torch.rsqrt(var + bn.eps).contiguous(), W["gamma"], W["beta"], c)
+    ops.gemm(c, W["w2"], W["b2"], x, N.EPI_RESIDUAL, residual=x, alpha=1.0, row_valid=row_valid)
+
+
+def _row_valid(pad_mask, B, T):
+    if pad_mask is None or pad_mask.dim() != 3 or pad_mask.size(2) == 0:
+        return None
+    m = pad_mask
+    if m.dtype not in (torch.bool, torch.uint8):
+        m = m != 0
+    m = m.expand(B, 1, T).contiguous()
+    return m.view(B * T)
+
+
+def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_caches, want_cache, dtype):
+    """Layer loop of encoder.py:72-74 / 109-118.
+
+    inputs (B,T,d) fp32 (not modified); layers: list of ConformerEncoderLayer; after_norm: LayerNorm
+    module or None; attn_caches: list (one per layer) of (B,H,C,128) tensors or None.
+    Returns (out (B,T,d) fp32 fresh tensor, [new caches])."""
+    B, T, d = inputs.shape
+    n = B * T
+    dev = inputs.device
+    ws = thread_workspace()
+    x = torch.empty((n, d), dtype=torch.float32, device=dev)
+    x.copy_(inputs.reshape(n, d))
+    y = ws.get("ln_y", (n, d), dtype, dev)
+    row_valid = _row_valid(pad_mask, B, T)
+    new_caches = []
+    out = x
+    for i, layer in enumerate(layers):
+        Wl = layer.derived_weights(dtype)
+        H = layer.self_attn.num_heads
+        if i == 0:
+            ops.layernorm(x, Wl["ffm_g"], Wl["ffm_b"], y=y)
+        ffn_into(x, y, Wl["ffm"], 0.5, ws)
+        ops.layernorm(x, Wl["mha_g"], Wl["mha_b"], y=y)
+        cache = attn_caches[i] if attn_caches is not None else None
+        new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws))
+        ops.layernorm(x, Wl["conv_g"], Wl["conv_b"], y=y, row_valid=row_valid)
+        conv_into(x, y, B, T, Wl["conv"], row_valid, layer.conv_module, ws)
+        ops.layernorm(x, Wl["ff_g"], Wl["ff_b"], y=y)
+        ffn_into(x, y, Wl["ff"], 0.5, ws)
+        if i + 1 < len(layers):
+            Wn = layers[i + 1].derived_weights(dtype)
+            # norm_final of this layer chained with norm_ff_macaron of the next one
+            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x, g2=Wn["ffm_g"], b2=Wn["ffm_b"], y=y)
+        elif after_norm is not None:
+            out = torch.empty((n, d), dtype=torch.float32, device=dev)
+            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], g2=_f32(after_norm.weight), b2=_f32(after_norm.bias), y=out)
+        else:
+            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x)
+    if not layers and after_norm is not None:
+        out = torch.empty((n, d), dtype=torch.float32, device=dev)
+        ops.layernorm(x, _f32(after_norm.weight), _f32(after_norm.bias), y=out)
+    return out.view(B, T, d), new_caches

@@ -1,0 +1,127 @@
+"""Tensor-level wrappers over the C-ABI (include/cfm_b200.h).
+
+PyTorch is used here for device memory and streams only: every function marshals
+``data_ptr()``s and the *current* CUDA stream of the calling thread into one native
+call.  CPU tensors raise (there is no CPU path).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+_DT = {torch.float32: N.F32, torch.bfloat16: N.BF16}
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, name, dtype=None, contiguous=True):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the B200 Conformer kernels have no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def ensure_init(t):
+    N.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def layernorm(x, g1, b1, *, x_out=None, g2=None, b2=None, y=None, row_valid=None, eps=1e-5):
+    """t = LN(x;g1,b1); x_out = t; t = LN(t;g2,b2) if g2; y = rowmask(t).  x (rows,d) fp32."""
+    _req(x, "layernorm.x", torch.float32)
+    rows, d = x.shape
+    ensure_init(x)
+    if y is not None:
+        _req(y, "layernorm.y")
+    N.check(N.lib().cfm_layernorm(x.data_ptr(), rows, d, g1.data_ptr(), b1.data_ptr(), _ptr(x_out),
+                                  _ptr(g2), _ptr(b2), _ptr(y), _DT[y.dtype] if y is not None else N.F32,
+                                  _ptr(row_valid), float(eps), _stream(x)))
+    return y
+
+
+def gemm(a, w, bias, out, epilogue, *, residual=None, alpha=1.0, row_valid=None, engine=N.ENGINE_AUTO):
+    """out = epilogue(a @ w.T + bias); a (M,K) (row stride may exceed K), w (N or 2N, K)."""
+    _req(a, "gemm.a", contiguous=False)
+    _req(w, "gemm.w", a.dtype)
+    _req(out, "gemm.out", contiguous=False)
+    if a.stride(1) != 1 or out.stride(1) != 1:
+        raise RuntimeError("gemm: inner dimension must be contiguous")
+    M, K = a.shape
+    Nn = out.shape[1]
+    ensure_init(a)
+    N.check(N.lib().cfm_gemm(a.data_ptr(), a.stride(0), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(0),
+                             M, Nn, K, _DT[a.dtype], epilogue, _ptr(residual), float(alpha), _ptr(row_valid),
+                             engine, _stream(a)))
+    return out
+
+
+def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
+    """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
+    mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""
+    _req(q, "attention.q", contiguous=False)
+    B, Tq, H, dk = q.shape
+    Tk = k.shape[1]
+    if dk != 64:
+        raise RuntimeError(f"attention: head dim {dk} unsupported (kernels are specialised for d_k = 64)")
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if t.stride(3) != 1 or t.stride(2) != 64 or t.dtype != q.dtype:
+            raise RuntimeError(f"attention.{n}: need (H,64) contiguous tail and a common dtype")
+    _req(out, "attention.out", q.dtype)
+    mbs = mrs = 0
+    if mask is not None:
+        _req(mask, "attention.mask", contiguous=False)
+        if mask.dtype not in (torch.uint8, torch.bool) or mask.stride(2) != 1 or mask.shape[2] != Tk:
+            raise RuntimeError("attention.mask: need uint8/bool with contiguous key axis of length Tk")
+        mbs = 0 if mask.shape[0] == 1 else mask.stride(0)
+        mrs = 0 if mask.shape[1] == 1 else mask.stride(1)
+    ensure_init(q)
+    N.check(N.lib().cfm_attention(q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1),
+                                  v.data_ptr(), v.stride(0), v.stride(1), out.data_ptr(), B, H, Tq, Tk,
+                                  _ptr(mask), mbs, mrs, _ptr(key_bias), float(scale), _DT[q.dtype], engine,
+                                  _stream(q)))
+    return out
+
+
+def relpos_keys(k, p, u, vb, k_out, key_bias):
+    """k (B,Tk,H,64) view, p (Bp,Tk,H*64) contiguous with Bp in {1,B}; see cfm_relpos_keys."""
+    B, Tk, H, _ = k.shape
+    _req(p, "relpos_keys.p", k.dtype)
+    p_bs = 0 if p.shape[0] == 1 else p.stride(0)
+    ensure_init(k)
+    N.check(N.lib().cfm_relpos_keys(k.data_ptr(), k.stride(0), k.stride(1), p.data_ptr(), p_bs, u.data_ptr(),
+                                    vb.data_ptr(), k_out.data_ptr(), key_bias.data_ptr(), B, H, Tk, _DT[k.dtype],
+                                    _stream(k)))
+
+
+def dwconv(x, w, bias, y, *, apply_silu=True):
+    """x (B,T,d) act dtype contiguous; w (k,d) fp32; bias (d) fp32; y (B,T,d) (fp32 if not apply_silu)."""
+    _req(x, "dwconv.x")
+    _req(y, "dwconv.y")
+    B, T, d = x.shape
+    ensure_init(x)
+    N.check(N.lib().cfm_dwconv(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, T, d, w.shape[0],
+                               _DT[x.dtype], 1 if apply_silu else 0, _stream(x)))
+    return y
+
+
+def bn_stats(x, s, q):
+    _req(x, "bn_stats.x", torch.float32)
+    rows, d = x.shape
+    N.check(N.lib().cfm_bn_stats(x.data_ptr(), rows, d, s.data_ptr(), q.data_ptr(), _stream(x)))
+
+
+def bn_apply_silu(x, mean, rstd, gamma, beta, y):
+    _req(x, "bn_apply_silu.x", torch.float32)
+    rows, d = x.shape
+    N.check(N.lib().cfm_bn_apply_silu(x.data_ptr(), rows, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), y.data_ptr(), _DT[y.dtype], _stream(x)))
+    return y

@@ -1,0 +1,135 @@
+/*
+ * cfm_b200.h -- C-ABI of the B200-native (sm_100a) Conformer-encoder kernels.
+ *
+ * The reference (Lingeng56/conformer-pytorch-lightning) is pure Python/PyTorch and has
+ * no FFI of its own: its hot path is a chain of ATen calls made from
+ * src/encoder_layer.py:49-71.  This header is therefore the boundary *we* define; each
+ * entry point names the reference statements it replaces.  The host side that mirrors
+ * the reference's nn.Module surface (the .py files of conformer_pytorch_lightning_b200) binds these
+ * with ctypes -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; no torch types;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - no hidden allocations, no hidden synchronisation: callers own all buffers;
+ *   - return value 0 = success, negative = error; cfm_last_error() gives the text of the
+ *     last failure on the calling thread.  Nothing throws across the ABI;
+ *   - "act" tensors are row-major (rows = B*T tokens, cols = channels) in `dtype`
+ *     CFM_F32 or CFM_BF16; the residual stream, biases, LayerNorm/BatchNorm parameters and
+ *     all accumulation are always fp32.
+ */
+#ifndef CFM_B200_H_
+#define CFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFM_ABI_VERSION 1
+
+/* activation dtypes */
+#define CFM_F32  0
+#define CFM_BF16 1
+
+/* GEMM epilogues (cfm_gemm) */
+#define CFM_EPI_BIAS      0  /* C[act]  = A W^T + b                        nn.Linear (attention.py:62-64,78,99)      */
+#define CFM_EPI_BIAS_SILU 1  /* C[act]  = silu(A W^T + b)                  w_1 + SiLU (feedforward.py:17-18)          */
+#define CFM_EPI_BIAS_GLU  2  /* C[act]  = (A Wa^T + ba) * sigmoid(A Wb^T + bb), W = [Wa;Wb]
+                                                                           pointwise_conv1 + GLU (convolution.py:41-42) */
+#define CFM_EPI_RESIDUAL  3  /* X[f32]  = R + alpha * rowmask(A W^T + b)   w_2 / linear_out / pointwise_conv2 + the
+                                                                           residual adds of encoder_layer.py:58,62,66,69
+                                                                           and the masked_fill of convolution.py:47-48 */
+
+/* GEMM engines */
+#define CFM_ENGINE_AUTO 0    /* tcgen05 when dtype==BF16 and the shape is supported, else SIMT */
+#define CFM_ENGINE_SIMT 1    /* fp32-accumulating CUDA-core kernel (exact-order reference engine) */
+#define CFM_ENGINE_TC   2    /* tcgen05/TMEM/TMA kernel; error if unsupported */
+
+int         cfm_abi_version(void);
+const char* cfm_last_error(void);
+/* one-time per-process/device initialisation (function attributes, driver entry points). Host only. */
+int         cfm_init(int device);
+/* number of kernel launches issued through this library by the calling process (for bench `gpu_launches`) */
+int64_t     cfm_launch_count(void);
+
+/*
+ * LayerNorm (+ optional second LayerNorm, + optional row mask).  Replaces nn.LayerNorm calls
+ * encoder_layer.py:56,59,63,67,70 and encoder.py:74, and the first masked_fill of
+ * convolution.py:36-37 when `row_valid` is given.
+ *   t = LN(x; g1,b1);  if x_out: x_out = t (fp32);  if g2: t = LN(t; g2,b2);
+ *   if row_valid: t = row_valid[row] ? t : 0;  if y: y = cast<y_dtype>(t)
+ * x, x_out: (rows, d) fp32.  y: (rows, d) in y_dtype.  d % 128 == 0, d <= 1024.
+ */
+int cfm_layernorm(const float* x, int rows, int d,
+                  const float* g1, const float* b1, float* x_out,
+                  const float* g2, const float* b2,
+                  void* y, int y_dtype, const uint8_t* row_valid, float eps, void* stream);
+
+/*
+ * C = epilogue(A W^T + bias).  A: (M,K) act dtype, row stride lda elements.  W: (N,K) act dtype
+ * row-major (nn.Linear / 1x1-conv weight layout), for CFM_EPI_BIAS_GLU W is (2N,K) = [Wa;Wb]
+ * and bias has 2N entries.  bias fp32 or NULL.
+ *   EPI_BIAS / EPI_BIAS_SILU / EPI_BIAS_GLU : C (M,N) act dtype, row stride ldc.
+ *   EPI_RESIDUAL : C (M,N) fp32 = residual (M,N) fp32 (may alias C) + alpha * v, where
+ *                  v = (A W^T + bias), zeroed on rows with row_valid[row]==0 when row_valid != NULL.
+ */
+int cfm_gemm(const void* A, int lda, const void* W, const float* bias,
+             void* C, int ldc, int M, int N, int K, int dtype, int epilogue,
+             const float* residual, float alpha, const uint8_t* row_valid,
+             int engine, void* stream);
+
+/*
+ * Scaled-dot-product attention with the reference's mask semantics (attention.py:84-97,
+ * 160-174): scores = (q . k'_j + key_bias_j) * scale; positions whose mask byte is 0 get -inf,
+ * softmax over keys, masked probabilities forced to 0 (a fully masked row yields 0), then . v.
+ *   q: (B,Tq,H,64) act dtype with strides (q_bs, q_ts) in elements, head h at offset h*64
+ *   k,v: (B,Tk,H,64) likewise.   out: (B,Tq,H*64) act dtype, contiguous rows of H*64.
+ *   mask: uint8, NULL = no mask; element (b,i,j) at mask[b*mask_bs + i*mask_rs + j]
+ *         (mask_rs = 0 broadcasts one key row over all queries, i.e. the (B,1,Tk) pad mask).
+ *   key_bias: fp32 (B,H,Tk) or NULL  (streaming position term, see cfm_relpos_keys).
+ * Head dim is 64 (d/H for both Conformer-M and -L).
+ */
+int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts,
+                  const void* k, int64_t k_bs, int64_t k_ts,
+                  const void* v, int64_t v_bs, int64_t v_ts,
+                  void* out, int B, int H, int Tq, int Tk,
+                  const uint8_t* mask, int64_t mask_bs, int64_t mask_rs,
+                  const float* key_bias, float scale, int dtype, int engine, void* stream);
+
+/*
+ * Streaming relative-position fold (attention.py:78-88 with P == Tk, B == 1).
+ * With q' = q + pos_bias_u folded into the q bias:  ac + bd = q'.(k_j + p_j) + (v - u).p_j
+ *   k_out[b,j,h,:] = k[b,j,h,:] + p[b,j,h,:]        key_bias[b,h,j] = sum_c (vbias-ubias)[h,c] * p[b,j,h,c]
+ * k: (B,Tk,H,64) act dtype strides (k_bs,k_ts); p: (B,Tk,H*64) act dtype, rows contiguous, batch stride
+ * p_bs elements (0 = one table shared by the batch); k_out contiguous (B,Tk,H,64); u,vb fp32 (H,64).
+ */
+int cfm_relpos_keys(const void* k, int64_t k_bs, int64_t k_ts, const void* p, int64_t p_bs,
+                    const float* u, const float* vb, void* k_out, float* key_bias,
+                    int B, int H, int Tk, int dtype, void* stream);
+
+/*
+ * Depthwise conv1d along time + per-channel affine + SiLU on channel-last activations:
+ *   y[b,t,c] = silu( sum_j w[j,c] * x[b,t+j-(k-1)/2,c] + bias[c] ),  zero outside [0,T)
+ * Replaces depthwise_conv -> BatchNorm1d(eval) -> SiLU (convolution.py:43-45): the host folds the
+ * BatchNorm running statistics and the conv bias into (w, bias).  x,y: (B,T,d) act dtype;
+ * w: (k,d) fp32 (tap-major); bias: (d) fp32.  With apply_silu == 0 the raw conv+bias is written as
+ * fp32 (training path, BatchNorm batch statistics follow).  d % 64 == 0, k odd <= 31.
+ */
+int cfm_dwconv(const void* x, const float* w, const float* bias, void* y,
+               int B, int T, int d, int k, int dtype, int apply_silu, void* stream);
+
+/*
+ * BatchNorm1d training-mode pieces (convolution.py:44): statistics over all B*T rows, unmasked.
+ *   cfm_bn_stats : sum[c] = sum_r x[r,c], sumsq[c] = sum_r (x[r,c])^2   (x fp32 (rows,d); outputs must be zeroed)
+ *   cfm_bn_apply_silu : y = silu((x-mean)*rstd*gamma+beta) in act dtype
+ */
+int cfm_bn_stats(const float* x, int rows, int d, float* sum, float* sumsq, void* stream);
+int cfm_bn_apply_silu(const float* x, int rows, int d, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, void* y, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFM_B200_H_ */

@@ -1,0 +1,181 @@
+"""Op-level parity of every C-ABI kernel against a plain PyTorch fp32 restatement of the same
+reference statements (level 1).  Runs on the B200 box: pytest -m gpu."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conformer_pytorch_lightning_b200 import _native as N
+from conformer_pytorch_lightning_b200 import ops
+
+DEV = "cuda"
+TOL = {torch.float32: 2e-5, torch.bfloat16: 1.5e-2}     # max-abs-err / max-abs-ref
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+@pytest.mark.parametrize("d", [128, 256, 512])
+@pytest.mark.parametrize("ydt", [torch.float32, torch.bfloat16])
+def test_layernorm_variants(d, ydt):
+    rows = 333
+    x = rnd(rows, d, scale=3.0) + 0.5
+    g1, b1, g2, b2 = rnd(d, seed=1) * 0.1 + 1, rnd(d, seed=2) * 0.1, rnd(d, seed=3) * 0.1 + 1, rnd(d, seed=4) * 0.1
+    F = torch.nn.functional
+    ref1 = F.layer_norm(x, (d,), g1, b1, 1e-5)
+    ref2 = F.layer_norm(ref1, (d,), g2, b2, 1e-5)
+    valid = (torch.arange(rows, device=DEV) % 5 != 0)
+    # single LN -> y
+    y = torch.empty(rows, d, dtype=ydt, device=DEV)
+    ops.layernorm(x, g1, b1, y=y)
+    assert rel_err(y.float(), ref1) < (1e-5 if ydt == torch.float32 else 6e-3)
+    # chained LN, x_out in place, masked y
+    xin = x.clone()
+    ops.layernorm(xin, g1, b1, x_out=xin, g2=g2, b2=b2, y=y, row_valid=valid.to(torch.uint8))
+    assert rel_err(xin, ref1) < 1e-5
+    assert rel_err(y.float(), ref2 * valid[:, None]) < (1e-5 if ydt == torch.float32 else 6e-3)
+    assert float(y[~valid].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,Nn,K", [(1, 256, 256), (77, 256, 2048), (300, 2048, 256), (129, 768, 256), (64, 512, 512)])
+def test_gemm_epilogues_simt(dt, M, Nn, K):
+    a = rnd(M, K, dtype=dt)
+    w = rnd(Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=1)
+    w2 = rnd(2 * Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=2)
+    bias = rnd(Nn, seed=3)
+    bias2 = rnd(2 * Nn, seed=4)
+    af, wf, w2f = a.float(), w.float(), w2.float()
+    lin = af @ wf.t() + bias
+    tol = TOL[dt]
+    for eng in (N.ENGINE_SIMT,):
+        out = torch.empty(M, Nn, dtype=dt, device=DEV)
+        ops.gemm(a, w, bias, out, N.EPI_BIAS, engine=eng)
+        assert rel_err(out.float(), lin) < tol
+        ops.gemm(a, w, bias, out, N.EPI_BIAS_SILU, engine=eng)
+        assert rel_err(out.float(), torch.nn.functional.silu(lin)) < tol
+        lin2 = af @ w2f.t() + bias2
+        ops.gemm(a, w2, bias2, out, N.EPI_BIAS_GLU, engine=eng)
+        assert rel_err(out.float(), lin2[:, :Nn] * torch.sigmoid(lin2[:, Nn:])) < tol
+        res = rnd(M, Nn, seed=5)
+        valid = (torch.arange(M, device=DEV) % 3 != 1)
+        x = res.clone()
+        ops.gemm(a, w, bias, x, N.EPI_RESIDUAL, residual=x, alpha=0.5, row_valid=valid.to(torch.uint8), engine=eng)
+        assert rel_err(x, res + 0.5 * lin * valid[:, None]) < tol
+        # no bias, strided A (row stride > K)
+        abig = rnd(M, K + 64, dtype=dt, seed=6)
+        ops.gemm(abig[:, :K], w, None, out, N.EPI_BIAS, engine=eng)
+        assert rel_err(out.float(), abig[:, :K].float() @ wf.t()) < tol
+
+
+def _attn_ref(q, k, v, mask, key_bias, scale):
+    # attention.py:84-97 in fp32 on (B,T,H,64) layouts
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = qf @ kf.transpose(-1, -2)
+    if key_bias is not None:
+        s = s + key_bias[:, :, None, :]
+    s = s * scale
+    if mask is not None:
+        m = mask.unsqueeze(1).eq(0)
+        s = s.masked_fill(m, -float("inf"))
+        p = torch.softmax(s, dim=-1).masked_fill(m, 0.0)
+        p = torch.nan_to_num(p, nan=0.0)
+    else:
+        p = torch.softmax(s, dim=-1)
+    return (p @ vf).permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[1], -1)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Tq,Tk,kind", [(2, 4, 49, 49, "pad"), (3, 4, 74, 74, "chunk"), (1, 4, 16, 48, "none"),
+                                           (2, 8, 130, 130, "left"), (1, 4, 16, 32, "bias"), (2, 4, 200, 200, "pad")])
+def test_attention_simt(dt, B, H, Tq, Tk, kind):
+    qkv = rnd(B, max(Tq, Tk), 3, H, 64, dtype=dt)
+    q, k, v = qkv[:, :Tq, 0], qkv[:, :Tk, 1], qkv[:, :Tk, 2]
+    mask, kb = None, None
+    if kind == "pad":
+        lens = torch.tensor([Tk, Tk - 13, Tk // 2][:B], device=DEV)
+        mask = (torch.arange(Tk, device=DEV)[None, :] < lens[:, None]).unsqueeze(1)        # (B,1,Tk)
+    elif kind in ("chunk", "left"):
+        from conformer_pytorch_lightning_b200 import subsequent_chunk_mask
+        cm = subsequent_chunk_mask(Tk, 16, 1 if kind == "left" else -1, torch.device(DEV))
+        lens = torch.tensor([Tk, Tk - 20, 7][:B], device=DEV)
+        pad = (torch.arange(Tk, device=DEV)[None, :] < lens[:, None]).unsqueeze(1)
+        mask = pad & cm.unsqueeze(0)                                                     # (B,Tq,Tk) with empty rows
+    elif kind == "bias":
+        kb = rnd(B, H, Tk, seed=9)
+    out = torch.empty(B, Tq, H * 64, dtype=dt, device=DEV)
+    ops.attention(q, k, v, out, mask=mask, key_bias=kb, scale=0.125, engine=N.ENGINE_SIMT)
+    ref = _attn_ref(q, k, v, mask, kb, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float(), ref) < TOL[dt]
+    if kind == "left":
+        empty = ~mask.any(dim=-1)                      # fully masked rows -> exactly 0
+        if empty.any():
+            assert float(out.float()[empty].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,d,k", [(2, 49, 256, 15), (3, 130, 512, 31), (1, 16, 256, 15), (2, 70, 128, 7)])
+def test_dwconv(dt, B, T, d, k):
+    x = rnd(B, T, d, dtype=dt)
+    w = rnd(d, 1, k, scale=0.3, seed=1)
+    b = rnd(d, seed=2)
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w, b, padding=(k - 1) // 2, groups=d).transpose(1, 2)
+    y = torch.empty_like(x)
+    ops.dwconv(x, w[:, 0].t().contiguous(), b, y, apply_silu=True)
+    assert rel_err(y.float(), torch.nn.functional.silu(ref)) < TOL[dt]
+    raw = torch.empty(B, T, d, dtype=torch.float32, device=DEV)
+    ops.dwconv(x, w[:, 0].t().contiguous(), b, raw, apply_silu=False)
+    assert rel_err(raw, ref) < 1e-5
+
+
+def test_bn_stats_and_apply():
+    rows, d = 1000, 256
+    x = rnd(rows, d, scale=2.0) + 1.0
+    st = torch.zeros(2, d, device=DEV)
+    ops.bn_stats(x, st[0], st[1])
+    assert rel_err(st[0], x.sum(0)) < 1e-5 and rel_err(st[1], (x * x).sum(0)) < 1e-5
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    g, b = rnd(d, seed=1), rnd(d, seed=2)
+    for dt in (torch.float32, torch.bfloat16):
+        y = torch.empty(rows, d, dtype=dt, device=DEV)
+        ops.bn_apply_silu(x, mean, torch.rsqrt(var + 1e-5), g, b, y)
+        ref = torch.nn.functional.silu((x - mean) * torch.rsqrt(var + 1e-5) * g + b)
+        assert rel_err(y.float(), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_relpos_keys(dt):
+    B, Tk, H = 2, 37, 4
+    k = rnd(B, Tk, 3, H, 64, dtype=dt)[:, :, 1]
+    for Bp in (1, B):
+        p = rnd(Bp, Tk, H * 64, dtype=dt, seed=3)
+        u, vb = rnd(H, 64, seed=4), rnd(H, 64, seed=5)
+        ko = torch.empty(B, Tk, H, 64, dtype=dt, device=DEV)
+        kb = torch.empty(B, H, Tk, device=DEV)
+        ops.relpos_keys(k, p, u, vb, ko, kb)
+        p4 = p.float().view(Bp, Tk, H, 64)
+        assert rel_err(ko.float(), k.float() + p4) < TOL[dt]
+        ref_kb = torch.einsum("hc,bjhc->bhj", vb - u, p4).expand(B, H, Tk)
+        assert rel_err(kb, ref_kb) < 1e-5
+
+
+def test_errors_are_reported_not_thrown_across_abi():
+    x = torch.zeros(4, 100, device=DEV)       # d=100 unsupported
+    g = torch.ones(100, device=DEV)
+    with pytest.raises(RuntimeError, match="cfm_layernorm"):
+        ops.layernorm(x, g, g, y=torch.empty_like(x))
+    before = N.launch_count()
+    ops.layernorm(torch.zeros(4, 128, device=DEV), torch.ones(128, device=DEV), torch.ones(128, device=DEV),
+                  y=torch.empty(4, 128, device=DEV))
+    assert N.launch_count() == before + 1

@@ -1,0 +1,178 @@
+"""Module/encoder-level parity of the CUDA path against (a) the committed golden outputs of the real
+reference and (b) the numpy oracle on the same seeded inputs.  pytest -m gpu (B200 box)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import conformer_oracle as O
+from _util import FWD_CASES, build_encoder, load_golden, max_rel
+
+FP32_TOL = 1e-4      # north_star: fp32 max-rel 1e-4
+BF16_TOL = 2e-2      # north_star: bf16 max-rel 2e-2
+
+
+def _run_forward(g, dtype):
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    if int(g["torch_seed"]) >= 0:
+        torch.manual_seed(int(g["torch_seed"]))
+    fw = g["fw"]
+    with torch.no_grad():
+        out, mask = enc(torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["lens"]).cuda(), **fw)
+    return enc, out, mask
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+def test_encoder_forward_fp32_vs_reference_golden(name):
+    g = load_golden(name)
+    _, out, mask = _run_forward(g, torch.float32)
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
+    assert np.array_equal(mask.cpu().numpy(), g["out_mask"])           # bit exact
+    assert max_rel(out.cpu().numpy(), g["out"]) < FP32_TOL              # all positions, padded rows too (D11)
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+def test_encoder_forward_bf16_vs_reference_golden(name):
+    g = load_golden(name)
+    _, out, mask = _run_forward(g, torch.bfloat16)
+    assert np.array_equal(mask.cpu().numpy(), g["out_mask"])
+    err = max_rel(out.cpu().numpy(), g["out"])
+    print(f"{name}: bf16 max-rel {err:.4f}")
+    assert err < BF16_TOL
+
+
+@pytest.mark.parametrize("name", ["m12_pad", "m3_static16", "m3_left1", "l2_pad"])
+def test_measured_path_only(name):
+    """encode_layers (= encoder.py:72-74) fed with the reference's own boundary tensors."""
+    g = load_golden(name)
+    enc = build_encoder(g["cfg"], g["weight_seed"])
+    t = lambda a: torch.from_numpy(a).cuda()
+    with torch.no_grad():
+        out = enc.encode_layers(t(g["embed_out"]), t(g["attn_mask"]), t(g["pos_embed"]), t(g["pad_mask"]))
+    assert max_rel(out.cpu().numpy(), g["out"]) < FP32_TOL
+
+
+def test_ctc_greedy_ids_bit_exact_fp32():
+    g = load_golden("m12_c1_wav")
+    c = load_golden("m12_c1_ctc")
+    _, out, mask = _run_forward(g, torch.float32)
+    crs = np.random.RandomState(int(c["ctc_seed"]))
+    w = torch.from_numpy(crs.uniform(-1 / 16, 1 / 16, size=(5002, 256)).astype(np.float32)).cuda()
+    b = torch.from_numpy(crs.uniform(-1 / 16, 1 / 16, size=(5002,)).astype(np.float32)).cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    best = torch.nn.functional.linear(out, w, b).argmax(-1).cpu().numpy().astype(np.int16)
+    assert np.array_equal(best, c["best"])
+    # bf16: report the agreement rate (reference's own bf16 agrees with its fp32 on ~94 % of frames, D9)
+    _, outb, _ = _run_forward(g, torch.bfloat16)
+    bestb = torch.nn.functional.linear(outb, w, b).argmax(-1).cpu().numpy().astype(np.int16)
+    valid = mask.cpu().numpy()[:, 0, :]
+    rate = float((bestb == c["best"])[valid].mean())
+    print(f"bf16 CTC frame-id agreement with the fp32 reference: {rate:.4f}")
+    assert rate > 0.85
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("tag", ["all", "none", "16"])
+def test_streaming_forward_chunk(tag, dtype, tol):
+    g = load_golden("m3_stream_" + tag)
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    req = int(g["required_cache_size"])
+    cache = torch.zeros((0, 0, 0, 0))
+    cnn = torch.zeros((0, 0, 0, 0))
+    offset = 0
+    feats = torch.from_numpy(g["feats"]).cuda()
+    for i in range(3):
+        with torch.no_grad():
+            o, cache, cnn = enc.forward_chunk(feats[:, i * 64:i * 64 + 67], offset, req, cache, cnn)
+        offset += o.size(1)
+        assert tuple(o.shape) == g[f"out{i}"].shape
+        assert tuple(cache.shape) == g[f"cache{i}"].shape
+        assert tuple(cnn.shape) == (3, 0, 0, 0)
+        assert max_rel(o.cpu().numpy(), g[f"out{i}"]) < tol
+        if cache.numel():
+            assert max_rel(cache.cpu().numpy(), g[f"cache{i}"]) < tol
+
+
+def test_forward_chunk_by_chunk():
+    g = load_golden("m3_chunk_by_chunk")
+    enc = build_encoder(g["cfg"], g["weight_seed"])
+    feats = torch.from_numpy(g["feats"]).cuda()
+    with torch.no_grad():
+        o, m = enc.forward_chunk_by_chunk(feats, 16, -1)
+        o2, _ = enc.forward_chunk_by_chunk(feats, 8, 2)
+        # the reference's greedy_search passes a 1-element length tensor as the chunk size (model.py:206-209)
+        o3, _ = enc.forward_chunk_by_chunk(feats, torch.tensor([16]))
+    assert tuple(m.shape) == g["mask"].shape and m.dtype == torch.float32
+    assert max_rel(o.cpu().numpy(), g["out_c16"]) < FP32_TOL
+    assert max_rel(o2.cpu().numpy(), g["out_c8_l2"]) < FP32_TOL
+    assert max_rel(o3.cpu().numpy(), g["out_c16"]) < FP32_TOL
+    g = load_golden("m3_abs_chunk_by_chunk")
+    enc = build_encoder(g["cfg"], g["weight_seed"])
+    with torch.no_grad():
+        o, _ = enc.forward_chunk_by_chunk(torch.from_numpy(g["feats"]).cuda(), 16, -1)
+    assert max_rel(o.cpu().numpy(), g["out_c16"]) < FP32_TOL
+
+
+def test_training_mode_forward_batchnorm():
+    g = load_golden("m3_train_fwd")
+    enc = build_encoder(g["cfg"], g["weight_seed"]).train()
+    with torch.no_grad():
+        out, _ = enc(torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["lens"]).cuda())
+    assert max_rel(out.cpu().numpy(), g["out"]) < FP32_TOL
+    sd = enc.state_dict()
+    for i in range(3):
+        key = f"encoders.{i}.conv_module.norm."
+        gk = key.replace(".", "__")
+        assert max_rel(sd[key + "running_mean"].cpu().numpy(), g[gk + "running_mean"]) < 1e-4
+        assert max_rel(sd[key + "running_var"].cpu().numpy(), g[gk + "running_var"]) < 1e-4
+        assert int(sd[key + "num_batches_tracked"]) == int(g[gk + "num_batches_tracked"])
+
+
+def test_submodules_vs_oracle():
+    """Layer / attention / conv / ffn modules called directly (module-level API), vs the numpy oracle."""
+    cfg = O.conformer_cfg("M", encoder_num_layers=1)
+    sd = O.make_state_dict(cfg, 21)
+    enc = build_encoder(cfg, 21)
+    layer = enc.encoders[0]
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((2, 40, 256)).astype(np.float32)
+    lens = np.array([40, 29])
+    pad = (np.arange(40)[None, :] < lens[:, None])[:, None, :]
+    pos = O.rel_pos_table(5000, 256)[:2]
+    t = lambda a: torch.from_numpy(a).cuda()
+    p = "encoders.0."
+    with torch.no_grad():
+        y = layer.feed_forward(t(x))
+        assert max_rel(y.cpu().numpy(), O.feed_forward(x, sd, p + "feed_forward.")) < FP32_TOL
+        y, c = layer.conv_module(t(x), t(pad))
+        assert max_rel(y.cpu().numpy(), O.conv_module(x, pad, sd, p + "conv_module.")) < FP32_TOL
+        assert tuple(c.shape) == (0, 0, 0)
+        y, cache = layer.self_attn(t(x), t(x), t(x), t(pad), t(pos))
+        ry, rc = O.rel_mhsa(x, pad, pos, None, sd, p + "self_attn.", 4)
+        assert max_rel(y.cpu().numpy(), ry) < FP32_TOL and max_rel(cache.cpu().numpy(), rc) < FP32_TOL
+        # float masks follow `.eq(0)` semantics; empty sentinel = no mask
+        y2, _ = layer.self_attn(t(x), t(x), t(x), t(pad.astype(np.float32)), t(pos))
+        assert torch.equal(y, y2)
+        y3, _ = layer.self_attn(t(x), t(x), t(x), torch.ones((0, 0, 0), device="cuda"), t(pos))
+        ry3, _ = O.rel_mhsa(x, None, pos, None, sd, p + "self_attn.", 4)
+        assert max_rel(y3.cpu().numpy(), ry3) < FP32_TOL
+        out, am, nc, cc = layer(t(x), t(pad), t(pos), t(pad))
+        ro, rcache = O.encoder_layer(x, pad, pos, pad, None, sd, p, cfg)
+        assert max_rel(out.cpu().numpy(), ro) < FP32_TOL and max_rel(nc.cpu().numpy(), rcache) < FP32_TOL
+        assert tuple(cc.shape) == (0, 0, 0)
+
+
+def test_weights_refresh_after_load_state_dict():
+    """Derived (bf16 / folded) weights are caches: loading new parameters must invalidate them."""
+    g = load_golden("m3_static16")
+    enc = build_encoder(g["cfg"], 123, compute_dtype=torch.bfloat16)       # wrong weights first
+    feats, lens = torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["lens"]).cuda()
+    with torch.no_grad():
+        bad, _ = enc(feats, lens)
+    assert max_rel(bad.cpu().numpy(), g["out"]) > 0.1
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(g["cfg"], g["weight_seed"]).items()}
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        good, _ = enc(feats, lens)
+    assert max_rel(good.cpu().numpy(), g["out"]) < BF16_TOL
