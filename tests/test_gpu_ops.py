@@ -179,3 +179,43 @@ def test_errors_are_reported_not_thrown_across_abi():
     ops.layernorm(torch.zeros(4, 128, device=DEV), torch.ones(128, device=DEV), torch.ones(128, device=DEV),
                   y=torch.empty(4, 128, device=DEV))
     assert N.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 256), (200, 256, 2048), (1000, 2048, 256), (333, 768, 256), (4096, 512, 512),
+                                    (15872, 2048, 256), (777, 384, 128), (64, 128, 64)])
+def test_gemm_tcgen05(M, Nn, K):
+    """tcgen05/TMEM/TMA engine vs fp32 matmul of the same bf16 operands (and vs the SIMT engine)."""
+    dt = torch.bfloat16
+    a = rnd(M, K, dtype=dt)
+    w = rnd(Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=1)
+    bias = rnd(Nn, seed=3)
+    af, wf = a.float(), w.float()
+    lin = af @ wf.t() + bias
+    out = torch.empty(M, Nn, dtype=dt, device=DEV)
+    ops.gemm(a, w, bias, out, N.EPI_BIAS, engine=N.ENGINE_TC)
+    assert rel_err(out.float(), lin) < 6e-3
+    ops.gemm(a, w, bias, out, N.EPI_BIAS_SILU, engine=N.ENGINE_TC)
+    assert rel_err(out.float(), torch.nn.functional.silu(lin)) < 6e-3
+    ops.gemm(a, w, None, out, N.EPI_BIAS, engine=N.ENGINE_TC)
+    assert rel_err(out.float(), af @ wf.t()) < 6e-3
+    res = rnd(M, Nn, seed=5)
+    valid = (torch.arange(M, device=DEV) % 3 != 1)
+    x = res.clone()
+    ops.gemm(a, w, bias, x, N.EPI_RESIDUAL, residual=x, alpha=0.5, row_valid=valid.to(torch.uint8), engine=N.ENGINE_TC)
+    assert rel_err(x, res + 0.5 * lin * valid[:, None]) < 1e-5      # fp32 output: only accumulation-order noise
+    x2 = res.clone()
+    ops.gemm(a, w, bias, x2, N.EPI_RESIDUAL, residual=x2, alpha=0.5, row_valid=valid.to(torch.uint8), engine=N.ENGINE_SIMT)
+    assert rel_err(x, x2) < 1e-5
+    if Nn % 256 == 0:   # GLU: W = [Wa;Wb] with Nn/2 outputs
+        No = Nn // 2
+        bias2 = rnd(Nn, seed=4)
+        lin2 = af @ wf.t() + bias2
+        o = torch.empty(M, No, dtype=dt, device=DEV)
+        ops.gemm(a, w, bias2, o, N.EPI_BIAS_GLU, engine=N.ENGINE_TC)
+        assert rel_err(o.float(), lin2[:, :No] * torch.sigmoid(lin2[:, No:])) < 6e-3
+    # strided A / strided C views
+    abig = rnd(M, K + 64, dtype=dt, seed=6)
+    obig = torch.zeros(M, Nn + 8, dtype=dt, device=DEV)
+    ops.gemm(abig[:, :K], w, bias, obig[:, :Nn], N.EPI_BIAS, engine=N.ENGINE_TC)
+    assert rel_err(obig[:, :Nn].float(), abig[:, :K].float() @ wf.t() + bias) < 6e-3
+    assert float(obig[:, Nn:].abs().max()) == 0.0
