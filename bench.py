@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: Conformer encoder audio-seconds per wall-second (RTFx) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4]
+
+Workload (BASELINE.json configs[1], "C2"): Conformer-M (12 layers, d=256, 4 heads, FFN 2048, conv k=15),
+bf16 compute, batch 64 x 10 s of synthetic 80-dim fbank (Tin = 998 -> T = 248 after 4x sub-sampling),
+random-init weights.  One *step* = one pass of the measured path (layer loop + after_norm,
+reference src/encoder.py:72-74) over one batch.  With N GPUs every rank processes its own batch of 64
+utterances (weak scaling, no data-path collective); the JSON line is printed by rank 0.
+
+value : RTFx of the measured path with its inputs (sub-sampled features, masks) resident in HBM,
+        CUDA events per step on the launch stream, L2 flushed between steps, max over ranks.
+e2e   : the same metric through the public drop-in API ``ConformerEncoder.forward(feats, lengths)`` with
+        pinned HOST fbank features: H2D copy + CMVN-less sub-sampling (PyTorch) + layers + D2H of the output.
+roofline : dominant kernel = the tcgen05 GEMM; the instance quoted is the FFN up-projection
+        (M=B*T, N=2048, K=256, bias+SiLU), timed in-step with CUDA events around each of its launches.
+cpu_baseline / --impl reference : the ATen-CPU oracle port of the reference's CPU path (the reference is
+        Python and cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cfg name, batch, seconds, padded lengths?)
+    "C2": ("M", 64, 10.0, False),
+    "C3": ("L", 32, 20.0, False),
+    "C4": ("M", 16, 60.0, True),
+}
+
+
+def frames(seconds):
+    tin = int((16000 * seconds - 400) // 160 + 1)
+    return tin, ((tin - 1) // 2 - 1) // 2
+
+
+def make_inputs(workload, seed=1234):
+    cfg_name, B, sec, padded = WORKLOADS[workload]
+    tin, T = frames(sec)
+    rs = np.random.RandomState(seed)
+    feats = rs.standard_normal((B, tin, 80)).astype(np.float32)
+    if padded:
+        lens = np.sort(rs.randint(tin // 2, tin + 1, size=B))[::-1].copy()
+        lens[0] = tin
+    else:
+        lens = np.full((B,), tin)
+    return cfg_name, feats, lens.astype(np.int32), T, float(np.sum(((lens.astype(np.float64) - 1) * 160 + 400) / 16000.0))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rtfx(workload, sample_b, repeats):
+    """The CPU port of the reference's algorithm (oracle/conformer_oracle_torch.py: the same ATen CPU
+    kernels the reference's modules run, all host threads), measured path only, fp32."""
+    import torch
+    from oracle import conformer_oracle as O
+    from oracle import conformer_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count())
+    cfg_name, feats, lens, T, _ = make_inputs(workload)
+    cfg = O.conformer_cfg(cfg_name)
+    sd = O.make_state_dict(cfg, 0)
+    sample_b = min(sample_b, feats.shape[0])
+    f, l = feats[:sample_b], lens[:sample_b]
+    audio = float(np.sum(((l.astype(np.float64) - 1) * 160 + 400) / 16000.0))
+    # boundary tensors of the measured path; the sub-sampling front-end is outside it (random stand-in
+    # with the right shape/statistics: timing does not depend on the values)
+    Ts = ((f.shape[1] - 1) // 2 - 1) // 2
+    x = torch.from_numpy(np.random.RandomState(7).standard_normal((sample_b, Ts, cfg["encoder_dim"])).astype(np.float32))
+    pad = torch.from_numpy(~O.make_pad_mask(l, f.shape[1])[:, None, :][:, :, 2::2][:, :, 2::2])
+    pos = torch.from_numpy(O.rel_pos_table(cfg["max_len"], cfg["encoder_dim"])[:sample_b])
+    attn = pad
+    sdc = OT.to_torch_sd(sd)
+    best = float("inf")
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        OT.encoder_layers(x, attn, pos, pad, sdc, cfg)
+        dt = time.perf_counter() - t0
+        times.append(dt)
+        best = min(best, dt)
+    return audio / best, best, sample_b, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    steps = max(1, args.steps)
+    # size the per-step sample so that the whole (warmup + steps) run stays within ~2 minutes
+    _, probe, _, _ = cpu_port_rtfx(args.workload, 1, 1)
+    budget = 120.0 / (args.warmup + steps)
+    sb = int(max(1, min(args.cpu_sample, budget // max(probe, 1e-3))))
+    rtfx, best, sb, times = cpu_port_rtfx(args.workload, sb, args.warmup + steps)
+    timed = times[args.warmup:] if len(times) > args.warmup else times
+    ms = 1e3 * float(np.mean(timed))
+    cfg_name, feats, lens, T, _ = make_inputs(args.workload)
+    audio = float(np.sum(((lens[:sb].astype(np.float64) - 1) * 160 + 400) / 16000.0))
+    val = audio / (ms / 1e3)
+    sample = f"measured path (12 layers + after_norm) on {sb} of the {feats.shape[0]} utterances per step"
+    line = {"impl": "reference", "metric": "encoder audio-sec/sec (RTFx), measured path", "value": val,
+            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: Conformer-{cfg_name} fp32 ATen-CPU port of the reference on the host cores, sample B={sb} x 10 s (T={T})"},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import build_encoder
+    from oracle import conformer_oracle as O  # only for cfg + seeded weights + the cpu_baseline leg
+    from conformer_pytorch_lightning_b200 import _native, ops
+    from conformer_pytorch_lightning_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    cfg_name, feats_np, lens_np, T, audio_s = make_inputs(args.workload, seed=1234 + rank)
+    cfg = O.conformer_cfg(cfg_name)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    enc = build_encoder(cfg, 0, device=dev, compute_dtype=dtype)
+    B = feats_np.shape[0]
+
+    feats_host = torch.from_numpy(feats_np).pin_memory()
+    lens_dev = torch.from_numpy(lens_np).to(dev)
+    with torch.no_grad():
+        feats_dev = feats_host.to(dev)
+        pad = ~enc_make_pad(lens_dev, feats_dev.size(1))
+        x_emb, pos, pad = enc.embed(feats_dev, pad)
+        from conformer_pytorch_lightning_b200.utils import make_attn_mask
+        attn = make_attn_mask(x_emb, pad, False, False, 0, -1, -1)
+    x_emb = x_emb.contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        with torch.no_grad():
+            return enc.encode_layers(x_emb, attn, pos, pad)
+
+    def e2e_step():
+        with torch.no_grad():
+            out, mask = enc(feats_host.to(dev, non_blocking=True), lens_dev)
+            return out.to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, wall=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        total_ms, n0 = 0.0, _native.launch_count()
+        t_wall = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)                      # evict L2 (126 MB) between steps; not inside the event bracket
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if wall:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                total_ms += 1e3 * (time.perf_counter() - t0)
+            else:
+                s.record()
+                fn()
+                e.record()
+                e.synchronize()
+                total_ms += s.elapsed_time(e)
+        barrier()
+        launches = _native.launch_count() - n0
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, time.perf_counter() - t_wall
+
+    with ClockSampler(local) as clk:
+        total_ms, launches, _ = timed(step, args.steps, args.warmup)
+    ms_per_step = total_ms / args.steps
+    value = world * audio_s / (ms_per_step / 1e3)
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches}))
+        return
+    e2e_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 3, wall=True)
+    e2e_ms /= max(3, args.steps // 4)
+    e2e_val = world * audio_s / (e2e_ms / 1e3)
+    out_bytes = B * T * cfg["encoder_dim"] * 4
+
+    # ---- roofline of the dominant kernel, timed in-step with events around each matching launch
+    pk = peaks()
+    n_tok, d, F = B * T, cfg["encoder_dim"], cfg["hidden_dim"]
+    ev = []
+    orig_gemm = ops.gemm
+
+    def probe(a, w, bias, out, epi, **kw):
+        match = (epi == _native.EPI_BIAS_SILU and tuple(w.shape) == (F, d))
+        if match:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+        r = orig_gemm(a, w, bias, out, epi, **kw)
+        if match:
+            e.record()
+            ev.append((s, e))
+        return r
+
+    ops.gemm = probe
+    engine.ops.gemm = probe
+    try:
+        for _ in range(3):
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig_gemm
+        engine.ops.gemm = orig_gemm
+    kt = float(np.mean([s.elapsed_time(e) for s, e in ev])) if ev else float("nan")
+    flops = 2.0 * n_tok * d * F
+    ach = flops / (kt * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<256,SILU> M={n_tok} N={F} K={d} (FFN w_1 + SiLU)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": None, "launch_us": kt * 1e3, "peak_source": pk["source"] + ", sustained bf16"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, best, sb, _ = cpu_port_rtfx(args.workload, args.cpu_sample, 3)
+            cpu = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"ATen-CPU port (oracle/conformer_oracle_torch.py), measured path on {sb} of {B} utterances, best of 3 ({best:.2f} s)"}
+        algo_tf = 1.024 if args.workload == "C2" else None
+        line = {"metric": "encoder audio-sec/sec (RTFx), measured path", "value": value, "unit": "audio-s/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: Conformer-{cfg_name} {cfg['encoder_num_layers']}L d={d} "
+                                       f"encoder layers+after_norm, batch {B} x {WORKLOADS[args.workload][2]:.0f} s per GPU (T={T})",
+                           "per_gpu_batch": B, "timing": "CUDA events per step on the launch stream; 256 MiB write flushes L2 between steps"},
+                "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(feats_host.numel() * 4 + lens_np.nbytes),
+                        "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_ms,
+                        "api": "ConformerEncoder.forward(feats_pinned_host.to(cuda), lengths) -> out.cpu()"},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary()}
+        if algo_tf:
+            line["model_tflops"] = algo_tf / (ms_per_step / 1e3) * world
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def enc_make_pad(lens, max_len):
+    from conformer_pytorch_lightning_b200.utils import make_pad_mask
+    return make_pad_mask(lens, max_len).unsqueeze(1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances per CPU-baseline step")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="measured path only (for ncu): no e2e / probe / cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

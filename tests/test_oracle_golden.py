@@ -124,3 +124,15 @@ def test_training_forward_batchnorm():
         assert int(g[key + "num_batches_tracked"]) == st["num_batches_tracked"] == 4
     out = O.layer_norm(x, sd["after_norm.weight"], sd["after_norm.bias"])
     assert max_rel(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["m12_pad", "m3_static16", "m3_left1", "l2_pad"])
+def test_torch_cpu_port_matches_reference(name):
+    """The multi-threaded CPU port used as bench.py's cpu_baseline is pinned to the same goldens."""
+    import torch
+    from oracle import conformer_oracle_torch as OT
+    g = load_golden(name)
+    sd = OT.to_torch_sd(O.make_state_dict(g["cfg"], g["weight_seed"]))
+    t = torch.from_numpy
+    out = OT.encoder_layers(t(g["embed_out"]), t(g["attn_mask"]), t(g["pos_embed"]), t(g["pad_mask"]), sd, g["cfg"])
+    assert max_rel(out.numpy(), g["out"]) < TOL
