@@ -66,7 +66,8 @@ extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const vo
   CFM_CHECK_ARG(B >= 0 && H > 0 && Tq >= 0 && Tk >= 0, "cfm_attention: bad shape");
   if (B == 0 || Tq == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_ok = attention_tc_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, dtype);
+  const bool tc_ok = key_bias == nullptr && scale > 0.f &&
+                     attention_tc_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, dtype);
   if (engine == CFM_ENGINE_TC) {
     CFM_CHECK_ARG(tc_ok, "cfm_attention: tcgen05 engine does not support this shape/dtype");
     return attention_tc(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,

@@ -266,6 +266,7 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
     x.copy_(inputs.reshape(n, d))
     y = ws.get("ln_y", (n, d), dtype, dev)
     row_valid = _row_valid(pad_mask, B, T)
+    attn_mask = _mask_u8(attn_mask)          # normalised once, not per layer
     new_caches = []
     out = x
     for i, layer in enumerate(layers):

@@ -219,3 +219,35 @@ def test_gemm_tcgen05(M, Nn, K):
     ops.gemm(abig[:, :K], w, bias, obig[:, :Nn], N.EPI_BIAS, engine=N.ENGINE_TC)
     assert rel_err(obig[:, :Nn].float(), abig[:, :K].float() @ wf.t() + bias) < 6e-3
     assert float(obig[:, Nn:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,kind", [(2, 4, 248, 248, "pad"), (3, 4, 74, 74, "chunk"), (2, 8, 130, 130, "left"),
+                                           (1, 4, 300, 300, "none"), (2, 4, 128, 128, "pad"), (1, 2, 1498, 1498, "pad"),
+                                           (2, 4, 129, 257, "none"), (2, 4, 64, 64, "chunk"), (1, 4, 40, 200, "padu8")])
+def test_attention_tcgen05(B, H, Tq, Tk, kind):
+    dt = torch.bfloat16
+    qkv = rnd(B, max(Tq, Tk), 3, H, 64, dtype=dt)
+    q, k, v = qkv[:, :Tq, 0], qkv[:, :Tk, 1], qkv[:, :Tk, 2]
+    mask = None
+    lens = torch.tensor([Tk, max(Tk - 13, 1), max(Tk // 2, 1)][:B], device=DEV)
+    pad = (torch.arange(Tk, device=DEV)[None, :] < lens[:, None]).unsqueeze(1)
+    if kind == "pad":
+        mask = pad
+    elif kind == "padu8":
+        mask = pad.to(torch.uint8) * 7          # any non-zero byte is "visible" (.eq(0) semantics)
+    elif kind in ("chunk", "left"):
+        from conformer_pytorch_lightning_b200 import subsequent_chunk_mask
+        cm = subsequent_chunk_mask(Tk, 16, 1 if kind == "left" else -1, torch.device(DEV))
+        mask = pad & cm.unsqueeze(0)
+    out = torch.full((B, Tq, H * 64), float("nan"), dtype=dt, device=DEV)
+    ops.attention(q, k, v, out, mask=mask, scale=0.125, engine=N.ENGINE_TC)
+    ref = _attn_ref(q, k, v, mask, None, 0.125)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float(), ref) < 1.5e-2
+    out2 = torch.empty_like(out)
+    ops.attention(q, k, v, out2, mask=mask, scale=0.125, engine=N.ENGINE_SIMT)
+    assert rel_err(out.float(), out2.float()) < 1.5e-2
+    if mask is not None and mask.shape[1] > 1:
+        empty = ~mask.any(dim=-1)
+        if empty.any():
+            assert float(out.float()[empty].abs().max()) == 0.0
