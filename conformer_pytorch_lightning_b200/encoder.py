@@ -1,8 +1,10 @@
 """Drop-in for the reference's src/encoder.py (ConformerEncoder, :9-153)."""
+import os
+
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import _native, engine
 from .attention import PositionalEncoding, RelativePositionalEncoding
 from .convolution import ConvolutionSubSampling
 from .encoder_layer import ConformerEncoderLayer
@@ -33,6 +35,9 @@ class ConformerEncoder(nn.Module):
         self.use_dynamic_left_chunk = use_dynamic_left_chunk
         self.static_chunk_size = static_chunk_size
         self.compute_dtype = None
+        # CUDA-graph plans of the measured path, one per (batch, frames, dtype, mask layout); see _graph_layers
+        self.use_cuda_graphs = os.environ.get("CFM_B200_CUDA_GRAPHS", "1") != "0"
+        self._plans = {}
 
     # ------------------------------------------------------------------ B200-specific knobs
     def set_compute_dtype(self, dtype):
@@ -47,9 +52,61 @@ class ConformerEncoder(nn.Module):
     def encode_layers(self, outputs, inputs_attn_mask, pos_embed, inputs_pad_mask):
         """The measured path: layer loop + after_norm (encoder.py:72-74)."""
         engine.check_inference_only(self, self._max_dropout())
+        dtype = engine.resolve_dtype(self)
+        batched_pos = pos_embed is None or pos_embed.numel() == outputs.size(0) * outputs.size(2)
+        if (self.use_cuda_graphs and not self.training and outputs.is_cuda and batched_pos
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._graph_layers(outputs, inputs_attn_mask, inputs_pad_mask, dtype)
         out, _ = engine.run_layers(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask, pos_embed,
-                                   inputs_pad_mask, None, False, engine.resolve_dtype(self))
+                                   inputs_pad_mask, None, False, dtype)
         return out
+
+    def _graph_layers(self, outputs, attn_mask, pad_mask, dtype):
+        """Replay the ~15 launches/layer of the layer stack as one CUDA graph.  The first call with a new
+        (shape, dtype, mask layout) runs eagerly, the second captures, later ones replay.  Inputs are
+        copied into the plan's static buffers; derived weights are refreshed in place before the replay so
+        load_state_dict / optimizer steps are honoured; a fresh output tensor is returned."""
+        attn_mask = engine._mask_u8(attn_mask)
+        pad_u8 = engine._mask_u8(pad_mask)
+        layers = list(self.encoders)
+        key = (tuple(outputs.shape), dtype, outputs.device,
+               None if attn_mask is None else tuple(attn_mask.shape),
+               None if pad_u8 is None else tuple(pad_u8.shape), len(layers))
+        plan = self._plans.get(key)
+        if plan is None:
+            self._plans[key] = {"graph": None}
+            out, _ = engine.run_layers(outputs.float(), layers, self.after_norm, attn_mask, None, pad_u8, None, False, dtype)
+            return out
+        if plan["graph"] is None:
+            x_s = torch.empty(outputs.shape, dtype=torch.float32, device=outputs.device)
+            am_s = None if attn_mask is None else torch.empty(attn_mask.shape, dtype=torch.bool, device=outputs.device)
+            pm_s = None if pad_u8 is None else torch.empty(pad_u8.shape, dtype=torch.bool, device=outputs.device)
+            self._fill(x_s, am_s, pm_s, outputs, attn_mask, pad_u8)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = _native.launch_count()
+            with torch.cuda.graph(g):
+                out_s, _ = engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype)
+            plan.update(graph=g, x=x_s, am=am_s, pm=pm_s, out=out_s, launches=_native.launch_count() - n0)
+        for layer in layers:                  # in-place refresh of stale derived weights (no-op when unchanged)
+            layer.derived_weights(dtype)
+        self._fill(plan["x"], plan["am"], plan["pm"], outputs, attn_mask, pad_u8)
+        plan["graph"].replay()
+        engine.GRAPH_REPLAYED_LAUNCHES[0] += plan["launches"]     # native kernels inside the replayed graph
+        return plan["out"].clone()
+
+    @staticmethod
+    def _fill(x_s, am_s, pm_s, outputs, attn_mask, pad_u8):
+        x_s.copy_(outputs)
+        if am_s is not None:
+            am_s.copy_(attn_mask != 0)
+        if pm_s is not None:
+            pm_s.copy_(pad_u8 != 0)
 
     def _max_dropout(self):
         return max([m.p for m in self.modules() if isinstance(m, nn.Dropout)] + [0.0])

@@ -24,6 +24,8 @@ from . import _native as N
 from . import ops
 
 _LN_EPS = 1e-5
+# native kernel launches executed through CUDA-graph replays (they bypass cfm_launch_count)
+GRAPH_REPLAYED_LAUNCHES = [0]
 
 
 # --------------------------------------------------------------------------- compute dtype

@@ -176,3 +176,33 @@ def test_weights_refresh_after_load_state_dict():
     with torch.no_grad():
         good, _ = enc(feats, lens)
     assert max_rel(good.cpu().numpy(), g["out"]) < BF16_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_replay_equals_eager(dtype):
+    """encode_layers captures a CUDA graph on the 2nd call of a shape; replays must equal eager bit for bit,
+    follow new inputs / masks, and pick up new weights."""
+    g = load_golden("m3_left1")
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    eager = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    eager.use_cuda_graphs = False
+    feats = torch.from_numpy(g["feats"]).cuda()
+    lens = torch.from_numpy(g["lens"]).cuda()
+    fw = g["fw"]
+    for it in range(4):
+        f = feats if it % 2 == 0 else feats.flip(0) * 0.5
+        l = lens if it < 2 else torch.tensor([300, 150, 299], dtype=torch.int32, device="cuda")
+        with torch.no_grad():
+            a, ma = enc(f, l, **fw)
+            b, mb = eager(f, l, **fw)
+        assert torch.equal(ma, mb)
+        assert torch.equal(a, b), f"iteration {it}"
+    assert any(p.get("graph") is not None for p in enc._plans.values())
+    # new weights must be honoured by the captured plan
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(g["cfg"], 777).items()}
+    enc.load_state_dict(sd)
+    eager.load_state_dict(sd)
+    with torch.no_grad():
+        a, _ = enc(feats, lens, **fw)
+        b, _ = eager(feats, lens, **fw)
+    assert torch.equal(a, b)
