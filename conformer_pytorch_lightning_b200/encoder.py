@@ -93,12 +93,38 @@ class ConformerEncoder(nn.Module):
             with torch.cuda.graph(g):
                 out_s, _ = engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype)
             plan.update(graph=g, x=x_s, am=am_s, pm=pm_s, out=out_s, launches=_native.launch_count() - n0)
-        for layer in layers:                  # in-place refresh of stale derived weights (no-op when unchanged)
-            layer.derived_weights(dtype)
+        ver = self._weights_version()
+        if plan.get("ver") != ver:            # in-place refresh of stale derived weights (bf16 copies, folded BN)
+            for layer in layers:
+                layer.derived_weights(dtype)
+            plan["ver"] = ver
         self._fill(plan["x"], plan["am"], plan["pm"], outputs, attn_mask, pad_u8)
         plan["graph"].replay()
         engine.GRAPH_REPLAYED_LAUNCHES[0] += plan["launches"]     # native kernels inside the replayed graph
         return plan["out"].clone()
+
+    def _weights_version(self):
+        """Cheap staleness key: sum of the autograd version counters of every parameter/buffer of the layer
+        stack (bumped by optimizer steps, load_state_dict, any in-place edit) + a counter bumped by
+        train()/eval()/.to()/.cuda() (see train, _apply)."""
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = [p for m in (self.encoders, self.after_norm) for p in list(m.parameters()) + list(m.buffers())]
+            self.__dict__["_plist"] = plist
+        return sum([p._version for p in plist]) + self.__dict__.get("_epoch", 0)
+
+    def _bump(self):
+        self.__dict__["_epoch"] = self.__dict__.get("_epoch", 0) + (1 << 40)
+        self.__dict__["_plist"] = None
+
+    def train(self, mode=True):
+        self._bump()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._bump()
+        self.__dict__["_plans"] = {}          # device / dtype moves invalidate captured graphs
+        return super()._apply(fn, *args, **kwargs)
 
     @staticmethod
     def _fill(x_s, am_s, pm_s, outputs, attn_mask, pad_u8):

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Tiny driver for `ncu --set full`: launches each hot kernel a few times on the C2 shapes."""
+import math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from conformer_pytorch_lightning_b200 import _native as N, ops
+
+M, d, F = 15872, 256, 2048
+dev = "cuda"
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+torch.manual_seed(0)
+if which == "gemm":
+    y = torch.randn(M, d, device=dev).bfloat16()
+    w1 = (torch.randn(F, d, device=dev) / 16).bfloat16(); b1 = torch.randn(F, device=dev)
+    w2 = (torch.randn(d, F, device=dev) / 45).bfloat16(); b2 = torch.randn(d, device=dev)
+    h = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(M, d, device=dev)
+    wo = (torch.randn(d, d, device=dev) / 16).bfloat16()
+    for _ in range(3):
+        ops.gemm(y, w1, b1, h, N.EPI_BIAS_SILU)
+        ops.gemm(h, w2, b2, x, N.EPI_RESIDUAL, residual=x, alpha=0.5)
+        ops.gemm(y, wo, b2, x, N.EPI_RESIDUAL, residual=x, alpha=1.0)
+elif which == "attn":
+    B, T, H = 64, 248, 4
+    qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
+    out = torch.empty(B, T, H * 64, device=dev, dtype=torch.bfloat16)
+    mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
+    for _ in range(3):
+        ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, mask=mask, scale=0.125)
+elif which == "dwconv":
+    B, T = 64, 248
+    x = torch.randn(B, T, d, device=dev).bfloat16(); y = torch.empty_like(x)
+    w = torch.randn(15, d, device=dev); b = torch.randn(d, device=dev)
+    for _ in range(3):
+        ops.dwconv(x, w, b, y)
+torch.cuda.synchronize()
+print("done")
