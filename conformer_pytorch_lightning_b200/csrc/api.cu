@@ -56,6 +56,31 @@ extern "C" int cfm_gemm(const void* A, int lda, const void* W, const float* bias
   return gemm_simt(A, lda, W, bias, C, ldc, M, N, K, dtype, epilogue, residual, alpha, row_valid, st);
 }
 
+extern "C" int cfm_gemm_ln(const void* A, int lda, const void* W, const float* bias, float* X, int ldx, int M, int N,
+                           int K, int dtype, float alpha, const uint8_t* row_valid, const float* g1, const float* b1,
+                           const float* g2, const float* b2, void* Y, int ldy, const uint8_t* y_row_valid, float eps,
+                           int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(A && W && X && Y && g1 && b1, "cfm_gemm_ln: null A/W/X/Y/g1/b1");
+  CFM_CHECK_ARG((g2 == nullptr) == (b2 == nullptr), "cfm_gemm_ln: g2/b2 must both be set or both null");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_gemm_ln: bad dtype %d", dtype);
+  CFM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lda >= K && ldx >= N && ldy >= N, "cfm_gemm_ln: bad shape");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fused_ok = gemm_tc_ln_supported(lda, ldx, ldy, M, N, K, dtype);
+  if (engine == CFM_ENGINE_TC)
+    CFM_CHECK_ARG(fused_ok, "cfm_gemm_ln: fused tcgen05 path does not support M=%d N=%d K=%d dtype=%d", M, N, K, dtype);
+  if (fused_ok && engine != CFM_ENGINE_SIMT)
+    return gemm_tc_ln(A, lda, W, bias, X, ldx, X, M, N, K, alpha, row_valid, g2 ? 2 : 1, g1, b1, g2, b2, Y, ldy,
+                      y_row_valid, eps, CFM_EPI_RESIDUAL, nullptr, 0, st);
+  // unfused: residual GEMM then the standalone LayerNorm kernel (which needs contiguous rows)
+  CFM_CHECK_ARG(ldx == N && ldy == N, "cfm_gemm_ln: the unfused path needs contiguous X and Y rows");
+  int rc = cfm_gemm(A, lda, W, bias, X, ldx, M, N, K, dtype, CFM_EPI_RESIDUAL, X, alpha, row_valid,
+                    engine == CFM_ENGINE_SIMT ? CFM_ENGINE_SIMT : CFM_ENGINE_AUTO, stream);
+  if (rc != 0) return rc;
+  return cfm_layernorm(X, M, N, g1, b1, g2 ? X : nullptr, g2, b2, Y, dtype, y_row_valid, eps, stream);
+}
+
 extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                              const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
                              const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,

@@ -122,6 +122,12 @@ int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, i
             int K, int dtype, int epilogue, const float* residual, float alpha,
             const uint8_t* row_valid, cudaStream_t st);
 int gemm_tc_init();
+// RESIDUAL epilogue with fused LayerNorm(s) (ln_mode 1 or 2); needs N == 256 (one tile per row)
+bool gemm_tc_ln_supported(int lda, int ldx, int ldy, int M, int N, int K, int dtype);
+int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* X, int ldx, const float* residual, int M,
+               int N, int K, float alpha, const uint8_t* row_valid, int ln_mode, const float* g1, const float* b1,
+               const float* g2, const float* b2, void* Y, int ldy, const uint8_t* y_row_valid, float eps, int epilogue,
+               void* Cact, int ldc, cudaStream_t st);
 
 int attention_simt(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                    const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,

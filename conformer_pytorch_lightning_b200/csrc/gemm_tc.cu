@@ -7,11 +7,18 @@
 //   warp 1 (1 thread)  MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two TMEM
 //                      accumulator buffers; tcgen05.commit releases the smem slot / publishes the tile
 //   warp 2             TMEM allocator (2 x BN fp32 columns)
-//   warps 4-7          epilogue: tcgen05.ld 32x32b (thread = output row), bias + SiLU / GLU / residual(+row
-//                      mask) in registers, 16-byte global stores.  Runs concurrently with the main loop of
-//                      the next tile thanks to the double-buffered accumulator.
-// Replaces the nn.Linear / 1x1 Conv1d calls of feedforward.py:17-20, attention.py:62-64,99 and
-// convolution.py:41-42,46 of the reference together with the elementwise ops that follow them.
+//   warps 4-7          epilogue, thread = output row (tcgen05.ld 32x32b).  All global traffic of the epilogue is
+//                      bulk-asynchronous: results are written into 128-byte-swizzled staging tiles in shared
+//                      memory and leave through TMA stores; the fp32 residual tile arrives through TMA loads that
+//                      are prefetched while the main loop is still running.
+// Epilogues:
+//   BIAS / BIAS_SILU / BIAS_GLU  -> bf16 activations                       (feedforward.py:17-18, attention.py:62-64,
+//                                                                           convolution.py:41-42)
+//   RESIDUAL                     -> X = R + alpha * rowmask(acc + bias)     (encoder_layer.py:58,62,66,69)
+//   RESIDUAL + LN  (N == tile)   -> additionally y = LN(X) (bf16, optional row mask), or X = LN1(.), y = LN2(X):
+//                                   the LayerNorms of encoder_layer.py:59,63,67,70 / 56 fused into the producing GEMM;
+//                                   row statistics are thread-local because a thread owns a whole output row, and the
+//                                   pre-norm row is parked in the tile's own TMEM accumulator between the passes.
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 
@@ -34,8 +41,8 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = encode_tiled_fn();
   CFM_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[3];
@@ -43,12 +50,19 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   cuuint32_t bx[3], es[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CFM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
                 (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
   return 0;
+}
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace tc
@@ -61,43 +75,57 @@ constexpr int BM = 128;       // rows per tile  = UMMA M
 constexpr int BK = 64;        // K per stage    = one 128-byte swizzle atom of bf16
 constexpr int UK = 16;        // K per tcgen05.mma (bf16)
 constexpr int kThreads = 256;
+constexpr int kBufBytes = 128 * 128;   // one staging tile: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
+constexpr int kMaxSmem = 232448;
 
-template <int BN> struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+template <int BN, bool RESID> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBufs = RESID ? 4 : 2;                      // epilogue staging ring
+  static constexpr int kParamFloats = RESID ? 5 * BN : BN;         // bias (+ LN gammas/betas)
+  static constexpr int kFixed = kBufs * kBufBytes + kParamFloats * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int kStages = (kMaxSmem - kFixed) / kStageBytes > 6 ? 6 : (kMaxSmem - kFixed) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kSmemBytes <= kMaxSmem, "shared memory budget exceeded");
 };
 
 struct GemmParams {
   const float* bias;
-  void* C;
-  const float* residual;
-  const uint8_t* row_valid;
-  float alpha;
-  int ldc, M, N, K;      // N = number of OUTPUT columns (GLU: W has 2N rows)
+  const uint8_t* row_valid;     // RESIDUAL: rows whose GEMM result is forced to 0 (pad mask)
+  const uint8_t* y_row_valid;   // LN modes: rows of y forced to 0
+  const float* g1; const float* b1; const float* g2; const float* b2;
+  float alpha, eps;
+  int M, N, K;                  // N = number of OUTPUT columns (GLU: W has 2N rows)
+  int ln_mode;                  // 0 none, 1 y = LN1(X), 2 X = LN1(.), y = LN2(X)
 };
 
-template <int EPI> __device__ __forceinline__ float epi_act(float v) {
-  if constexpr (EPI == CFM_EPI_BIAS_SILU) return silu_fast(v);
-  return v;
-}
+// byte offset of 16-byte chunk j of row r inside a 128B-swizzled [128 x 128 B] tile
+__device__ __forceinline__ uint32_t sw_off(int r, int j) { return r * 128 + (((j ^ r) & 7) << 4); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
-  using C = Cfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmC,   // F1: bf16 output; RESIDUAL: fp32 X store
+               const __grid_constant__ CUtensorMap tmR,   // RESIDUAL: fp32 residual load
+               const __grid_constant__ CUtensorMap tmY,   // LN modes: bf16 y store
+               const GemmParams p) {
   constexpr bool GLU = (EPI == CFM_EPI_BIAS_GLU);
+  constexpr bool RESID = (EPI == CFM_EPI_RESIDUAL);
+  using C = Cfg<BN, RESID>;
   constexpr int OUT_BN = GLU ? BN / 2 : BN;      // output columns per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* ring = smem + C::kStages * C::kStageBytes;                       // kBufs x 16 KB, 1024-aligned
+  float* sparam = reinterpret_cast<float*>(ring + C::kBufs * kBufBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sparam + C::kParamFloats);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;    // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;              // [kBufs] residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + C::kBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BM - 1) / BM;
@@ -108,10 +136,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
+    prefetch_tmap(&tmC);
+    if constexpr (RESID) { prefetch_tmap(&tmR); if (p.ln_mode) prefetch_tmap(&tmY); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 128); }
+    for (int s = 0; s < C::kBufs; ++s) mbar_init(res_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -167,76 +198,224 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue (128 threads, thread = output row) =====================
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;                      // row inside the tile
+    const int et = threadIdx.x - 128;                 // 0..127
+    const bool elected = (et == 0);
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t ring_phase = 0;                          // bit b = parity of the next completion of res_bar[b]
+    int sub_cnt = 0;                                  // F1: running staging-buffer counter
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * OUT_BN;
-      const int row = m0 + q * 32 + lane;
+      const int row = m0 + r;
       const bool row_ok = row < p.M;
-      mbar_wait(tfull_bar + acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      bool valid = true;
-      if constexpr (EPI == CFM_EPI_RESIDUAL) valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
+      const uint32_t taddr = tmem_base + lane_base + acc * BN;
+
+      // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync)
+      for (int i = et; i < OUT_BN; i += 128) {
+        sparam[i] = p.bias ? p.bias[n0 + i] : 0.f;
+        if constexpr (GLU) sparam[OUT_BN + i] = p.bias ? p.bias[p.N + n0 + i] : 0.f;
+        if constexpr (RESID) {
+          if (p.ln_mode >= 1) { sparam[BN + i] = p.g1[i]; sparam[2 * BN + i] = p.b1[i]; }
+          if (p.ln_mode == 2) { sparam[3 * BN + i] = p.g2[i]; sparam[4 * BN + i] = p.b2[i]; }
+        }
+      }
+
+      if constexpr (!RESID) {
+        // ---------------- bf16 activations: 64-column sub-tiles through a 2-deep staging ring + TMA store
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < OUT_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        [[maybe_unused]] uint32_t g[32];
-        if constexpr (GLU) tmem_ld32(taddr + OUT_BN + c * 32, g);
-        tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (row_ok) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        for (int sub = 0; sub < OUT_BN / 64; ++sub, ++sub_cnt) {
+          uint8_t* buf = ring + (sub_cnt & 1) * kBufBytes;
+          if (elected) bulk_wait_read<1>();            // the store issued two sub-tiles ago has left this buffer
+          named_bar_sync(1, 128);                      // (also publishes sparam on the first sub-tile)
+          uint32_t v[64];
+          {
+            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+            tmem_ld32(taddr + sub * 64, v0);
+            tmem_ld32(taddr + sub * 64 + 32, v1);
           }
+          [[maybe_unused]] uint32_t g[GLU ? 64 : 1];
           if constexpr (GLU) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.N + n + j));
-              f[j] *= sigmoid_fast(__uint_as_float(g[j]) + b4.x);
-              f[j + 1] *= sigmoid_fast(__uint_as_float(g[j + 1]) + b4.y);
-              f[j + 2] *= sigmoid_fast(__uint_as_float(g[j + 2]) + b4.z);
-              f[j + 3] *= sigmoid_fast(__uint_as_float(g[j + 3]) + b4.w);
-            }
+            uint32_t (&g0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&g[0]);
+            uint32_t (&g1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&g[32]);
+            tmem_ld32(taddr + OUT_BN + sub * 64, g0);
+            tmem_ld32(taddr + OUT_BN + sub * 64 + 32, g1);
           }
-          if constexpr (EPI == CFM_EPI_RESIDUAL) {
-            const size_t off = (size_t)row * p.ldc + n;
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
-            const float a = valid ? p.alpha : 0.f;
+          tmem_ld_wait();
+          const float* bs = sparam + sub * 64;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = r4[j];
-              r.x = fmaf(a, f[4 * j], r.x);
-              r.y = fmaf(a, f[4 * j + 1], r.y);
-              r.z = fmaf(a, f[4 * j + 2], r.z);
-              r.w = fmaf(a, f[4 * j + 3], r.w);
-              o4[j] = r;
+          for (int j = 0; j < 8; ++j) {                // 8 x 16-byte chunks = 64 bf16
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(v[8 * j + e]) + bs[8 * j + e];
+              if constexpr (EPI == CFM_EPI_BIAS_SILU) x = silu_fast(x);
+              if constexpr (GLU) x *= sigmoid_fast(__uint_as_float(g[8 * j + e]) + bs[OUT_BN + 8 * j + e]);
+              f[e] = x;
             }
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + n);
+            *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
+                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (elected) {
+            tma_store_2d(&tmC, buf, n0 + sub * 64, m0);   // rows >= M are clipped by the tensor map
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar + acc);
+      } else {
+        // ---------------- fp32 residual stream (+ fused LayerNorms)
+        constexpr int NCH = BN / 32;                   // 32-column fp32 chunks per row
+        constexpr int R = C::kBufs;
+        const int ln = p.ln_mode;
+        // prefetch the first R residual chunks; they land while the main loop of this tile is still running
+        if (elected) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              o[j] = make_uint4(pack_bf16x2(epi_act<EPI>(f[8 * j]), epi_act<EPI>(f[8 * j + 1])),
-                                pack_bf16x2(epi_act<EPI>(f[8 * j + 2]), epi_act<EPI>(f[8 * j + 3])),
-                                pack_bf16x2(epi_act<EPI>(f[8 * j + 4]), epi_act<EPI>(f[8 * j + 5])),
-                                pack_bf16x2(epi_act<EPI>(f[8 * j + 6]), epi_act<EPI>(f[8 * j + 7])));
+          for (int c = 0; c < (NCH < R ? NCH : R); ++c) {
+            mbar_expect_tx(res_bar + c, kBufBytes);
+            tma_load_2d(ring + c * kBufBytes, &tmR, res_bar + c, n0 + c * 32, m0);
+          }
+        }
+        const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
+        const float a = valid ? p.alpha : 0.f;
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
+        named_bar_sync(1, 128);                        // sparam visible
+        float s1 = 0.f, s2 = 0.f;
+        // ---- pass 1: v = R + alpha*(acc + bias)
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int b = c % R;
+          uint8_t* buf = ring + b * kBufBytes;
+          mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
+          ring_phase ^= (1u << b);
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const float* bs = sparam + c * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
+            float4 x = *cell;
+            x.x = fmaf(a, __uint_as_float(v[4 * j]) + bs[4 * j], x.x);
+            x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], x.y);
+            x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], x.z);
+            x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], x.w);
+            s1 += (x.x + x.y) + (x.z + x.w);
+            s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+            v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+            v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+            if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
+          }
+          if (ln != 0) tmem_st32(taddr + c * 32, v);   // park the pre-norm row in our accumulator columns
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (elected) {
+            if (ln != 2) {
+              tma_store_2d(&tmC, buf, n0 + c * 32, m0);
+              bulk_commit();
+              // refill the PREVIOUS chunk's buffer once its store has finished reading it
+              if (c >= 1 && c - 1 + R < NCH) {
+                bulk_wait_read<1>();
+                const int pb = (c - 1) % R;
+                mbar_expect_tx(res_bar + pb, kBufBytes);
+                tma_load_2d(ring + pb * kBufBytes, &tmR, res_bar + pb, n0 + (c - 1 + R) * 32, m0);
+              }
+            } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
+              mbar_expect_tx(res_bar + b, kBufBytes);
+              tma_load_2d(buf, &tmR, res_bar + b, n0 + (c + R) * 32, m0);
             }
           }
         }
+        if (ln != 0) {
+          tmem_st_wait();
+          const float inv_n = 1.0f / BN;
+          float mean = s1 * inv_n;
+          float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
+          if (elected) bulk_wait_read<0>();
+          named_bar_sync(1, 128);                      // every staging buffer is free again
+          int nbuf = 0;
+          if (ln == 2) {
+            // ---- pass 2 (double LN): X = LN1(v) -> TMEM + fp32 TMA store, statistics of X
+            s1 = 0.f; s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c, ++nbuf) {
+              uint8_t* buf = ring + (nbuf % R) * kBufBytes;
+              if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(1, 128); }
+              uint32_t v[32];
+              tmem_ld32(taddr + c * 32, v);
+              tmem_ld_wait();
+              const float* g = sparam + BN + c * 32;
+              const float* be = sparam + 2 * BN + c * 32;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 x;
+                x.x = fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g[4 * j], be[4 * j]);
+                x.y = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g[4 * j + 1], be[4 * j + 1]);
+                x.z = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g[4 * j + 2], be[4 * j + 2]);
+                x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g[4 * j + 3], be[4 * j + 3]);
+                s1 += (x.x + x.y) + (x.z + x.w);
+                s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+                v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+                v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+                *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
+              }
+              tmem_st32(taddr + c * 32, v);
+              fence_proxy_async_smem();
+              named_bar_sync(1, 128);
+              if (elected) { tma_store_2d(&tmC, buf, n0 + c * 32, m0); bulk_commit(); }
+            }
+            tmem_st_wait();
+            mean = s1 * inv_n;
+            rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
+          }
+          // ---- final pass: y = LN(X) as bf16 (64-column sub-tiles), optional row mask
+          const float* g = sparam + (ln == 2 ? 3 * BN : BN);
+          const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
+          const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
+#pragma unroll 1
+          for (int sub = 0; sub < BN / 64; ++sub, ++nbuf) {
+            uint8_t* buf = ring + (nbuf % R) * kBufBytes;
+            if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(1, 128); }
+            uint32_t v[64];
+            {
+              uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+              uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+              tmem_ld32(taddr + sub * 64, v0);
+              tmem_ld32(taddr + sub * 64 + 32, v1);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int col = sub * 64 + 8 * j + e;
+                const float y = fmaf((__uint_as_float(v[8 * j + e]) - mean) * rstd, g[col], be[col]);
+                f[e] = ykeep ? y : 0.f;
+              }
+              *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (elected) { tma_store_2d(&tmY, buf, sub * 64, m0); bulk_commit(); }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar + acc);
+        // the staging ring must be drained before the next tile's residual prefetch overwrites it
+        if (elected) bulk_wait_read<0>();
+        named_bar_sync(1, 128);
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar + acc);
     }
+    if (elected) bulk_wait_all<0>();                   // all bulk stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -245,8 +424,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int EPI>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+              const CUtensorMap& tmY, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL>;
   static bool attr_set = false;
   if (!attr_set) {
     CFM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -255,7 +435,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& 
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmW, p);
+  gemm_tc_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmW, tmC, tmR, tmY, p);
   CFM_LAUNCHED();
   return 0;
 }
@@ -265,6 +445,15 @@ inline int pick_bn(int N, int epilogue) {
   if (epilogue == CFM_EPI_BIAS_GLU) return 256;          // 128 value + 128 gate columns
   return (N % 256 == 0) ? 256 : 128;
 }
+
+int make_2d(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, int ld, int box_rows) {
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t str[1] = {(uint64_t)ld * (f32 ? 4 : 2)};
+  const uint32_t box[2] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)box_rows};
+  return f32 ? tc::make_tmap_f32(tm, base, 2, dims, str, box) : tc::make_tmap_bf16(tm, base, 2, dims, str, box);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -277,48 +466,67 @@ bool gemm_tc_supported(int lda, int ldc, int M, int N, int K, int dtype, int epi
   return true;
 }
 
+bool gemm_tc_ln_supported(int lda, int ldx, int ldy, int M, int N, int K, int dtype) {
+  return gemm_tc_supported(lda, ldx, M, N, K, dtype, CFM_EPI_RESIDUAL) && N == 256 && ldy % 8 == 0;
+}
+
 int gemm_tc_init() {
   tc::encode_tiled_fn();
   return 0;
 }
 
-int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N, int K, int dtype,
-            int epilogue, const float* residual, float alpha, const uint8_t* row_valid, cudaStream_t st) {
-  CFM_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(C) & 15) == 0,
-                "cfm_gemm(tc): A/W/C must be 16-byte aligned");
-  CFM_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "cfm_gemm(tc): bias must be 16-byte aligned");
+int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* X, int ldx, const float* residual, int M,
+               int N, int K, float alpha, const uint8_t* row_valid, int ln_mode, const float* g1, const float* b1,
+               const float* g2, const float* b2, void* Y, int ldy, const uint8_t* y_row_valid, float eps, int epilogue,
+               void* Cact, int ldc, cudaStream_t st) {
+  // common launcher: epilogue == RESIDUAL uses (X, residual, ln_*), otherwise (Cact, ldc)
+  CFM_CHECK_ARG(aligned16(A) && aligned16(W), "cfm_gemm(tc): A/W must be 16-byte aligned");
   const int bn = pick_bn(N, epilogue);
   const int w_rows = (epilogue == CFM_EPI_BIAS_GLU) ? 2 * N : N;
-  CUtensorMap tmA, tmW;
-  {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t str[1] = {(uint64_t)lda * 2};
-    const uint32_t box[2] = {BK, BM};
-    int rc = tc::make_tmap_bf16(&tmA, A, 2, dims, str, box);
-    if (rc) return rc;
+  CUtensorMap tmA, tmW, tmC, tmR, tmY;
+  int rc;
+  if ((rc = make_2d(&tmA, false, A, M, K, lda, BM)) != 0) return rc;
+  if ((rc = make_2d(&tmW, false, W, w_rows, K, K, (epilogue == CFM_EPI_BIAS_GLU) ? 128 : bn)) != 0) return rc;
+  GemmParams p{};
+  p.bias = bias; p.row_valid = row_valid; p.y_row_valid = y_row_valid;
+  p.g1 = g1; p.b1 = b1; p.g2 = g2; p.b2 = b2;
+  p.alpha = alpha; p.eps = eps; p.M = M; p.N = N; p.K = K; p.ln_mode = ln_mode;
+  if (epilogue == CFM_EPI_RESIDUAL) {
+    CFM_CHECK_ARG(aligned16(X) && aligned16(residual), "cfm_gemm(tc): X/residual must be 16-byte aligned");
+    if ((rc = make_2d(&tmC, true, X, M, N, ldx, BM)) != 0) return rc;
+    if ((rc = make_2d(&tmR, true, residual, M, N, ldx, BM)) != 0) return rc;
+    tmY = tmC;
+    if (ln_mode != 0) {
+      CFM_CHECK_ARG(N == bn, "cfm_gemm_ln(tc): fused LayerNorm needs the whole row in one tile (N=%d, tile %d)", N, bn);
+      CFM_CHECK_ARG(aligned16(Y) && ldy % 8 == 0, "cfm_gemm_ln(tc): Y must be 16-byte aligned with ldy %% 8 == 0");
+      if ((rc = make_2d(&tmY, false, Y, M, N, ldy, BM)) != 0) return rc;
+    }
+    if (bn == 256) return launch_tc<256, CFM_EPI_RESIDUAL>(tmA, tmW, tmC, tmR, tmY, p, st);
+    return launch_tc<128, CFM_EPI_RESIDUAL>(tmA, tmW, tmC, tmR, tmY, p, st);
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)w_rows};
-    const uint64_t str[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {BK, (uint32_t)((epilogue == CFM_EPI_BIAS_GLU) ? 128 : bn)};
-    int rc = tc::make_tmap_bf16(&tmW, W, 2, dims, str, box);
-    if (rc) return rc;
-  }
-  GemmParams p{bias, C, residual, row_valid, alpha, ldc, M, N, K};
+  CFM_CHECK_ARG(aligned16(Cact), "cfm_gemm(tc): C must be 16-byte aligned");
+  if ((rc = make_2d(&tmC, false, Cact, M, N, ldc, BM)) != 0) return rc;
+  tmR = tmC; tmY = tmC;
   if (bn == 256) {
     switch (epilogue) {
-      case CFM_EPI_BIAS: return launch_tc<256, CFM_EPI_BIAS>(tmA, tmW, p, st);
-      case CFM_EPI_BIAS_SILU: return launch_tc<256, CFM_EPI_BIAS_SILU>(tmA, tmW, p, st);
-      case CFM_EPI_BIAS_GLU: return launch_tc<256, CFM_EPI_BIAS_GLU>(tmA, tmW, p, st);
-      default: return launch_tc<256, CFM_EPI_RESIDUAL>(tmA, tmW, p, st);
+      case CFM_EPI_BIAS: return launch_tc<256, CFM_EPI_BIAS>(tmA, tmW, tmC, tmR, tmY, p, st);
+      case CFM_EPI_BIAS_SILU: return launch_tc<256, CFM_EPI_BIAS_SILU>(tmA, tmW, tmC, tmR, tmY, p, st);
+      default: return launch_tc<256, CFM_EPI_BIAS_GLU>(tmA, tmW, tmC, tmR, tmY, p, st);
     }
   }
   switch (epilogue) {
-    case CFM_EPI_BIAS: return launch_tc<128, CFM_EPI_BIAS>(tmA, tmW, p, st);
-    case CFM_EPI_BIAS_SILU: return launch_tc<128, CFM_EPI_BIAS_SILU>(tmA, tmW, p, st);
-    default: return launch_tc<128, CFM_EPI_RESIDUAL>(tmA, tmW, p, st);
+    case CFM_EPI_BIAS: return launch_tc<128, CFM_EPI_BIAS>(tmA, tmW, tmC, tmR, tmY, p, st);
+    default: return launch_tc<128, CFM_EPI_BIAS_SILU>(tmA, tmW, tmC, tmR, tmY, p, st);
   }
+}
+
+int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N, int K, int dtype,
+            int epilogue, const float* residual, float alpha, const uint8_t* row_valid, cudaStream_t st) {
+  if (epilogue == CFM_EPI_RESIDUAL)
+    return gemm_tc_ln(A, lda, W, bias, (float*)C, ldc, residual, M, N, K, alpha, row_valid, 0, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, 0, nullptr, 0.f, epilogue, nullptr, 0, st);
+  return gemm_tc_ln(A, lda, W, bias, nullptr, 0, nullptr, M, N, K, alpha, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, 0, nullptr, 0.f, epilogue, C, ldc, st);
 }
 
 }  // namespace cfm

@@ -4,10 +4,12 @@ This is the host-side schedule of the hot path (reference: encoder_layer.py:49-7
 modules it calls).  All tensors handled here are 2-D ``(N = B*T, channels)`` row-major
 device buffers; the residual stream ``x`` is fp32 and is updated *in place* by GEMM
 epilogues, GEMM operands are in the compute dtype (fp32 or bf16).  Per layer the
-schedule is 15 native launches:
+schedule is:
 
-    LN | W1+SiLU | W2+0.5*res | LN | QKV | flash-attn | Wo+res | LN+mask | PW1+GLU |
-    dwconv+BN+SiLU | PW2+mask+res | LN | W1+SiLU | W2+0.5*res | LN_final(+LN of next layer)
+    W1+SiLU | W2+0.5*res+LN_mha | QKV | flash-attn | Wo+res+LN_conv(+mask) | PW1+GLU |
+    dwconv+BN+SiLU | PW2+mask+res+LN_ff | W1+SiLU | W2+0.5*res+LN_final+LN_ffm(next layer)
+
+(11 launches; each LayerNorm rides in the epilogue of the residual GEMM that produces its input)
 
 Derived weights (bf16 copies, fused QKV with pos_bias_u folded into the q bias, the
 BatchNorm-folded depthwise filter) are caches keyed on parameter versions; the
@@ -152,12 +154,22 @@ def conv_weights(m, dtype):
 
 
 # --------------------------------------------------------------------------- module chains
-def ffn_into(x, y, W, alpha, ws):
+def _residual_gemm(a, w, bias, x, alpha, row_valid, ln):
+    """x += alpha * rowmask(a w^T + bias), optionally with the LayerNorm(s) that follow fused in.
+    ln = None or dict(y=, g1=, b1=, g2=None, b2=None, y_row_valid=None)."""
+    if ln is None:
+        ops.gemm(a, w, bias, x, N.EPI_RESIDUAL, residual=x, alpha=alpha, row_valid=row_valid)
+    else:
+        ops.gemm_ln(a, w, bias, x, ln["y"], alpha=alpha, g1=ln["g1"], b1=ln["b1"], g2=ln.get("g2"), b2=ln.get("b2"),
+                    row_valid=row_valid, y_row_valid=ln.get("y_row_valid"), eps=_LN_EPS)
+
+
+def ffn_into(x, y, W, alpha, ws, ln=None):
     """x += alpha * (w_2 silu(w_1 y + b1) + b2)   (feedforward.py:16-21 + encoder_layer.py:58,69)."""
     n = y.shape[0]
     h = ws.get("ffn_h", (n, W["w1"].shape[0]), y.dtype, y.device)
     ops.gemm(y, W["w1"], W["b1"], h, N.EPI_BIAS_SILU)
-    ops.gemm(h, W["w2"], W["b2"], x, N.EPI_RESIDUAL, residual=x, alpha=alpha)
+    _residual_gemm(h, W["w2"], W["b2"], x, alpha, None, ln)
 
 
 def _mask_u8(mask):
@@ -171,7 +183,7 @@ def _mask_u8(mask):
     return mask
 
 
-def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws):
+def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws, ln=None):
     """x += linear_out(attn(...))  (attention.py:54-100 / 148-179 + encoder_layer.py:60-62).
     Returns new_cache (B,H,Tk,128) fp32 when want_cache else None."""
     n, d = y.shape
@@ -211,11 +223,11 @@ def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws):
     ctx = ws.get("attn_ctx", (n, d), dt, dev)
     ops.attention(q, k_use, v, ctx.view(B, T, d), mask=_mask_u8(attn_mask), key_bias=key_bias,
                   scale=1.0 / math.sqrt(64.0))
-    ops.gemm(ctx, W["wo"], W["bo"], x, N.EPI_RESIDUAL, residual=x, alpha=1.0)
+    _residual_gemm(ctx, W["wo"], W["bo"], x, 1.0, None, ln)
     return new_cache
 
 
-def conv_into(x, y, B, T, W, row_valid, module, ws):
+def conv_into(x, y, B, T, W, row_valid, module, ws, ln=None):
     """x += mask(pw2(silu(bn(dw(glu(pw1(y)))))))  (convolution.py:34-49 + encoder_layer.py:64-66).
     ``y`` must already be zeroed on padded rows (done by the LayerNorm kernel's row mask)."""
     n, d = y.shape
@@ -241,7 +253,7 @@ def conv_into(x, y, B, T, W, row_valid, module, ws):
             bn.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
             bn.num_batches_tracked += 1
         ops.bn_apply_silu(raw, mean.contiguous(), torch.rsqrt(var + bn.eps).contiguous(), W["gamma"], W["beta"], c)
-    ops.gemm(c, W["w2"], W["b2"], x, N.EPI_RESIDUAL, residual=x, alpha=1.0, row_valid=row_valid)
+    _residual_gemm(c, W["w2"], W["b2"], x, 1.0, row_valid, ln)
 
 
 def _row_valid(pad_mask, B, T):
@@ -276,23 +288,25 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
         H = layer.self_attn.num_heads
         if i == 0:
             ops.layernorm(x, Wl["ffm_g"], Wl["ffm_b"], y=y)
-        ffn_into(x, y, Wl["ffm"], 0.5, ws)
-        ops.layernorm(x, Wl["mha_g"], Wl["mha_b"], y=y)
+        # every residual GEMM carries the LayerNorm that feeds the next module in its epilogue
+        ffn_into(x, y, Wl["ffm"], 0.5, ws, ln={"y": y, "g1": Wl["mha_g"], "b1": Wl["mha_b"]})
         cache = attn_caches[i] if attn_caches is not None else None
-        new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws))
-        ops.layernorm(x, Wl["conv_g"], Wl["conv_b"], y=y, row_valid=row_valid)
-        conv_into(x, y, B, T, Wl["conv"], row_valid, layer.conv_module, ws)
-        ops.layernorm(x, Wl["ff_g"], Wl["ff_b"], y=y)
-        ffn_into(x, y, Wl["ff"], 0.5, ws)
+        new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws,
+                                    ln={"y": y, "g1": Wl["conv_g"], "b1": Wl["conv_b"], "y_row_valid": row_valid}))
+        conv_into(x, y, B, T, Wl["conv"], row_valid, layer.conv_module, ws,
+                  ln={"y": y, "g1": Wl["ff_g"], "b1": Wl["ff_b"]})
         if i + 1 < len(layers):
             Wn = layers[i + 1].derived_weights(dtype)
             # norm_final of this layer chained with norm_ff_macaron of the next one
-            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x, g2=Wn["ffm_g"], b2=Wn["ffm_b"], y=y)
-        elif after_norm is not None:
-            out = torch.empty((n, d), dtype=torch.float32, device=dev)
-            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], g2=_f32(after_norm.weight), b2=_f32(after_norm.bias), y=out)
+            ffn_into(x, y, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
+                                                  "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})
         else:
-            ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x)
+            ffn_into(x, y, Wl["ff"], 0.5, ws)
+            if after_norm is not None:
+                out = torch.empty((n, d), dtype=torch.float32, device=dev)
+                ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], g2=_f32(after_norm.weight), b2=_f32(after_norm.bias), y=out)
+            else:
+                ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x)
     if not layers and after_norm is not None:
         out = torch.empty((n, d), dtype=torch.float32, device=dev)
         ops.layernorm(x, _f32(after_norm.weight), _f32(after_norm.bias), y=out)

@@ -64,6 +64,22 @@ def gemm(a, w, bias, out, epilogue, *, residual=None, alpha=1.0, row_valid=None,
     return out
 
 
+def gemm_ln(a, w, bias, x, y, *, alpha, g1, b1, g2=None, b2=None, row_valid=None, y_row_valid=None, eps=1e-5,
+            engine=N.ENGINE_AUTO):
+    """x (M,N) fp32 in place: v = x + alpha*rowmask(a @ w.T + bias); then the fused LayerNorm(s) -> x, y
+    (see cfm_gemm_ln in include/cfm_b200.h)."""
+    _req(a, "gemm_ln.a", contiguous=False)
+    _req(w, "gemm_ln.w", a.dtype)
+    _req(x, "gemm_ln.x", torch.float32, contiguous=False)
+    _req(y, "gemm_ln.y", a.dtype, contiguous=False)
+    M, K = a.shape
+    Nn = x.shape[1]
+    ensure_init(a)
+    N.check(N.lib().cfm_gemm_ln(a.data_ptr(), a.stride(0), w.data_ptr(), _ptr(bias), x.data_ptr(), x.stride(0), M, Nn, K,
+                                _DT[a.dtype], float(alpha), _ptr(row_valid), g1.data_ptr(), b1.data_ptr(), _ptr(g2),
+                                _ptr(b2), y.data_ptr(), y.stride(0), _ptr(y_row_valid), float(eps), engine, _stream(a)))
+
+
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
     """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
     mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""

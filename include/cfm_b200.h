@@ -81,6 +81,21 @@ int cfm_gemm(const void* A, int lda, const void* W, const float* bias,
              int engine, void* stream);
 
 /*
+ * Residual GEMM with the following LayerNorm(s) fused into its epilogue (in place on the residual stream X):
+ *   v = X + alpha * rowmask(A W^T + bias)                      (rowmask: rows with row_valid[row]==0 contribute 0)
+ *   g2 == NULL :  X = v            ; Y = ymask(LN(v; g1,b1))   (encoder_layer.py:58-59, 62-63, 66-67)
+ *   g2 != NULL :  X = LN(v; g1,b1) ; Y = ymask(LN(X; g2,b2))   (norm_final chained with the next layer's
+ *                                                               norm_ff_macaron, encoder_layer.py:69-70,56)
+ * X: (M,N) fp32 row stride ldx.  Y: (M,N) act dtype row stride ldy, rows with y_row_valid[row]==0 are zeroed
+ * (the masked_fill of convolution.py:36-37).  On the tcgen05 engine (bf16, N == 256) this is ONE kernel: the
+ * row statistics are thread-local in the epilogue; otherwise the library runs cfm_gemm + cfm_layernorm.
+ */
+int cfm_gemm_ln(const void* A, int lda, const void* W, const float* bias, float* X, int ldx,
+                int M, int N, int K, int dtype, float alpha, const uint8_t* row_valid,
+                const float* g1, const float* b1, const float* g2, const float* b2,
+                void* Y, int ldy, const uint8_t* y_row_valid, float eps, int engine, void* stream);
+
+/*
  * Scaled-dot-product attention with the reference's mask semantics (attention.py:84-97,
  * 160-174): scores = (q . k'_j + key_bias_j) * scale; positions whose mask byte is 0 get -inf,
  * softmax over keys, masked probabilities forced to 0 (a fully masked row yields 0), then . v.

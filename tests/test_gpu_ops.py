@@ -251,3 +251,49 @@ def test_attention_tcgen05(B, H, Tq, Tk, kind):
         empty = ~mask.any(dim=-1)
         if empty.any():
             assert float(out.float()[empty].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (333, 2048), (15872, 256), (200, 512)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_ln_fused_tcgen05(M, K, mode):
+    """Residual GEMM with the following LayerNorm(s) in its epilogue vs fp32 torch (and vs the unfused path)."""
+    dt, Nn = torch.bfloat16, 256
+    a = rnd(M, K, dtype=dt)
+    w = rnd(Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=1)
+    bias = rnd(Nn, seed=3)
+    g1, b1 = rnd(Nn, seed=4) * 0.1 + 1, rnd(Nn, seed=5) * 0.1
+    g2, b2 = (rnd(Nn, seed=6) * 0.1 + 1, rnd(Nn, seed=7) * 0.1) if mode == 2 else (None, None)
+    x0 = rnd(M, Nn, seed=8, scale=2.0)
+    rv = (torch.arange(M, device=DEV) % 3 != 1).to(torch.uint8)
+    yv = (torch.arange(M, device=DEV) % 5 != 2).to(torch.uint8)
+    F = torch.nn.functional
+    v = x0 + 0.5 * (a.float() @ w.float().t() + bias) * rv[:, None]
+    if mode == 1:
+        x_ref, y_ref = v, F.layer_norm(v, (Nn,), g1, b1, 1e-5)
+    else:
+        x_ref = F.layer_norm(v, (Nn,), g1, b1, 1e-5)
+        y_ref = F.layer_norm(x_ref, (Nn,), g2, b2, 1e-5)
+    y_ref = y_ref * yv[:, None]
+    outs = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_SIMT):
+        x = x0.clone()
+        y = torch.full((M, Nn), float("nan"), dtype=dt, device=DEV)
+        ops.gemm_ln(a, w, bias, x, y, alpha=0.5, g1=g1, b1=b1, g2=g2, b2=b2, row_valid=rv, y_row_valid=yv, engine=eng)
+        assert rel_err(x, x_ref) < 2e-5, eng
+        assert rel_err(y.float(), y_ref) < 6e-3, eng
+        assert float(y.float()[yv == 0].abs().max()) == 0.0
+        outs[eng] = (x, y)
+    assert rel_err(outs[N.ENGINE_TC][0], outs[N.ENGINE_SIMT][0]) < 2e-5
+
+
+def test_gemm_ln_fp32_unfused_path():
+    M, K, Nn = 77, 256, 256
+    a, w, bias = rnd(M, K), rnd(Nn, K, scale=1 / 16, seed=1), rnd(Nn, seed=2)
+    g1, b1 = rnd(Nn, seed=4) * 0.1 + 1, rnd(Nn, seed=5) * 0.1
+    x0 = rnd(M, Nn, seed=8)
+    x = x0.clone()
+    y = torch.empty(M, Nn, device=DEV)
+    ops.gemm_ln(a, w, bias, x, y, alpha=1.0, g1=g1, b1=b1)
+    v = x0 + a @ w.t() + bias
+    assert rel_err(x, v) < 2e-5
+    assert rel_err(y, torch.nn.functional.layer_norm(v, (Nn,), g1, b1, 1e-5)) < 2e-5
