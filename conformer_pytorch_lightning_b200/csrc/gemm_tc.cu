@@ -74,7 +74,6 @@ using namespace tc;
 constexpr int BM = 128;       // rows per tile  = UMMA M
 constexpr int BK = 64;        // K per stage    = one 128-byte swizzle atom of bf16
 constexpr int UK = 16;        // K per tcgen05.mma (bf16)
-constexpr int kThreads = 256;
 constexpr int kBufBytes = 128 * 128;   // one staging tile: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
 constexpr int kMaxSmem = 232448;
 
@@ -82,7 +81,11 @@ template <int BN, bool RESID> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBufs = RESID ? 4 : 2;                      // epilogue staging ring
+  // epilogue warps: the residual/LN epilogue keeps one thread per row (row statistics stay thread-local); the
+  // activation epilogues are MUFU/latency bound, so two warpgroups split the tile's columns (2 warps / SMSP)
+  static constexpr int kEpiThreads = RESID ? 128 : 256;
+  static constexpr int kThreads = 128 + kEpiThreads;
+  static constexpr int kBufs = 4;                                  // staging ring (2 per warpgroup for F1)
   static constexpr int kParamFloats = RESID ? 5 * BN : BN;         // bias (+ LN gammas/betas)
   static constexpr int kFixed = kBufs * kBufBytes + kParamFloats * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
   static constexpr int kStages = (kMaxSmem - kFixed) / kStageBytes > 6 ? 6 : (kMaxSmem - kFixed) / kStageBytes;
@@ -106,7 +109,7 @@ struct GemmParams {
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return r * 128 + (((j ^ r) & 7) << 4); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC,   // F1: bf16 output; RESIDUAL: fp32 X store
                const __grid_constant__ CUtensorMap tmR,   // RESIDUAL: fp32 residual load
@@ -141,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, C::kEpiThreads); }
     for (int s = 0; s < C::kBufs; ++s) mbar_init(res_bar + s, 1);
     fence_barrier_init();
   }
@@ -196,11 +199,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tfull_bar + acc);                   // accumulator complete -> epilogue
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (128 threads, thread = output row) =====================
+    // ===================== epilogue (thread = output row; F1: two warpgroups split the columns) ==============
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                      // row inside the tile
-    const int et = threadIdx.x - 128;                 // 0..127
+    const int grp = (warp - 4) >> 2;                  // epilogue warpgroup (always 0 for the residual epilogue)
+    const int et = threadIdx.x - 128 - grp * 128;     // 0..127 inside the warpgroup
     const bool elected = (et == 0);
+    const int bar_id = 1 + grp;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ring_phase = 0;                          // bit b = parity of the next completion of res_bar[b]
     int sub_cnt = 0;                                  // F1: running staging-buffer counter
@@ -212,8 +217,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + lane_base + acc * BN;
 
-      // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync)
-      for (int i = et; i < OUT_BN; i += 128) {
+      // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync); each warpgroup
+      //      stages (and later reads) only the columns it owns
+      constexpr int GCOLS = RESID ? OUT_BN : OUT_BN / 2;
+      for (int ii = et; ii < GCOLS; ii += 128) {
+        const int i = grp * GCOLS + ii;
         sparam[i] = p.bias ? p.bias[n0 + i] : 0.f;
         if constexpr (GLU) sparam[OUT_BN + i] = p.bias ? p.bias[p.N + n0 + i] : 0.f;
         if constexpr (RESID) {
@@ -227,10 +235,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int sub = 0; sub < OUT_BN / 64; ++sub, ++sub_cnt) {
-          uint8_t* buf = ring + (sub_cnt & 1) * kBufBytes;
+        for (int ss = 0; ss < OUT_BN / 128; ++ss, ++sub_cnt) {
+          const int sub = grp * (OUT_BN / 128) + ss;   // 64-column sub-tile owned by this warpgroup
+          uint8_t* buf = ring + (grp * 2 + (sub_cnt & 1)) * kBufBytes;
           if (elected) bulk_wait_read<1>();            // the store issued two sub-tiles ago has left this buffer
-          named_bar_sync(1, 128);                      // (also publishes sparam on the first sub-tile)
+          named_bar_sync(bar_id, 128);                 // (also publishes sparam on the first sub-tile)
           uint32_t v[64];
           {
             uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -261,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (elected) {
             tma_store_2d(&tmC, buf, n0 + sub * 64, m0);   // rows >= M are clipped by the tensor map
             bulk_commit();
@@ -435,7 +444,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmW, tmC, tmR, tmY, p);
+  gemm_tc_kernel<BN, EPI><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmA, tmW, tmC, tmR, tmY, p);
   CFM_LAUNCHED();
   return 0;
 }
