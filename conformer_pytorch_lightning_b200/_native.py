@@ -19,7 +19,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 # every symbol include/cfm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln",
+    "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu",
 ]
 
@@ -38,6 +38,7 @@ def _declare(lib):
     lib.cfm_layernorm.argtypes = [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _f, _p]
     lib.cfm_gemm.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _p, _i, _p]
     lib.cfm_gemm_ln.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _f, _i, _p]
+    lib.cfm_ffn.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p, _f, _p, _i, _p]
     lib.cfm_attention.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i, _i, _i, _i,
                                   _p, _i64, _i64, _p, _f, _i, _i, _p]
     lib.cfm_relpos_keys.argtypes = [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _p]

@@ -81,6 +81,34 @@ extern "C" int cfm_gemm_ln(const void* A, int lda, const void* W, const float* b
   return cfm_layernorm(X, M, N, g1, b1, g2 ? X : nullptr, g2, b2, Y, dtype, y_row_valid, eps, stream);
 }
 
+extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
+                       int ldx, int M, int d, int F, int dtype, float alpha, const float* g1, const float* be1,
+                       const float* g2, const float* be2, void* Y, int ld_out, const uint8_t* y_row_valid, float eps,
+                       void* hidden_ws, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(y && W1 && W2 && b1 && b2 && X, "cfm_ffn: null pointer");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_ffn: bad dtype %d", dtype);
+  CFM_CHECK_ARG((g1 == nullptr) == (be1 == nullptr) && (g2 == nullptr) == (be2 == nullptr) && (g1 || !g2),
+                "cfm_ffn: inconsistent LayerNorm parameters");
+  CFM_CHECK_ARG(g1 == nullptr || Y != nullptr, "cfm_ffn: LayerNorm requested but Y is null");
+  CFM_CHECK_ARG(M >= 0 && d > 0 && F > 0 && ld_in >= d && ldx >= d, "cfm_ffn: bad shape");
+  if (M == 0) return 0;
+  const int ln_mode = g1 ? (g2 ? 2 : 1) : 0;
+  const bool fused_ok = ffn_fused_supported(ld_in, ldx, ld_out, M, d, F, dtype, ln_mode);
+  if (engine == CFM_ENGINE_TC)
+    CFM_CHECK_ARG(fused_ok, "cfm_ffn: fused tcgen05 path does not support M=%d d=%d F=%d dtype=%d", M, d, F, dtype);
+  if (fused_ok && engine != CFM_ENGINE_SIMT)
+    return ffn_fused(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
+                     eps, (cudaStream_t)stream);
+  CFM_CHECK_ARG(hidden_ws != nullptr, "cfm_ffn: the unfused path needs hidden_ws");
+  int rc = cfm_gemm(y, ld_in, W1, b1, hidden_ws, F, M, F, d, dtype, CFM_EPI_BIAS_SILU, nullptr, 1.f, nullptr, engine, stream);
+  if (rc != 0) return rc;
+  if (ln_mode == 0)
+    return cfm_gemm(hidden_ws, F, W2, b2, X, ldx, M, d, F, dtype, CFM_EPI_RESIDUAL, X, alpha, nullptr, engine, stream);
+  return cfm_gemm_ln(hidden_ws, F, W2, b2, X, ldx, M, d, F, dtype, alpha, nullptr, g1, be1, g2, be2, Y, ld_out, y_row_valid,
+                     eps, engine == CFM_ENGINE_TC ? CFM_ENGINE_AUTO : engine, stream);
+}
+
 extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                              const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
                              const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,

@@ -1,0 +1,293 @@
+// Fused macaron feed-forward for sm_100a (d = 256):
+//     X += alpha * ( W2 . silu(W1 . y + b1) + b2 )        [+ the LayerNorm(s) that follow, in the same kernel]
+// replacing w_1 -> SiLU -> w_2 of feedforward.py:16-21 plus encoder_layer.py:58-59 / 69-70,56 of the reference.
+// The (tokens x 2048) hidden activation never leaves the SM: per 128-token tile the hidden dimension is walked in
+// chunks of 128 units,
+//     S_c = y . W1_c^T        tcgen05.mma M=128 N=128 K=256   -> TMEM S[c&1]   (double buffered)
+//     H_c = silu(S_c + b1_c)  8 epilogue warps: tcgen05.ld -> tanh.approx -> bf16 -> swizzled smem (A operand)
+//     Y  += H_c . W2_c^T      tcgen05.mma M=128 N=2x128 K=128 -> TMEM Y (256 columns, lives for the whole tile)
+// and the tensor pipe alternates G1(c+2) / G2(c) so that the SiLU of chunk c+1 overlaps both.  Weights stream
+// through a ring of 16 KB TMA pieces (128 rows x 64 k, 128-byte swizzle); the input tile y (64 KB) is loaded once.
+// The final epilogue is the shared residual/LayerNorm epilogue (resid_epilogue.cuh) on the Y accumulator; its
+// staging ring aliases the H buffers, which are dead by then.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-11: epilogue (two warpgroups,
+//   each owning 64 of the 128 hidden columns of a chunk; warpgroup 0 alone runs the final residual epilogue).
+#include "cfm_common.cuh"
+#include "tc_common.cuh"
+#include "resid_epilogue.cuh"
+
+namespace cfm {
+namespace {
+
+using namespace tc;
+
+constexpr int D = 256;          // model dim = K of GEMM1 = N of GEMM2
+constexpr int HC = 128;         // hidden units per chunk
+constexpr int BM = 128;
+constexpr int kPiece = 16384;   // one weight piece: 128 rows x 64 k bf16
+constexpr int NST = 5;          // weight ring depth
+constexpr int kABytes = BM * D * 2;            // 64 KB
+constexpr int kHBytes = BM * HC * 2;           // 32 KB per H buffer
+constexpr int kThreads = 384;
+constexpr int kParamFloats = 5 * D + 2 * HC;   // residual params + double-buffered b1 chunk
+constexpr int kSmemBytes = kABytes + 2 * kHBytes + NST * kPiece + kParamFloats * 4 + 512 + 1024;
+static_assert(kSmemBytes <= 232448, "smem budget");
+static_assert(2 * kHBytes == 4 * kBufBytes, "residual staging ring aliases the two H buffers");
+
+struct FfnParams {
+  const float* b1;
+  const float* b2;
+  const float* g1; const float* be1; const float* g2; const float* be2;
+  const uint8_t* y_row_valid;
+  float alpha, eps;
+  int M, F, ln_mode;
+};
+
+// job jx of a tile: G1(c) or G2(c), ordered so the tensor pipe always has independent work while SiLU(c) runs:
+//   G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(NC-3) G1(NC-1) | G2(NC-2) G2(NC-1)
+__device__ __forceinline__ void job_of(int jx, int NC, bool& g1, int& c) {
+  if (jx < 2) { g1 = true; c = jx; }
+  else if (jx >= 2 * NC - 2) { g1 = false; c = jx - NC; }
+  else if (jx & 1) { g1 = true; c = (jx + 1) >> 1; }
+  else { g1 = false; c = (jx - 2) >> 1; }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmW1,   // W1 (F, 256) bf16, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmW2,   // W2 (256, F) bf16, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmX,    // X  (M, 256) fp32 store, box 32 x 128
+                 const __grid_constant__ CUtensorMap tmR,    // residual load (same tensor as X)
+                 const __grid_constant__ CUtensorMap tmY,    // y out (M, 256) bf16 store, box 64 x 128
+                 const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sH = sA + kABytes;                 // 2 x 32 KB; also the residual staging ring (4 x 16 KB)
+  uint8_t* sW = sH + 2 * kHBytes;             // NST x 16 KB
+  float* sparam = reinterpret_cast<float*>(sW + NST * kPiece);
+  float* sb1 = sparam + 5 * D;                // [2][HC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb1 + 2 * HC);
+  uint64_t* w_full = bars;                    // [NST]
+  uint64_t* w_empty = w_full + NST;           // [NST]
+  uint64_t* a_full = w_empty + NST;           // [1]
+  uint64_t* s_full = a_full + 1;              // [2]  S[b] accumulator complete (MMA commit)
+  uint64_t* s_empty = s_full + 2;             // [2]  S[b] drained by the 256 epilogue threads
+  uint64_t* h_full = s_empty + 2;             // [2]  H[b] written by the 256 epilogue threads
+  uint64_t* h_empty = h_full + 2;             // [2]  G2 finished reading H[b] (MMA commit)
+  uint64_t* y_full = h_empty + 2;             // [1]  all MMAs of the tile complete
+  uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (128 arrivals)
+  uint64_t* res_bar = tile_done + 1;          // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int NC = p.F / HC;
+  const int n_jobs = 2 * NC;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
+    prefetch_tmap(&tmX); prefetch_tmap(&tmR); prefetch_tmap(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    mbar_init(a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256);
+      mbar_init(h_full + s, 256); mbar_init(h_empty + s, 1);
+    }
+    mbar_init(y_full, 1);
+    mbar_init(tile_done, 128);
+    for (int s = 0; s < 4; ++s) mbar_init(res_bar + s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_y = tmem_base + 256;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      const int m0 = t * BM;
+      if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // sA / sH / ring of the previous tile are dead
+      mbar_expect_tx(a_full, kABytes);
+#pragma unroll
+      for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kPiece, &tmA, a_full, ka * 64, m0);
+      for (int jx = 0; jx < n_jobs; ++jx) {
+        bool g1; int c;
+        job_of(jx, NC, g1, c);
+        for (int pc = 0; pc < 4; ++pc) {
+          mbar_wait(w_empty + stage, phase ^ 1);
+          mbar_expect_tx(w_full + stage, kPiece);
+          if (g1) tma_load_2d(sW + stage * kPiece, &tmW1, w_full + stage, pc * 64, c * HC);
+          else    tma_load_2d(sW + stage * kPiece, &tmW2, w_full + stage, c * HC + (pc & 1) * 64, (pc >> 1) * 128);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, 128);
+    int stage = 0, phase = 0, it = 0;
+    uint32_t n_se[2] = {0, 0}, n_hf[2] = {0, 0};
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
+      mbar_wait(a_full, it & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
+      for (int jx = 0; jx < n_jobs; ++jx) {
+        bool g1; int c;
+        job_of(jx, NC, g1, c);
+        const int b = c & 1;
+        if (g1) {
+          mbar_wait(s_empty + b, (n_se[b] & 1) ^ 1);      // SiLU stage drained S[b] (two chunks ago)
+          ++n_se[b];
+          tc_fence_after();
+          for (int pc = 0; pc < 4; ++pc) {
+            mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(a_addr + pc * kPiece);
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
+            umma_commit(w_empty + stage);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(s_full + b);
+        } else {
+          mbar_wait(h_full + b, n_hf[b] & 1);             // H[b] written (and fenced) by the SiLU stage
+          ++n_hf[b];
+          tc_fence_after();
+          for (int pc = 0; pc < 4; ++pc) {
+            const int o = pc >> 1, kk = pc & 1;
+            mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + kk * kPiece);
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_y + o * 128, da + 2 * k, db + 2 * k, idesc, (c | kk | k) != 0);
+            umma_commit(w_empty + stage);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(h_empty + b);
+        }
+      }
+      umma_commit(y_full);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int grp = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128 - grp * 128;
+    const bool elected = (et == 0);
+    const int bar_id = 1 + grp;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t ring_phase = 0;
+    uint32_t n_sf[2] = {0, 0}, n_he[2] = {0, 0};
+    int it = 0;
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      const int m0 = t * BM;
+      if (it > 0 && grp == 1) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
+      if (grp == 0) resid_stage_params<D>(sparam, et, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
+      // ---- SiLU stage: S[b] -> H[b]
+      for (int c = 0; c < NC; ++c) {
+        const int b = c & 1;
+        if (et < 64) sb1[b * HC + grp * 64 + et] = p.b1[c * HC + grp * 64 + et];
+        named_bar_sync(bar_id, 128);
+        mbar_wait(s_full + b, n_sf[b] & 1);
+        ++n_sf[b];
+        tc_fence_after();
+        uint32_t v[64];
+        {
+          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          tmem_ld32(tmem_base + lane_base + b * HC + grp * 64, v0);
+          tmem_ld32(tmem_base + lane_base + b * HC + grp * 64 + 32, v1);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_empty + b);                         // S[b] may be overwritten by G1(c+2)
+        const float* bs = sb1 + b * HC + grp * 64;
+        uint4 pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[8 * j + e]) + bs[8 * j + e]);
+          pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+        mbar_wait(h_empty + b, (n_he[b] & 1) ^ 1);        // G2(c-2) finished reading H[b]
+        ++n_he[b];
+        uint8_t* hb = sH + b * kHBytes + grp * kPiece;    // this warpgroup's 64 hidden columns = one swizzle atom
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, j)) = pk[j];
+        fence_proxy_async_smem();
+        mbar_arrive(h_full + b);
+      }
+      // ---- final epilogue on Y (warpgroup 0)
+      if (grp == 0) {
+        mbar_wait(y_full, it & 1);
+        tc_fence_after();
+        if (elected) resid_prefetch<D, 4>(sH, res_bar, &tmR, 0, m0);
+        ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
+        resid_ln_epilogue<D, 4>(tmem_y + lane_base, r, m0, 0, elected, bar_id, sH, res_bar, ring_phase, sparam, &tmX,
+                                &tmR, &tmY, rp);
+        mbar_arrive(tile_done);
+      }
+    }
+    if (elected) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+int make_2d_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, int ld) {
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t str[1] = {(uint64_t)ld * (f32 ? 4 : 2)};
+  const uint32_t box[2] = {(uint32_t)(f32 ? 32 : 64), 128u};
+  return f32 ? tc::make_tmap_f32(tm, base, 2, dims, str, box) : tc::make_tmap_bf16(tm, base, 2, dims, str, box);
+}
+
+}  // namespace
+
+bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, int dtype, int ln_mode) {
+  if (dtype != CFM_BF16 || tc::encode_tiled_fn() == nullptr) return false;
+  if (d != D || F % HC != 0 || F < 2 * HC || M < 64) return false;
+  if (ld_in % 8 != 0 || ldx % 4 != 0) return false;
+  if (ln_mode != 0 && ld_out % 8 != 0) return false;
+  return true;
+}
+
+int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
+              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
+              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
+  int rc;
+  if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F)) != 0) return rc;
+  if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
+  tmY = tmA;
+  if (ln_mode != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
+  FfnParams p{b1, b2, g1, be1, g2, be2, y_row_valid, alpha, eps, M, F, ln_mode};
+  const int m_tiles = (M + BM - 1) / BM;
+  const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
+  ffn_fused_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmW1, tmW2, tmX, tmX, tmY, p);
+  CFM_LAUNCHED();
+  return 0;
+}
+
+}  // namespace cfm

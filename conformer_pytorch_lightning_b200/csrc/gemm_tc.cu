@@ -21,6 +21,7 @@
 //                                   pre-norm row is parked in the tile's own TMEM accumulator between the passes.
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
+#include "resid_epilogue.cuh"
 
 #include <mutex>
 
@@ -74,7 +75,6 @@ using namespace tc;
 constexpr int BM = 128;       // rows per tile  = UMMA M
 constexpr int BK = 64;        // K per stage    = one 128-byte swizzle atom of bf16
 constexpr int UK = 16;        // K per tcgen05.mma (bf16)
-constexpr int kBufBytes = 128 * 128;   // one staging tile: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
 constexpr int kMaxSmem = 232448;
 
 template <int BN, bool RESID> struct Cfg {
@@ -105,8 +105,6 @@ struct GemmParams {
   int ln_mode;                  // 0 none, 1 y = LN1(X), 2 X = LN1(.), y = LN2(X)
 };
 
-// byte offset of 16-byte chunk j of row r inside a 128B-swizzled [128 x 128 B] tile
-__device__ __forceinline__ uint32_t sw_off(int r, int j) { return r * 128 + (((j ^ r) & 7) << 4); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL>::kThreads), 1)
@@ -219,14 +217,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync); each warpgroup
       //      stages (and later reads) only the columns it owns
-      constexpr int GCOLS = RESID ? OUT_BN : OUT_BN / 2;
-      for (int ii = et; ii < GCOLS; ii += 128) {
-        const int i = grp * GCOLS + ii;
-        sparam[i] = p.bias ? p.bias[n0 + i] : 0.f;
-        if constexpr (GLU) sparam[OUT_BN + i] = p.bias ? p.bias[p.N + n0 + i] : 0.f;
-        if constexpr (RESID) {
-          if (p.ln_mode >= 1) { sparam[BN + i] = p.g1[i]; sparam[2 * BN + i] = p.b1[i]; }
-          if (p.ln_mode == 2) { sparam[3 * BN + i] = p.g2[i]; sparam[4 * BN + i] = p.b2[i]; }
+      if constexpr (RESID) {
+        resid_stage_params<BN>(sparam, et, p.bias, n0, p.ln_mode, p.g1, p.b1, p.g2, p.b2);
+      } else {
+        constexpr int GCOLS = OUT_BN / 2;
+        for (int ii = et; ii < GCOLS; ii += 128) {
+          const int i = grp * GCOLS + ii;
+          sparam[i] = p.bias ? p.bias[n0 + i] : 0.f;
+          if constexpr (GLU) sparam[OUT_BN + i] = p.bias ? p.bias[p.N + n0 + i] : 0.f;
         }
       }
 
@@ -279,149 +277,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(tempty_bar + acc);
       } else {
-        // ---------------- fp32 residual stream (+ fused LayerNorms)
-        constexpr int NCH = BN / 32;                   // 32-column fp32 chunks per row
-        constexpr int R = C::kBufs;
-        const int ln = p.ln_mode;
-        // prefetch the first R residual chunks; they land while the main loop of this tile is still running
-        if (elected) {
-#pragma unroll
-          for (int c = 0; c < (NCH < R ? NCH : R); ++c) {
-            mbar_expect_tx(res_bar + c, kBufBytes);
-            tma_load_2d(ring + c * kBufBytes, &tmR, res_bar + c, n0 + c * 32, m0);
-          }
-        }
-        const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
-        const float a = valid ? p.alpha : 0.f;
+        // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
+        if (elected) resid_prefetch<BN, C::kBufs>(ring, res_bar, &tmR, n0, m0);   // lands during the main loop
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
-        named_bar_sync(1, 128);                        // sparam visible
-        float s1 = 0.f, s2 = 0.f;
-        // ---- pass 1: v = R + alpha*(acc + bias)
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          const int b = c % R;
-          uint8_t* buf = ring + b * kBufBytes;
-          mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
-          ring_phase ^= (1u << b);
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const float* bs = sparam + c * 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
-            float4 x = *cell;
-            x.x = fmaf(a, __uint_as_float(v[4 * j]) + bs[4 * j], x.x);
-            x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], x.y);
-            x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], x.z);
-            x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], x.w);
-            s1 += (x.x + x.y) + (x.z + x.w);
-            s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-            v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
-            v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
-            if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
-          }
-          if (ln != 0) tmem_st32(taddr + c * 32, v);   // park the pre-norm row in our accumulator columns
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (elected) {
-            if (ln != 2) {
-              tma_store_2d(&tmC, buf, n0 + c * 32, m0);
-              bulk_commit();
-              // refill the PREVIOUS chunk's buffer once its store has finished reading it
-              if (c >= 1 && c - 1 + R < NCH) {
-                bulk_wait_read<1>();
-                const int pb = (c - 1) % R;
-                mbar_expect_tx(res_bar + pb, kBufBytes);
-                tma_load_2d(ring + pb * kBufBytes, &tmR, res_bar + pb, n0 + (c - 1 + R) * 32, m0);
-              }
-            } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
-              mbar_expect_tx(res_bar + b, kBufBytes);
-              tma_load_2d(buf, &tmR, res_bar + b, n0 + (c + R) * 32, m0);
-            }
-          }
-        }
-        if (ln != 0) {
-          tmem_st_wait();
-          const float inv_n = 1.0f / BN;
-          float mean = s1 * inv_n;
-          float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
-          if (elected) bulk_wait_read<0>();
-          named_bar_sync(1, 128);                      // every staging buffer is free again
-          int nbuf = 0;
-          if (ln == 2) {
-            // ---- pass 2 (double LN): X = LN1(v) -> TMEM + fp32 TMA store, statistics of X
-            s1 = 0.f; s2 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c, ++nbuf) {
-              uint8_t* buf = ring + (nbuf % R) * kBufBytes;
-              if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(1, 128); }
-              uint32_t v[32];
-              tmem_ld32(taddr + c * 32, v);
-              tmem_ld_wait();
-              const float* g = sparam + BN + c * 32;
-              const float* be = sparam + 2 * BN + c * 32;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 x;
-                x.x = fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g[4 * j], be[4 * j]);
-                x.y = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g[4 * j + 1], be[4 * j + 1]);
-                x.z = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g[4 * j + 2], be[4 * j + 2]);
-                x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g[4 * j + 3], be[4 * j + 3]);
-                s1 += (x.x + x.y) + (x.z + x.w);
-                s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-                v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
-                v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
-                *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
-              }
-              tmem_st32(taddr + c * 32, v);
-              fence_proxy_async_smem();
-              named_bar_sync(1, 128);
-              if (elected) { tma_store_2d(&tmC, buf, n0 + c * 32, m0); bulk_commit(); }
-            }
-            tmem_st_wait();
-            mean = s1 * inv_n;
-            rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
-          }
-          // ---- final pass: y = LN(X) as bf16 (64-column sub-tiles), optional row mask
-          const float* g = sparam + (ln == 2 ? 3 * BN : BN);
-          const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
-          const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
-#pragma unroll 1
-          for (int sub = 0; sub < BN / 64; ++sub, ++nbuf) {
-            uint8_t* buf = ring + (nbuf % R) * kBufBytes;
-            if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(1, 128); }
-            uint32_t v[64];
-            {
-              uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-              uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-              tmem_ld32(taddr + sub * 64, v0);
-              tmem_ld32(taddr + sub * 64 + 32, v1);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int col = sub * 64 + 8 * j + e;
-                const float y = fmaf((__uint_as_float(v[8 * j + e]) - mean) * rstd, g[col], be[col]);
-                f[e] = ykeep ? y : 0.f;
-              }
-              *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (elected) { tma_store_2d(&tmY, buf, sub * 64, m0); bulk_commit(); }
-          }
-        }
-        tc_fence_before();
+        ResidParams rp{p.row_valid, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
+        resid_ln_epilogue<BN, C::kBufs>(taddr, r, m0, n0, elected, bar_id, ring, res_bar, ring_phase, sparam, &tmC, &tmR,
+                                        &tmY, rp);
         mbar_arrive(tempty_bar + acc);
-        // the staging ring must be drained before the next tile's residual prefetch overwrites it
-        if (elected) bulk_wait_read<0>();
-        named_bar_sync(1, 128);
       }
     }
     if (elected) bulk_wait_all<0>();                   // all bulk stores complete before the CTA retires

@@ -1,0 +1,195 @@
+// Residual-stream epilogue shared by the tcgen05 GEMM (gemm_tc.cu) and the fused FFN kernel (ffn_fused.cu):
+//   v = R + alpha * rowmask(acc + bias)                    (encoder_layer.py:58,62,66,69 of the reference)
+//   ln_mode 0:  X = v
+//   ln_mode 1:  X = v,          y = ymask(LN(v; g1,b1))    (encoder_layer.py:59,63,67)
+//   ln_mode 2:  X = LN(v;g1,b1), y = ymask(LN(X; g2,b2))   (encoder_layer.py:70 chained with :56 of the next layer)
+// 128 threads, thread = output row: tcgen05.ld 32x32b gives each thread 32 consecutive fp32 columns of ITS row, so
+// LayerNorm statistics need no cross-thread reduction.  The fp32 residual arrives through TMA loads into a ring of
+// 128-byte-swizzled [128 x 128 B] staging tiles, X and y leave through TMA stores from the same ring, and between
+// the passes the pre-norm row is parked in the tile's own TMEM accumulator columns (tcgen05.st).
+#pragma once
+#include "cfm_common.cuh"
+#include "tc_common.cuh"
+
+namespace cfm {
+namespace tc {
+
+constexpr int kBufBytes = 128 * 128;   // one staging tile: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
+
+// byte offset of 16-byte chunk j of row r inside a 128B-swizzled [128 x 128 B] tile
+__device__ __forceinline__ uint32_t sw_off(int r, int j) { return r * 128 + (((j ^ r) & 7) << 4); }
+
+struct ResidParams {
+  const uint8_t* row_valid;     // rows whose GEMM result is forced to 0 (pad mask)
+  const uint8_t* y_row_valid;   // rows of y forced to 0
+  float alpha, eps;
+  int ln_mode;
+  int M;
+};
+
+// sparam layout: [0,BN) bias  [BN,2BN) g1  [2BN,3BN) b1  [3BN,4BN) g2  [4BN,5BN) b2
+template <int BN>
+__device__ __forceinline__ void resid_stage_params(float* sparam, int et, const float* bias, int n0, int ln_mode,
+                                                   const float* g1, const float* b1, const float* g2, const float* b2) {
+  for (int i = et; i < BN; i += 128) {
+    sparam[i] = bias ? bias[n0 + i] : 0.f;
+    if (ln_mode >= 1) { sparam[BN + i] = g1[i]; sparam[2 * BN + i] = b1[i]; }
+    if (ln_mode == 2) { sparam[3 * BN + i] = g2[i]; sparam[4 * BN + i] = b2[i]; }
+  }
+}
+
+// issue the TMA loads of the first min(R, BN/32) residual chunks (elected thread only)
+template <int BN, int R>
+__device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar, const CUtensorMap* tmR, int n0, int m0) {
+#pragma unroll
+  for (int c = 0; c < (BN / 32 < R ? BN / 32 : R); ++c) {
+    mbar_expect_tx(res_bar + c, kBufBytes);
+    tma_load_2d(ring + c * kBufBytes, tmR, res_bar + c, n0 + c * 32, m0);
+  }
+}
+
+// Body of the epilogue.  Preconditions: accumulator complete and visible (tfull waited + tcgen05 after-sync fence),
+// resid_stage_params + resid_prefetch done.  `taddr` = TMEM address of this thread's row, column 0 of the accumulator.
+// `bar_id` names a 128-thread barrier private to the calling warpgroup.  On return every TMEM access of the thread
+// has completed and all TMA stores have finished READING the ring (it may be overwritten).
+template <int BN, int R>
+__device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0, int n0, bool elected, int bar_id,
+                                                  uint8_t* ring, uint64_t* res_bar, uint32_t& ring_phase,
+                                                  const float* sparam, const CUtensorMap* tmX, const CUtensorMap* tmR,
+                                                  const CUtensorMap* tmY, const ResidParams& p) {
+  constexpr int NCH = BN / 32;                   // 32-column fp32 chunks per row
+  const int ln = p.ln_mode;
+  const int row = m0 + r;
+  const bool row_ok = row < p.M;
+  const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
+  const float a = valid ? p.alpha : 0.f;
+  named_bar_sync(bar_id, 128);                   // sparam visible
+  float s1 = 0.f, s2 = 0.f;
+  // ---- pass 1: v = R + alpha*(acc + bias)
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int b = c % R;
+    uint8_t* buf = ring + b * kBufBytes;
+    mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
+    ring_phase ^= (1u << b);
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+    tmem_ld_wait();
+    const float* bs = sparam + c * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
+      float4 x = *cell;
+      x.x = fmaf(a, __uint_as_float(v[4 * j]) + bs[4 * j], x.x);
+      x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], x.y);
+      x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], x.z);
+      x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], x.w);
+      s1 += (x.x + x.y) + (x.z + x.w);
+      s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+      v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+      v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+      if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
+    }
+    if (ln != 0) tmem_st32(taddr + c * 32, v);   // park the pre-norm row in our accumulator columns
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (elected) {
+      if (ln != 2) {
+        tma_store_2d(tmX, buf, n0 + c * 32, m0);
+        bulk_commit();
+        // refill the PREVIOUS chunk's buffer once its store has finished reading it
+        if (c >= 1 && c - 1 + R < NCH) {
+          bulk_wait_read<1>();
+          const int pb = (c - 1) % R;
+          mbar_expect_tx(res_bar + pb, kBufBytes);
+          tma_load_2d(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (c - 1 + R) * 32, m0);
+        }
+      } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
+        mbar_expect_tx(res_bar + b, kBufBytes);
+        tma_load_2d(buf, tmR, res_bar + b, n0 + (c + R) * 32, m0);
+      }
+    }
+  }
+  if (ln != 0) {
+    tmem_st_wait();
+    const float inv_n = 1.0f / BN;
+    float mean = s1 * inv_n;
+    float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
+    if (elected) bulk_wait_read<0>();
+    named_bar_sync(bar_id, 128);                 // every staging buffer is free again
+    int nbuf = 0;
+    if (ln == 2) {
+      // ---- pass 2 (double LN): X = LN1(v) -> TMEM + fp32 TMA store, statistics of X
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++nbuf) {
+        uint8_t* buf = ring + (nbuf % R) * kBufBytes;
+        if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const float* g = sparam + BN + c * 32;
+        const float* be = sparam + 2 * BN + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x;
+          x.x = fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g[4 * j], be[4 * j]);
+          x.y = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g[4 * j + 1], be[4 * j + 1]);
+          x.z = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g[4 * j + 2], be[4 * j + 2]);
+          x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g[4 * j + 3], be[4 * j + 3]);
+          s1 += (x.x + x.y) + (x.z + x.w);
+          s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+          v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+          *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
+        }
+        tmem_st32(taddr + c * 32, v);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (elected) { tma_store_2d(tmX, buf, n0 + c * 32, m0); bulk_commit(); }
+      }
+      tmem_st_wait();
+      mean = s1 * inv_n;
+      rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
+    }
+    // ---- final pass: y = LN(X) as bf16 (64-column sub-tiles), optional row mask
+    const float* g = sparam + (ln == 2 ? 3 * BN : BN);
+    const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
+    const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
+#pragma unroll 1
+    for (int sub = 0; sub < BN / 64; ++sub, ++nbuf) {
+      uint8_t* buf = ring + (nbuf % R) * kBufBytes;
+      if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
+      uint32_t v[64];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        tmem_ld32(taddr + sub * 64, v0);
+        tmem_ld32(taddr + sub * 64 + 32, v1);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = sub * 64 + 8 * j + e;
+          const float y = fmaf((__uint_as_float(v[8 * j + e]) - mean) * rstd, g[col], be[col]);
+          f[e] = ykeep ? y : 0.f;
+        }
+        *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (elected) { tma_store_2d(tmY, buf, sub * 64, m0); bulk_commit(); }
+    }
+  }
+  tc_fence_before();
+  // the staging ring must be drained before anything overwrites it (next tile's residual prefetch)
+  if (elected) bulk_wait_read<0>();
+  named_bar_sync(bar_id, 128);
+}
+
+}  // namespace tc
+}  // namespace cfm

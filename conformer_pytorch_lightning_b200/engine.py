@@ -167,9 +167,10 @@ def _residual_gemm(a, w, bias, x, alpha, row_valid, ln):
 def ffn_into(x, y, W, alpha, ws, ln=None):
     """x += alpha * (w_2 silu(w_1 y + b1) + b2)   (feedforward.py:16-21 + encoder_layer.py:58,69)."""
     n = y.shape[0]
+    # one fused kernel on the tcgen05 engine (hidden activation stays on chip); `h` is only touched by the
+    # unfused fallback inside the library (fp32 path, unsupported shapes)
     h = ws.get("ffn_h", (n, W["w1"].shape[0]), y.dtype, y.device)
-    ops.gemm(y, W["w1"], W["b1"], h, N.EPI_BIAS_SILU)
-    _residual_gemm(h, W["w2"], W["b2"], x, alpha, None, ln)
+    ops.ffn(y, W["w1"], W["b1"], W["w2"], W["b2"], x, alpha=alpha, ln=ln, hidden_ws=h)
 
 
 def _mask_u8(mask):

@@ -80,6 +80,25 @@ def gemm_ln(a, w, bias, x, y, *, alpha, g1, b1, g2=None, b2=None, row_valid=None
                                 _ptr(b2), y.data_ptr(), y.stride(0), _ptr(y_row_valid), float(eps), engine, _stream(a)))
 
 
+def ffn(y_in, w1, b1, w2, b2, x, *, alpha, ln=None, hidden_ws=None, engine=N.ENGINE_AUTO):
+    """x += alpha*(w2 silu(w1 y_in + b1) + b2) (+ fused LayerNorms, ln = dict(y,g1,b1,g2,b2,y_row_valid) or None);
+    see cfm_ffn in include/cfm_b200.h."""
+    _req(y_in, "ffn.y_in", contiguous=False)
+    _req(w1, "ffn.w1", y_in.dtype)
+    _req(w2, "ffn.w2", y_in.dtype)
+    _req(x, "ffn.x", torch.float32, contiguous=False)
+    M, d = y_in.shape
+    F = w1.shape[0]
+    ln = ln or {}
+    yo = ln.get("y")
+    ensure_init(x)
+    N.check(N.lib().cfm_ffn(y_in.data_ptr(), y_in.stride(0), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                            x.data_ptr(), x.stride(0), M, d, F, _DT[y_in.dtype], float(alpha), _ptr(ln.get("g1")),
+                            _ptr(ln.get("b1")), _ptr(ln.get("g2")), _ptr(ln.get("b2")), _ptr(yo),
+                            yo.stride(0) if yo is not None else 0, _ptr(ln.get("y_row_valid")), 1e-5, _ptr(hidden_ws),
+                            engine, _stream(x)))
+
+
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
     """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
     mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""

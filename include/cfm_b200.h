@@ -96,6 +96,20 @@ int cfm_gemm_ln(const void* A, int lda, const void* W, const float* bias, float*
                 void* Y, int ldy, const uint8_t* y_row_valid, float eps, int engine, void* stream);
 
 /*
+ * Whole macaron feed-forward on the residual stream, in place (feedforward.py:16-21 + encoder_layer.py:56-59,67-70):
+ *   X += alpha * (W2 silu(W1 y + b1) + b2), followed by the optional LayerNorm(s) exactly as in cfm_gemm_ln
+ *   (g1 == NULL: none; g2 == NULL: Y = ymask(LN(X;g1,be1)); else X = LN(.;g1,be1), Y = ymask(LN(X;g2,be2))).
+ * y: (M,d) act dtype (row stride ld_in), W1: (F,d), W2: (d,F) act dtype, b1 (F), b2 (d) fp32, X: (M,d) fp32.
+ * Y may alias y.  On the tcgen05 engine (bf16, d == 256, F % 128 == 0) this is ONE kernel and the (M,F) hidden
+ * activation stays in TMEM / shared memory; otherwise the library runs cfm_gemm (SiLU) + cfm_gemm / cfm_gemm_ln
+ * through `hidden_ws`, a caller-provided (M,F) act-dtype scratch buffer (may be NULL only if the fused path applies).
+ */
+int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2,
+            float* X, int ldx, int M, int d, int F, int dtype, float alpha,
+            const float* g1, const float* be1, const float* g2, const float* be2,
+            void* Y, int ld_out, const uint8_t* y_row_valid, float eps, void* hidden_ws, int engine, void* stream);
+
+/*
  * Scaled-dot-product attention with the reference's mask semantics (attention.py:84-97,
  * 160-174): scores = (q . k'_j + key_bias_j) * scale; positions whose mask byte is 0 get -inf,
  * softmax over keys, masked probabilities forced to 0 (a fully masked row yields 0), then . v.

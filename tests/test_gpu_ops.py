@@ -297,3 +297,54 @@ def test_gemm_ln_fp32_unfused_path():
     v = x0 + a @ w.t() + bias
     assert rel_err(x, v) < 2e-5
     assert rel_err(y, torch.nn.functional.layer_norm(v, (Nn,), g1, b1, 1e-5)) < 2e-5
+
+
+@pytest.mark.parametrize("M,F", [(128, 2048), (333, 2048), (15872, 2048), (200, 256), (20000, 512)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_ffn_fused_tcgen05(M, F, mode):
+    """Whole feed-forward (+ LayerNorms) in one kernel vs fp32 torch on the same bf16 operands, and vs the
+    unfused two-GEMM path of the library."""
+    dt, d = torch.bfloat16, 256
+    yin = rnd(M, d, dtype=dt)
+    w1 = rnd(F, d, dtype=dt, scale=1 / 16, seed=1)
+    b1 = rnd(F, seed=2) * 0.5
+    w2 = rnd(d, F, dtype=dt, scale=1 / math.sqrt(F), seed=3)
+    b2 = rnd(d, seed=4) * 0.5
+    g1, be1 = rnd(d, seed=5) * 0.1 + 1, rnd(d, seed=6) * 0.1
+    g2, be2 = rnd(d, seed=7) * 0.1 + 1, rnd(d, seed=8) * 0.1
+    x0 = rnd(M, d, seed=9, scale=2.0)
+    yv = (torch.arange(M, device=DEV) % 5 != 2).to(torch.uint8)
+    Fn = torch.nn.functional
+    h = Fn.silu(yin.float() @ w1.float().t() + b1).to(dt).float()       # hidden is rounded to bf16 on chip
+    v = x0 + 0.5 * (h @ w2.float().t() + b2)
+    ln = None
+    if mode == 0:
+        x_ref, y_ref = v, None
+    elif mode == 1:
+        x_ref, y_ref = v, Fn.layer_norm(v, (d,), g1, be1, 1e-5) * yv[:, None]
+    else:
+        x_ref = Fn.layer_norm(v, (d,), g1, be1, 1e-5)
+        y_ref = Fn.layer_norm(x_ref, (d,), g2, be2, 1e-5) * yv[:, None]
+    res = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_AUTO if False else N.ENGINE_SIMT):
+        x = x0.clone()
+        y = torch.full((M, d), float("nan"), dtype=dt, device=DEV)
+        if mode == 1:
+            ln = {"y": y, "g1": g1, "b1": be1, "y_row_valid": yv}
+        elif mode == 2:
+            ln = {"y": y, "g1": g1, "b1": be1, "g2": g2, "b2": be2, "y_row_valid": yv}
+        hws = torch.empty(M, F, dtype=dt, device=DEV)
+        ops.ffn(yin, w1, b1, w2, b2, x, alpha=0.5, ln=ln, hidden_ws=hws, engine=eng)
+        assert torch.isfinite(x).all()
+        assert rel_err(x, x_ref) < 2e-3, (eng, rel_err(x, x_ref))      # tanh.approx SiLU + bf16 hidden
+        if y_ref is not None:
+            assert rel_err(y.float(), y_ref) < 8e-3, eng
+            assert float(y.float()[yv == 0].abs().max()) == 0.0
+        res[eng] = x
+    assert rel_err(res[N.ENGINE_TC], res[N.ENGINE_SIMT]) < 2e-3
+    # in-place aliasing of the LayerNorm output with the FFN input (how the layer chain uses it)
+    if mode == 1:
+        x = x0.clone()
+        yio = yin.clone()
+        ops.ffn(yio, w1, b1, w2, b2, x, alpha=0.5, ln={"y": yio, "g1": g1, "b1": be1, "y_row_valid": yv}, engine=N.ENGINE_TC)
+        assert rel_err(x, x_ref) < 2e-3 and rel_err(yio.float(), y_ref) < 8e-3
