@@ -44,5 +44,32 @@ def main():
         print(f"{name:14s} M={M} N={wrows} K={K}: ours {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)   torch.linear(no epilogue) {tref:7.1f} us ({fl / tref / 1e6:7.1f} TF/s)")
 
 
+def ffn_bench(M=15872, d=256, F=2048):
+    dev = "cuda"
+    y = torch.randn(M, d, device=dev).bfloat16()
+    w1 = (torch.randn(F, d, device=dev) / 16).bfloat16(); b1 = torch.randn(F, device=dev)
+    w2 = (torch.randn(d, F, device=dev) / 45).bfloat16(); b2 = torch.randn(d, device=dev)
+    g = torch.ones(d, device=dev); b = torch.zeros(d, device=dev)
+    x = torch.randn(M, d, device=dev)
+    h = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    fl = 4.0 * M * d * F
+    for name, eng in (("fused", N.ENGINE_TC), ("two GEMMs", N.ENGINE_SIMT + 99)):
+        for mode, ln in (("no LN", None), ("LN", {"y": y, "g1": g, "b1": b}), ("2xLN", {"y": y, "g1": g, "b1": b, "g2": g, "b2": b})):
+            if eng == N.ENGINE_TC:
+                fn = lambda: ops.ffn(y, w1, b1, w2, b2, x, alpha=0.5, ln=ln, hidden_ws=h, engine=N.ENGINE_TC)
+            else:
+                def fn():
+                    ops.gemm(y, w1, b1, h, N.EPI_BIAS_SILU)
+                    if ln is None:
+                        ops.gemm(h, w2, b2, x, N.EPI_RESIDUAL, residual=x, alpha=0.5)
+                    else:
+                        ops.gemm_ln(h, w2, b2, x, y, alpha=0.5, g1=ln["g1"], b1=ln["b1"], g2=ln.get("g2"), b2=ln.get("b2"))
+            t = timeit(fn)
+            print(f"ffn {name:10s} {mode:6s} M={M} F={F}: {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ffn":
+        ffn_bench()
+        sys.exit(0)
     main()
