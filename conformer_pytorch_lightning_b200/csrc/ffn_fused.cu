@@ -15,6 +15,7 @@
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 #include "resid_epilogue.cuh"
+#include <stdlib.h>
 
 namespace cfm {
 namespace {
@@ -52,6 +53,10 @@ __device__ __forceinline__ void job_of(int jx, int NC, bool& g1, int& c) {
   else { g1 = false; c = (jx - 2) >> 1; }
 }
 
+// CL = thread-block cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on adjacent
+// 128-token tiles in lock-step and share every weight piece: each CTA fetches half of the piece's rows and
+// TMA-multicasts it into both CTAs' rings, halving the L2 -> SM weight traffic (2 MB per tile otherwise).
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16, box 64 x 128
                  const __grid_constant__ CUtensorMap tmW1,   // W1 (F, 256) bf16, box 64 x 128
@@ -81,16 +86,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
+  // zero-fills their loads and clips their stores) so that the shared weight ring stays in lock-step
+  const int m_tiles = ((p.M + BM - 1) / BM + CL - 1) / CL * CL;
   const int NC = p.F / HC;
   const int n_jobs = 2 * NC;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (1u << CL) - 1u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
     prefetch_tmap(&tmX); prefetch_tmap(&tmR); prefetch_tmap(&tmY);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
     mbar_init(a_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256);
@@ -104,6 +113,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
@@ -111,7 +121,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0, phase = 0, it = 0;
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // sA / sH / ring of the previous tile are dead
       mbar_expect_tx(a_full, kABytes);
@@ -121,10 +131,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         bool g1; int c;
         job_of(jx, NC, g1, c);
         for (int pc = 0; pc < 4; ++pc) {
-          mbar_wait(w_empty + stage, phase ^ 1);
+          mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
           mbar_expect_tx(w_full + stage, kPiece);
-          if (g1) tma_load_2d(sW + stage * kPiece, &tmW1, w_full + stage, pc * 64, c * HC);
-          else    tma_load_2d(sW + stage * kPiece, &tmW2, w_full + stage, c * HC + (pc & 1) * 64, (pc >> 1) * 128);
+          const int k0 = g1 ? pc * 64 : c * HC + (pc & 1) * 64;
+          const int r0 = g1 ? c * HC : (pc >> 1) * 128;
+          const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
+          if constexpr (CL == 1) {
+            tma_load_2d(sW + stage * kPiece, tm, w_full + stage, k0, r0);
+          } else {   // my half of the rows, delivered to both CTAs
+            constexpr int RH = 128 / CL;
+            tma_load_2d_mc(sW + stage * kPiece + crank * (RH * 128), tm, w_full + stage, k0, r0 + crank * RH, kMask);
+          }
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
@@ -134,7 +151,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     constexpr uint32_t idesc = umma_idesc_bf16(BM, 128);
     int stage = 0, phase = 0, it = 0;
     uint32_t n_se[2] = {0, 0}, n_hf[2] = {0, 0};
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
       mbar_wait(a_full, it & 1);
       tc_fence_after();
@@ -154,7 +171,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
-            umma_commit(w_empty + stage);
+            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
           umma_commit(s_full + b);
@@ -171,7 +188,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_y + o * 128, da + 2 * k, db + 2 * k, idesc, (c | kk | k) != 0);
-            umma_commit(w_empty + stage);
+            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
           umma_commit(h_empty + b);
@@ -191,7 +208,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     uint32_t ring_phase = 0;
     uint32_t n_sf[2] = {0, 0}, n_he[2] = {0, 0};
     int it = 0;
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
       if (it > 0 && grp == 1) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
       if (grp == 0) resid_stage_params<D>(sparam, et, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
@@ -246,13 +263,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into it / signal it
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-int make_2d_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, int ld) {
+int make_2d_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, int ld, int box_rows = 128) {
   const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
   const uint64_t str[1] = {(uint64_t)ld * (f32 ? 4 : 2)};
-  const uint32_t box[2] = {(uint32_t)(f32 ? 32 : 64), 128u};
+  const uint32_t box[2] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)box_rows};
   return f32 ? tc::make_tmap_f32(tm, base, 2, dims, str, box) : tc::make_tmap_bf16(tm, base, 2, dims, str, box);
 }
 
@@ -269,23 +287,41 @@ bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, in
 int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
               int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
               const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  static int cl_env = -1;
+  if (cl_env < 0) {
+    const char* e = getenv("CFM_B200_FFN_CLUSTER");
+    cl_env = (e && e[0] == '1') ? 1 : 2;
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
+  const int CL = cl_env;
   CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
   int rc;
   if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D, 128 / CL)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F, 128 / CL)) != 0) return rc;
   if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
   tmY = tmA;
   if (ln_mode != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
   FfnParams p{b1, b2, g1, be1, g2, be2, y_row_valid, alpha, eps, M, F, ln_mode};
-  const int m_tiles = (M + BM - 1) / BM;
-  const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
-  ffn_fused_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmW1, tmW2, tmX, tmX, tmY, p);
+  const int m_tiles = ((M + BM - 1) / BM + CL - 1) / CL * CL;
+  const int max_ctas = num_sms() / CL * CL;
+  const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
+  if (CL == 1) {
+    ffn_fused_kernel<1><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmW1, tmW2, tmX, tmX, tmY, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, ffn_fused_kernel<2>, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
+  }
   CFM_LAUNCHED();
   return 0;
 }
