@@ -20,6 +20,14 @@ if which == "gemm":
         ops.gemm(y, w1, b1, h, N.EPI_BIAS_SILU)
         ops.gemm(h, w2, b2, x, N.EPI_RESIDUAL, residual=x, alpha=0.5)
         ops.gemm(y, wo, b2, x, N.EPI_RESIDUAL, residual=x, alpha=1.0)
+elif which == "ffn":
+    y = torch.randn(M, d, device=dev).bfloat16()
+    w1 = (torch.randn(F, d, device=dev) / 16).bfloat16(); b1 = torch.randn(F, device=dev)
+    w2 = (torch.randn(d, F, device=dev) / 45).bfloat16(); b2 = torch.randn(d, device=dev)
+    g = torch.ones(d, device=dev); b = torch.zeros(d, device=dev)
+    x = torch.randn(M, d, device=dev)
+    for _ in range(3):
+        ops.ffn(y, w1, b1, w2, b2, x, alpha=0.5, ln={"y": y, "g1": g, "b1": b}, engine=N.ENGINE_TC)
 elif which == "attn":
     B, T, H = 64, 248, 4
     qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
