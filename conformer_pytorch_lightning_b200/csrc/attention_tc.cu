@@ -96,34 +96,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DK, 1);   // B = V tile, MN-major (dk contiguous)
+    // whole warp converged; one elected lane issues the async instructions (see elect_one in tc_common.cuh)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DK, 1);   // B = V tile, MN-major (dk contiguous)
+    if (elect_one()) {
       mbar_expect_tx(q_full, kTileBytes);
       tma_load_3d(sQ, &tmQ, q_full, h * DK, i0, b);
       mbar_expect_tx(k_full, kTileBytes);
       tma_load_3d(sK, &tmK, k_full, h * DK, 0, b);
       mbar_expect_tx(v_full, kTileBytes);
       tma_load_3d(sV, &tmV, v_full, h * DK, 0, b);
-      mbar_wait(q_full, 0);
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ)), dk = umma_desc_sw128(smem_u32(sK));
-      const uint64_t dv = umma_desc_sw128(smem_u32(sV));
-      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dp1 = umma_desc_sw128(smem_u32(sP) + kPBytes / 2);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(k_full, ph);
-        tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(q_full, 0);
+    const uint64_t dq = umma_desc_sw128(smem_u32(sQ)), dk = umma_desc_sw128(smem_u32(sK));
+    const uint64_t dv = umma_desc_sw128(smem_u32(sV));
+    const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dp1 = umma_desc_sw128(smem_u32(sP) + kPBytes / 2);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(k_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
-        mbar_wait(s_full, ph);                       // S done -> K tile may be overwritten
-        if (j + 1 < n_kv) {
+      }
+      __syncwarp();
+      mbar_wait(s_full, ph);                       // S done -> K tile may be overwritten
+      if (j + 1 < n_kv) {
+        if (elect_one()) {
           mbar_expect_tx(k_full, kTileBytes);
           tma_load_3d(sK, &tmK, k_full, h * DK, (j + 1) * KT, b);
         }
-        mbar_wait(p_ready, ph);                      // P in smem, S / O_tile drained by the softmax warps
-        mbar_wait(v_full, ph);
-        tc_fence_after();
+        __syncwarp();
+      }
+      mbar_wait(p_ready, ph);                      // P in smem, S / O_tile drained by the softmax warps
+      mbar_wait(v_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k) {
           // A: P, K-major, two 64-key swizzle atoms (16 KB each), 32 bytes per K step inside an atom
@@ -132,11 +142,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_bf16(tmem_o, da, dv + 128 * k, idesc_o, k != 0);
         }
         umma_commit(o_full);
-        mbar_wait(o_full, ph);                       // PV done -> V tile and P may be overwritten
-        if (j + 1 < n_kv) {
+      }
+      __syncwarp();
+      mbar_wait(o_full, ph);                       // PV done -> V tile and P may be overwritten
+      if (j + 1 < n_kv) {
+        if (elect_one()) {
           mbar_expect_tx(v_full, kTileBytes);
           tma_load_3d(sV, &tmV, v_full, h * DK, (j + 1) * KT, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp < 4) {

@@ -118,39 +118,45 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0, phase = 0, it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // sA / sH / ring of the previous tile are dead
-      mbar_expect_tx(a_full, kABytes);
+      if (elect_one()) {
+        mbar_expect_tx(a_full, kABytes);
 #pragma unroll
-      for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kPiece, &tmA, a_full, ka * 64, m0);
+        for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kPiece, &tmA, a_full, ka * 64, m0);
+      }
+      __syncwarp();
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NC, g1, c);
         for (int pc = 0; pc < 4; ++pc) {
           mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
-          mbar_expect_tx(w_full + stage, kPiece);
-          const int k0 = g1 ? pc * 64 : c * HC + (pc & 1) * 64;
-          const int r0 = g1 ? c * HC : (pc >> 1) * 128;
-          const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
-          if constexpr (CL == 1) {
-            tma_load_2d(sW + stage * kPiece, tm, w_full + stage, k0, r0);
-          } else {   // my half of the rows, delivered to both CTAs
-            constexpr int RH = 128 / CL;
-            tma_load_2d_mc(sW + stage * kPiece + crank * (RH * 128), tm, w_full + stage, k0, r0 + crank * RH, kMask);
+          if (elect_one()) {
+            mbar_expect_tx(w_full + stage, kPiece);
+            const int k0 = g1 ? pc * 64 : c * HC + (pc & 1) * 64;
+            const int r0 = g1 ? c * HC : (pc >> 1) * 128;
+            const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
+            if constexpr (CL == 1) {
+              tma_load_2d(sW + stage * kPiece, tm, w_full + stage, k0, r0);
+            } else {   // my half of the rows, delivered to both CTAs
+              constexpr int RH = 128 / CL;
+              tma_load_2d_mc(sW + stage * kPiece + crank * (RH * 128), tm, w_full + stage, k0, r0 + crank * RH, kMask);
+            }
           }
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, 128);
     int stage = 0, phase = 0, it = 0;
-    uint32_t n_se[2] = {0, 0}, n_hf[2] = {0, 0};
+    uint32_t n_se0 = 0, n_se1 = 0, n_hf0 = 0, n_hf1 = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
       mbar_wait(a_full, it & 1);
@@ -161,40 +167,50 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         job_of(jx, NC, g1, c);
         const int b = c & 1;
         if (g1) {
-          mbar_wait(s_empty + b, (n_se[b] & 1) ^ 1);      // SiLU stage drained S[b] (two chunks ago)
-          ++n_se[b];
+          uint32_t& n_se = b ? n_se1 : n_se0;
+          mbar_wait(s_empty + b, (n_se & 1) ^ 1);         // SiLU stage drained S[b] (two chunks ago)
+          ++n_se;
           tc_fence_after();
           for (int pc = 0; pc < 4; ++pc) {
             mbar_wait(w_full + stage, phase);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(a_addr + pc * kPiece);
-            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+            if (elect_one()) {
+              const uint64_t da = umma_desc_sw128(a_addr + pc * kPiece);
+              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
+              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              if (pc == 3) umma_commit(s_full + b);
+            }
+            __syncwarp();
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
-          umma_commit(s_full + b);
         } else {
-          mbar_wait(h_full + b, n_hf[b] & 1);             // H[b] written (and fenced) by the SiLU stage
-          ++n_hf[b];
+          uint32_t& n_hf = b ? n_hf1 : n_hf0;
+          mbar_wait(h_full + b, n_hf & 1);                // H[b] written (and fenced) by the SiLU stage
+          ++n_hf;
           tc_fence_after();
           for (int pc = 0; pc < 4; ++pc) {
             const int o = pc >> 1, kk = pc & 1;
             mbar_wait(w_full + stage, phase);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + kk * kPiece);
-            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+            if (elect_one()) {
+              const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + kk * kPiece);
+              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_y + o * 128, da + 2 * k, db + 2 * k, idesc, (c | kk | k) != 0);
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_y + o * 128, da + 2 * k, db + 2 * k, idesc, (c | kk | k) != 0);
+              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              if (pc == 3) {
+                umma_commit(h_empty + b);
+                if (jx == n_jobs - 1) umma_commit(y_full);
+              }
+            }
+            __syncwarp();
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
-          umma_commit(h_empty + b);
         }
       }
-      umma_commit(y_full);
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
@@ -206,7 +222,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     const int bar_id = 1 + grp;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ring_phase = 0;
-    uint32_t n_sf[2] = {0, 0}, n_he[2] = {0, 0};
+    uint32_t n_sf0 = 0, n_sf1 = 0, n_he0 = 0, n_he1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
@@ -217,8 +233,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         const int b = c & 1;
         if (et < 64) sb1[b * HC + grp * 64 + et] = p.b1[c * HC + grp * 64 + et];
         named_bar_sync(bar_id, 128);
-        mbar_wait(s_full + b, n_sf[b] & 1);
-        ++n_sf[b];
+        uint32_t& n_sf = b ? n_sf1 : n_sf0;
+        mbar_wait(s_full + b, n_sf & 1);
+        ++n_sf;
         tc_fence_after();
         uint32_t v[64];
         {
@@ -239,8 +256,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[8 * j + e]) + bs[8 * j + e]);
           pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
-        mbar_wait(h_empty + b, (n_he[b] & 1) ^ 1);        // G2(c-2) finished reading H[b]
-        ++n_he[b];
+        uint32_t& n_he = b ? n_he1 : n_he0;
+        mbar_wait(h_empty + b, (n_he & 1) ^ 1);           // G2(c-2) finished reading H[b]
+        ++n_he;
         uint8_t* hb = sH + b * kHBytes + grp * kPiece;    // this warpgroup's 64 hidden columns = one swizzle atom
 #pragma unroll
         for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, j)) = pk[j];

@@ -152,28 +152,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0, phase = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int m0 = (t / n_tiles) * BM, nb = t % n_tiles;
       for (int kb = 0; kb < kb_count; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
-        uint8_t* sa = smem + stage * C::kStageBytes;
-        uint8_t* sb = sa + C::kABytes;
-        mbar_expect_tx(full_bar + stage, C::kStageBytes);
-        tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m0);
-        if constexpr (GLU) {   // value half and gate half of [Wa;Wb] side by side in one B tile
-          tma_load_2d(sb, &tmW, full_bar + stage, kb * BK, nb * OUT_BN);
-          tma_load_2d(sb + C::kBBytes / 2, &tmW, full_bar + stage, kb * BK, p.N + nb * OUT_BN);
-        } else {
-          tma_load_2d(sb, &tmW, full_bar + stage, kb * BK, nb * BN);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          mbar_expect_tx(full_bar + stage, C::kStageBytes);
+          tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m0);
+          if constexpr (GLU) {   // value half and gate half of [Wa;Wb] side by side in one B tile
+            tma_load_2d(sb, &tmW, full_bar + stage, kb * BK, nb * OUT_BN);
+            tma_load_2d(sb + C::kBBytes / 2, &tmW, full_bar + stage, kb * BK, p.N + nb * OUT_BN);
+          } else {
+            tma_load_2d(sb, &tmW, full_bar + stage, kb * BK, nb * BN);
+          }
         }
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     int stage = 0, phase = 0, it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
@@ -184,17 +187,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < kb_count; ++kb) {
         mbar_wait(full_bar + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + C::kABytes);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + C::kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / UK; ++k) {
-          // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the 16-byte-unit start address
-          umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the 16-byte-unit start address
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + stage);             // frees the smem slot when these MMAs retire
+          if (kb == kb_count - 1) umma_commit(tfull_bar + acc);   // accumulator complete -> epilogue
         }
-        umma_commit(empty_bar + stage);               // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar + acc);                   // accumulator complete -> epilogue
     }
   } else if (warp >= 4) {
     // ===================== epilogue (thread = output row; F1: two warpgroups split the columns) ==============

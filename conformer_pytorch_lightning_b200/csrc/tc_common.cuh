@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp (returns true in exactly one lane).  tcgen05.mma / TMA operands live in uniform
+// registers; issuing them from `if (lane == 0)` of a diverged warp makes the compiler wrap every operand in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~3x the issue cost of the MMA itself, measured), whereas a
+// warp-uniform loop with only the async instruction under elect keeps descriptors in the uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // make generic-proxy writes to shared memory visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
