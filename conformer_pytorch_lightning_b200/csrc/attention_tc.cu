@@ -76,6 +76,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_ready = bars + 4;   // P written to smem by the 128 softmax threads (also: S and O_tile drained)
   uint64_t* o_full = bars + 5;    // O_tile = PV landed in TMEM (also: P and V tile free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint32_t* svis = tmem_slot + 1;   // [2][4] visibility words of a broadcast (B,1,Tk) mask, double buffered by tile parity
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * QT;
@@ -170,20 +171,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int j0 = j * KT;
       // visibility bits of this row for the 4 x 32 keys of the tile
       uint32_t vis[4];
+      if (p.mask != nullptr && p.mask_rs == 0) {
+        // (B,1,Tk) key-padding mask: the 128 threads fetch one byte each and ballot -> 4 words shared by all rows
+        const int jj = j0 + r;
+        const bool on = (jj < p.Tk) && (__ldg(p.mask + b * p.mask_bs + jj) != 0);
+        const uint32_t w = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) svis[(j & 1) * 4 + warp] = w;
+        named_bar_sync(1, 128);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int jj = j0 + c * 32;
-        const int nvalid = p.Tk - jj;
-        uint32_t bits = !row_ok ? 0u : (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
-        if (mrow != nullptr && bits != 0u) {
-          if (nvalid >= 32) bits &= mask_bits32(mrow + jj, p.mask_aligned8 != 0);
-          else {
-            uint32_t mb = 0;
-            for (int c2 = 0; c2 < nvalid; ++c2) mb |= (__ldg(mrow + jj + c2) != 0 ? 1u : 0u) << c2;
-            bits &= mb;
+        for (int c = 0; c < 4; ++c) vis[c] = row_ok ? svis[(j & 1) * 4 + c] : 0u;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int jj = j0 + c * 32;
+          const int nvalid = p.Tk - jj;
+          uint32_t bits = !row_ok ? 0u : (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+          if (mrow != nullptr && bits != 0u) {
+            if (nvalid >= 32) bits &= mask_bits32(mrow + jj, p.mask_aligned8 != 0);
+            else {
+              uint32_t mb = 0;
+              for (int c2 = 0; c2 < nvalid; ++c2) mb |= (__ldg(mrow + jj + c2) != 0 ? 1u : 0u) << c2;
+              bits &= mb;
+            }
           }
+          vis[c] = bits;
         }
-        vis[c] = bits;
       }
       mbar_wait(s_full, ph);
       tc_fence_after();

@@ -13,29 +13,39 @@ constexpr int kDwTT = 64;   // output frames per block
 constexpr int kDwCG = 64;   // channels per block (one 128-byte line of bf16)
 constexpr int kDwR = 16;    // outputs per thread along time (4 warps x 16 = 64)
 
-// stage rows [t0 - pad, t0 + TT + pad) x 64 channels as fp32 in shared memory; zero outside [0,T)
-template <typename T>
+// stage rows [t0 - pad, t0 + TT + pad) x 64 channels as fp32 in shared memory; zero outside [0,T).
+// All 16-byte global loads of a thread are issued back to back (MAXL independent loads in flight) before any
+// of them is converted and stored: the kernel is latency bound otherwise (ncu: long-scoreboard stalls on the
+// first use of each load with ~1 wave of CTAs).
+template <typename T, int MAXL>
 __device__ __forceinline__ void dw_stage(const T* __restrict__ xb, float* smem, int t0, int Tlen, int d,
                                          int c0, int rows_needed, int pad) {
   constexpr int V = Act<T>::kVec;            // elements per 16-byte load
   constexpr int CHUNKS = kDwCG / V;          // 16-byte chunks per staged row
-  for (int idx = threadIdx.x; idx < rows_needed * CHUNKS; idx += blockDim.x) {
+  const int total = rows_needed * CHUNKS;
+  uint4 raw[MAXL];
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+    const int idx = threadIdx.x + l * 128;
     const int r = idx / CHUNKS, ch = idx % CHUNKS;
     const int t = t0 - pad + r;
-    float* dst = smem + r * kDwCG + ch * V;
-    if (t >= 0 && t < Tlen) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * d + c0 + ch * V));
-      if constexpr (sizeof(T) == 4) {
-        *reinterpret_cast<uint4*>(dst) = raw;
-      } else {
-        const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
-        const float2 c = unpack_bf16x2(raw.z), e = unpack_bf16x2(raw.w);
-        *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(c.x, c.y, e.x, e.y);
-      }
-    } else {
+    raw[l] = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < total && t >= 0 && t < Tlen)
+      raw[l] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * d + c0 + ch * V));
+  }
 #pragma unroll
-      for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < MAXL; ++l) {
+    const int idx = threadIdx.x + l * 128;
+    if (idx >= total) break;
+    const int r = idx / CHUNKS, ch = idx % CHUNKS;
+    float* dst = smem + r * kDwCG + ch * V;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<uint4*>(dst) = raw[l];
+    } else {
+      const float2 a = unpack_bf16x2(raw[l].x), b = unpack_bf16x2(raw[l].y);
+      const float2 c = unpack_bf16x2(raw[l].z), e = unpack_bf16x2(raw[l].w);
+      *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(c.x, c.y, e.x, e.y);
     }
   }
 }
@@ -53,7 +63,10 @@ dwconv_kernel(const T* __restrict__ x, const float* __restrict__ w, const float*
   const int b = blockIdx.z;
   const T* xb = x + (size_t)b * Tlen * d;
   const int rows_needed = kDwTT + k - 1;
-  dw_stage<T>(xb, smem, t0, Tlen, d, c0, rows_needed, pad);
+  // loads per thread: (64 + k - 1) rows x (64 channels / elements-per-16-bytes) chunks over 128 threads
+  constexpr int KMAX = (K > 0) ? K : 31;
+  constexpr int MAXL = ((kDwTT + KMAX - 1) * (kDwCG / Act<T>::kVec) + 127) / 128;
+  dw_stage<T, MAXL>(xb, smem, t0, Tlen, d, c0, rows_needed, pad);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
