@@ -8,17 +8,50 @@ import torch
 from conformer_pytorch_lightning_b200 import _native as N, ops
 
 
-def timeit(fn, iters=30):
-    for _ in range(5):
+def timeit(fn, iters=20, per_graph=10):
+    """Average device time of one call, measured by replaying a CUDA graph of `per_graph` calls (Python /
+    ctypes launch overhead is ~10 us per call and would otherwise hide every kernel shorter than that)."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(per_graph):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(iters):
-        fn()
+        g.replay()
     e.record()
     e.synchronize()
-    return s.elapsed_time(e) / iters * 1e3  # us
+    return s.elapsed_time(e) / (iters * per_graph) * 1e3  # us
+
+
+def small_kernels():
+    B, T, d, H = 64, 248, 256, 4
+    dev = "cuda"
+    x = torch.randn(B, T, d, device=dev).bfloat16(); y = torch.empty_like(x)
+    w = torch.randn(15, d, device=dev); b = torch.randn(d, device=dev)
+    t = timeit(lambda: ops.dwconv(x, w, b, y))
+    print(f"dwconv k=15 (B={B},T={T},d={d}): {t:6.1f} us  -> {2 * x.numel() * 2 / t / 1e3:7.1f} GB/s algorithmic")
+    qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
+    out = torch.empty(B, T, d, device=dev, dtype=torch.bfloat16)
+    fl = 4.0 * B * T * T * d
+    for name, m in (("pad mask (B,1,T)", torch.ones(B, 1, T, dtype=torch.bool, device=dev)), ("no mask", None),
+                    ("full mask (B,T,T)", torch.ones(B, T, T, dtype=torch.bool, device=dev))):
+        t = timeit(lambda: ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, mask=m, scale=0.125))
+        print(f"attention {name:18s}: {t:6.1f} us  ({fl / t / 1e6:6.1f} TF/s)")
+    xr = torch.randn(B * T, d, device=dev); g = torch.ones(d, device=dev); be = torch.zeros(d, device=dev)
+    yb = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.layernorm(xr, g, be, y=yb))
+    print(f"layernorm fp32->bf16: {t:6.1f} us -> {(xr.numel() * 6) / t / 1e3:7.1f} GB/s")
 
 
 def main():
@@ -69,6 +102,9 @@ def ffn_bench(M=15872, d=256, F=2048):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        small_kernels()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ffn":
         ffn_bench()
         sys.exit(0)
