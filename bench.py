@@ -13,8 +13,9 @@ value : RTFx of the measured path with its inputs (sub-sampled features, masks) 
         CUDA events per step on the launch stream, L2 flushed between steps, max over ranks.
 e2e   : the same metric through the public drop-in API ``ConformerEncoder.forward(feats, lengths)`` with
         pinned HOST fbank features: H2D copy + CMVN-less sub-sampling (PyTorch) + layers + D2H of the output.
-roofline : dominant kernel = the tcgen05 GEMM; the instance quoted is the FFN up-projection
-        (M=B*T, N=2048, K=256, bias+SiLU), timed in-step with CUDA events around each of its launches.
+roofline : dominant kernel = the fused feed-forward kernel (w_1 + SiLU + w_2 + residual + LayerNorm, ~half of
+        the step), timed in-step with CUDA events around each of its 24 launches; `roofline_hbm` is the same
+        for the HBM-bound depthwise-conv + BatchNorm + SiLU kernel.
 cpu_baseline / --impl reference : the ATen-CPU oracle port of the reference's CPU path (the reference is
         Python and cannot travel to the GPU box) on a bounded sample of the same workload.
 """
@@ -258,42 +259,53 @@ def run_ours(args):
     e2e_val = world * audio_s / (e2e_ms / 1e3)
     out_bytes = B * T * cfg["encoder_dim"] * 4
 
-    # ---- roofline of the dominant kernel, timed in-step with events around each matching launch
+    # ---- roofline of the dominant kernels, timed in-step with CUDA events around each matching launch
+    #      (eager launches: graph replays cannot be bracketed per kernel)
     pk = peaks()
     n_tok, d, F = B * T, cfg["encoder_dim"], cfg["hidden_dim"]
-    ev = []
-    orig_gemm = ops.gemm
+    ev = {"ffn": [], "dw": []}
 
-    def probe(a, w, bias, out, epi, **kw):
-        match = (epi == _native.EPI_BIAS_SILU and tuple(w.shape) == (F, d))
-        if match:
+    def wrap(mod, name, key):
+        orig = getattr(mod, name)
+
+        def probe(*a, **kw):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-        r = orig_gemm(a, w, bias, out, epi, **kw)
-        if match:
+            r = orig(*a, **kw)
             e.record()
-            ev.append((s, e))
-        return r
+            ev[key].append((s, e))
+            return r
+        setattr(mod, name, probe)
+        return orig
 
-    ops.gemm = probe
-    engine.ops.gemm = probe
     graphs = enc.use_cuda_graphs
-    enc.use_cuda_graphs = False               # the probe needs eager launches to bracket single kernels
+    enc.use_cuda_graphs = False
+    o_ffn, o_dw = wrap(ops, "ffn", "ffn"), wrap(ops, "dwconv", "dw")
     try:
         for _ in range(3):
             flush.fill_(1)
             step()
         torch.cuda.synchronize()
     finally:
+        ops.ffn, ops.dwconv = o_ffn, o_dw
         enc.use_cuda_graphs = graphs
-        ops.gemm = orig_gemm
-        engine.ops.gemm = orig_gemm
-    kt = float(np.mean([s.elapsed_time(e) for s, e in ev])) if ev else float("nan")
-    flops = 2.0 * n_tok * d * F
-    ach = flops / (kt * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<256,SILU> M={n_tok} N={F} K={d} (FFN w_1 + SiLU)",
+    t_ffn = float(np.mean([s.elapsed_time(e) for s, e in ev["ffn"]])) if ev["ffn"] else float("nan")
+    t_dw = float(np.mean([s.elapsed_time(e) for s, e in ev["dw"]])) if ev["dw"] else float("nan")
+    flops = 4.0 * n_tok * d * F                       # two GEMMs of 2*M*d*F each (8*N*d*F per layer / 2 FFNs)
+    ach = flops / (t_ffn * 1e-3) / 1e12
+    n_ffn = 2 * cfg["encoder_num_layers"]
+    roofline = {"bound": "tensor",
+                "kernel": f"ffn_fused_kernel (w_1+SiLU+w_2+residual+LayerNorm in one kernel) M={n_tok} d={d} F={F}",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "launch_us": kt * 1e3, "peak_source": pk["source"] + ", sustained bf16"}
+                "traffic": None, "launch_us": t_ffn * 1e3, "launches_per_step": n_ffn,
+                "share_of_step": n_ffn * t_ffn / ms_per_step,
+                "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside the step)"}
+    dw_bytes = 2.0 * n_tok * d * 2                    # read + write one bf16 (N,d) tensor
+    ach_dw = dw_bytes / (t_dw * 1e-3) / 1e9
+    roofline_hbm = {"bound": "hbm", "kernel": f"dwconv_kernel k={cfg['kernel_size']} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
+                    "achieved": ach_dw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_dw / pk["hbm_gbs"],
+                    "traffic": None, "launch_us": t_dw * 1e3, "launches_per_step": cfg["encoder_num_layers"],
+                    "peak_source": pk["source"]}
 
     if rank == 0:
         cpu = None
@@ -312,7 +324,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(feats_host.numel() * 4 + lens_np.nbytes),
                         "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_ms,
                         "api": "ConformerEncoder.forward(feats_pinned_host.to(cuda), lengths) -> out.cpu()"},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary()}
+                "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+                "clocks": clk.summary()}
         if algo_tf:
             line["model_tflops"] = algo_tf / (ms_per_step / 1e3) * world
         print(json.dumps(line), flush=True)
