@@ -62,8 +62,9 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8)
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
+  // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;
   uint8_t* sV = smem + 2 * kTileBytes;

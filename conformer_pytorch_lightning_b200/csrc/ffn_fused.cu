@@ -65,8 +65,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
                  const __grid_constant__ CUtensorMap tmR,    // residual load (same tensor as X)
                  const __grid_constant__ CUtensorMap tmY,    // y out (M, 256) bf16 store, box 64 x 128
                  const FfnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
+  // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sH = sA + kABytes;                 // 2 x 32 KB; also the residual staging ring (4 x 16 KB)
   uint8_t* sW = sH + 2 * kHBytes;             // NST x 16 KB

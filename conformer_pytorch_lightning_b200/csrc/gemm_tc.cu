@@ -117,8 +117,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool RESID = (EPI == CFM_EPI_RESIDUAL);
   using C = Cfg<BN, RESID>;
   constexpr int OUT_BN = GLU ? BN / 2 : BN;      // output columns per tile
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
+  // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + C::kStages * C::kStageBytes;                       // kBufs x 16 KB, 1024-aligned
   float* sparam = reinterpret_cast<float*>(ring + C::kBufs * kBufBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sparam + C::kParamFloats);
