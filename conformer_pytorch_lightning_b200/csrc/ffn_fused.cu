@@ -25,13 +25,18 @@ using namespace tc;
 constexpr int D = 256;          // model dim = K of GEMM1 = N of GEMM2
 constexpr int HC = 128;         // hidden units per chunk
 constexpr int BM = 128;
-constexpr int kPiece = 16384;   // one weight piece: 128 rows x 64 k bf16
-constexpr int NST = 5;          // weight ring depth
+constexpr int kAtom = 16384;    // one swizzle atom tile: 128 rows x 64 k bf16
+constexpr int kPiece = 32768;   // one weight piece = one ring slot = 512 tensor-pipe cycles of MMA work per barrier wait
+                                //   G1: W1 rows [c*128,+128) x 128 k  (two atoms side by side, 8 MMAs N=128)
+                                //   G2: W2 rows [0,256) x 64 hidden-k  (one 256-row tile,      4 MMAs N=256)
+constexpr int NST = 3;          // weight ring depth
 constexpr int kABytes = BM * D * 2;            // 64 KB
 constexpr int kHBytes = BM * HC * 2;           // 32 KB per H buffer
 constexpr int kThreads = 384;
-constexpr int kParamFloats = 5 * D + 2 * HC;   // residual params + double-buffered b1 chunk
-constexpr int kSmemBytes = kABytes + 2 * kHBytes + NST * kPiece + kParamFloats * 4 + 512 + 1024;
+constexpr int kParamFloats = 2 * HC;           // double-buffered b1 chunk (the residual-epilogue parameters alias the
+                                               // input tile, which is dead by the time they are needed)
+constexpr int kSmemBytes = kABytes + 2 * kHBytes + NST * kPiece + kParamFloats * 4 + 512;
+static_assert(5 * D * 4 <= kABytes, "residual parameters alias the input tile");
 static_assert(kSmemBytes <= 232448, "smem budget");
 static_assert(2 * kHBytes == 4 * kBufBytes, "residual staging ring aliases the two H buffers");
 
@@ -42,6 +47,7 @@ struct FfnParams {
   const uint8_t* y_row_valid;
   float alpha, eps;
   int M, F, ln_mode;
+  long long* trace;   // optional per-event clock64 timestamps of CTA 0 (tools/ffn_trace.py); nullptr in production
 };
 
 // job jx of a tile: G1(c) or G2(c), ordered so the tensor pipe always has independent work while SiLU(c) runs:
@@ -70,9 +76,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sH = sA + kABytes;                 // 2 x 32 KB; also the residual staging ring (4 x 16 KB)
-  uint8_t* sW = sH + 2 * kHBytes;             // NST x 16 KB
-  float* sparam = reinterpret_cast<float*>(sW + NST * kPiece);
-  float* sb1 = sparam + 5 * D;                // [2][HC]
+  uint8_t* sW = sH + 2 * kHBytes;             // NST x 32 KB
+  float* sparam = reinterpret_cast<float*>(sA);   // residual-epilogue parameters alias the input tile, which is dead after
+                                                  // the last MMA of the tile and is only ever written by this CTA's own TMA
+  float* sb1 = reinterpret_cast<float*>(sW + NST * kPiece);   // [2][HC]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb1 + 2 * HC);
   uint64_t* w_full = bars;                    // [NST]
   uint64_t* w_empty = w_full + NST;           // [NST]
@@ -128,24 +135,31 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       if (elect_one()) {
         mbar_expect_tx(a_full, kABytes);
 #pragma unroll
-        for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kPiece, &tmA, a_full, ka * 64, m0);
+        for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kAtom, &tmA, a_full, ka * 64, m0);
       }
       __syncwarp();
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NC, g1, c);
-        for (int pc = 0; pc < 4; ++pc) {
+        for (int pc = 0; pc < 2; ++pc) {
           mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
           if (elect_one()) {
+            uint8_t* dst = sW + stage * kPiece;
             mbar_expect_tx(w_full + stage, kPiece);
-            const int k0 = g1 ? pc * 64 : c * HC + (pc & 1) * 64;
-            const int r0 = g1 ? c * HC : (pc >> 1) * 128;
-            const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
-            if constexpr (CL == 1) {
-              tma_load_2d(sW + stage * kPiece, tm, w_full + stage, k0, r0);
-            } else {   // my half of the rows, delivered to both CTAs
-              constexpr int RH = 128 / CL;
-              tma_load_2d_mc(sW + stage * kPiece + crank * (RH * 128), tm, w_full + stage, k0, r0 + crank * RH, kMask);
+            if (g1) {          // W1_c[:, pc*128 .. +128): atoms a = 0,1 at k = pc*128 + a*64
+              if constexpr (CL == 1) {
+                tma_load_2d(dst, &tmW1, w_full + stage, pc * 128, c * HC);
+                tma_load_2d(dst + kAtom, &tmW1, w_full + stage, pc * 128 + 64, c * HC);
+              } else {         // each CTA fetches one atom and multicasts it
+                tma_load_2d_mc(dst + crank * kAtom, &tmW1, w_full + stage, pc * 128 + crank * 64, c * HC, kMask);
+              }
+            } else {           // W2[:, c*128 + pc*64 .. +64): 256 output rows
+              if constexpr (CL == 1) {
+                tma_load_2d(dst, &tmW2, w_full + stage, c * HC + pc * 64, 0);
+                tma_load_2d(dst + kAtom, &tmW2, w_full + stage, c * HC + pc * 64, 128);
+              } else {         // each CTA fetches 128 of the 256 rows and multicasts them
+                tma_load_2d_mc(dst + crank * kAtom, &tmW2, w_full + stage, c * HC + pc * 64, crank * 128, kMask);
+              }
             }
           }
           __syncwarp();
@@ -155,7 +169,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, 128);
+    constexpr uint32_t idesc1 = umma_idesc_bf16(BM, 128);   // G1: N = 128 hidden units
+    constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 256);   // G2: N = 256 outputs
     int stage = 0, phase = 0, it = 0;
     uint32_t n_se0 = 0, n_se1 = 0, n_hf0 = 0, n_hf1 = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
@@ -167,21 +182,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         bool g1; int c;
         job_of(jx, NC, g1, c);
         const int b = c & 1;
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + jx] = clock64();
         if (g1) {
           uint32_t& n_se = b ? n_se1 : n_se0;
           mbar_wait(s_empty + b, (n_se & 1) ^ 1);         // SiLU stage drained S[b] (two chunks ago)
           ++n_se;
           tc_fence_after();
-          for (int pc = 0; pc < 4; ++pc) {
+          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
+          for (int pc = 0; pc < 2; ++pc) {
             mbar_wait(w_full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = umma_desc_sw128(a_addr + pc * kPiece);
-              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+              const uint32_t w_addr = smem_u32(sW + stage * kPiece);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
+              for (int a = 0; a < 2; ++a) {
+                const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
+                const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
+              }
               if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-              if (pc == 3) umma_commit(s_full + b);
+              if (pc == 1) umma_commit(s_full + b);
             }
             __syncwarp();
             if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -191,18 +213,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           mbar_wait(h_full + b, n_hf & 1);                // H[b] written (and fenced) by the SiLU stage
           ++n_hf;
           tc_fence_after();
-          for (int pc = 0; pc < 4; ++pc) {
-            const int o = pc >> 1, kk = pc & 1;
+          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
+          for (int pc = 0; pc < 2; ++pc) {                // pc = 64-wide k atom of the hidden chunk
             mbar_wait(w_full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + kk * kPiece);
+              const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
               const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_y + o * 128, da + 2 * k, db + 2 * k, idesc, (c | kk | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
               if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-              if (pc == 3) {
+              if (pc == 1) {
                 umma_commit(h_empty + b);
                 if (jx == n_jobs - 1) umma_commit(y_full);
               }
@@ -228,16 +249,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
       if (it > 0 && grp == 1) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
-      if (grp == 0) resid_stage_params<D>(sparam, et, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
       // ---- SiLU stage: S[b] -> H[b]
       for (int c = 0; c < NC; ++c) {
         const int b = c & 1;
         if (et < 64) sb1[b * HC + grp * 64 + et] = p.b1[c * HC + grp * 64 + et];
         named_bar_sync(bar_id, 128);
         uint32_t& n_sf = b ? n_sf1 : n_sf0;
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[2 * 64 + c] = clock64();
         mbar_wait(s_full + b, n_sf & 1);
         ++n_sf;
         tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[3 * 64 + c] = clock64();
         uint32_t v[64];
         {
           uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -258,18 +280,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
         uint32_t& n_he = b ? n_he1 : n_he0;
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[5 * 64 + c] = clock64();
         mbar_wait(h_empty + b, (n_he & 1) ^ 1);           // G2(c-2) finished reading H[b]
         ++n_he;
-        uint8_t* hb = sH + b * kHBytes + grp * kPiece;    // this warpgroup's 64 hidden columns = one swizzle atom
+        uint8_t* hb = sH + b * kHBytes + grp * kAtom;     // this warpgroup's 64 hidden columns = one swizzle atom
 #pragma unroll
         for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, j)) = pk[j];
         fence_proxy_async_smem();
         mbar_arrive(h_full + b);
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + c] = clock64();
       }
       // ---- final epilogue on Y (warpgroup 0)
       if (grp == 0) {
         mbar_wait(y_full, it & 1);
         tc_fence_after();
+        // every MMA of the tile has retired: the input tile (-> parameters) and H buffers (-> staging ring) are dead
+        resid_stage_params<D>(sparam, et, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
         if (elected) resid_prefetch<D, 4>(sH, res_bar, &tmR, 0, m0);
         ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
         resid_ln_epilogue<D, 4>(tmem_y + lane_base, r, m0, 0, elected, bar_id, sH, res_bar, ring_phase, sparam, &tmX,
@@ -317,12 +343,13 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
   CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
   int rc;
   if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D, 128 / CL)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F, 128 / CL)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D)) != 0) return rc;
+  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F)) != 0) return rc;
   if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
   tmY = tmA;
   if (ln_mode != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
-  FfnParams p{b1, b2, g1, be1, g2, be2, y_row_valid, alpha, eps, M, F, ln_mode};
+  FfnParams p{b1, b2, g1, be1, g2, be2, y_row_valid, alpha, eps, M, F, ln_mode, nullptr};
+  if (const char* e = getenv("CFM_B200_FFN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   const int m_tiles = ((M + BM - 1) / BM + CL - 1) / CL * CL;
   const int max_ctas = num_sms() / CL * CL;
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
