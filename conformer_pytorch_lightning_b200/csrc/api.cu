@@ -2,6 +2,7 @@
 #include "cfm_common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cfm {
 
@@ -97,9 +98,19 @@ extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1
   const bool fused_ok = ffn_fused_supported(ld_in, ldx, ld_out, M, d, F, dtype, ln_mode);
   if (engine == CFM_ENGINE_TC)
     CFM_CHECK_ARG(fused_ok, "cfm_ffn: fused tcgen05 path does not support M=%d d=%d F=%d dtype=%d", M, d, F, dtype);
-  if (fused_ok && engine != CFM_ENGINE_SIMT)
+  if (fused_ok && engine != CFM_ENGINE_SIMT) {
+    // CFM_B200_FFN_MODE: "pair" = tcgen05 cta_group::2 kernel (ffn_pair.cu), anything else = ffn_fused.cu
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+      const char* e = getenv("CFM_B200_FFN_MODE");
+      pair_mode = (e && strcmp(e, "pair") == 0) ? 1 : 0;
+    }
+    if (pair_mode)
+      return ffn_pair(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
+                      eps, (cudaStream_t)stream);
     return ffn_fused(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
                      eps, (cudaStream_t)stream);
+  }
   CFM_CHECK_ARG(hidden_ws != nullptr, "cfm_ffn: the unfused path needs hidden_ws");
   int rc = cfm_gemm(y, ld_in, W1, b1, hidden_ws, F, M, F, d, dtype, CFM_EPI_BIAS_SILU, nullptr, 1.f, nullptr, engine, stream);
   if (rc != 0) return rc;

@@ -134,6 +134,10 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
               int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
               const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st);
 
+int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
+             int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
+             const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st);
+
 int attention_simt(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                    const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
                    const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,
