@@ -178,74 +178,60 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       mbar_wait(a_full, it & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
-      // Flattened piece loop (2 pieces per job).  The tensor pipe accepts only a few MMAs ahead, so the issuing warp
-      // runs in lock-step with it and every cycle the warp spends waiting is an idle pipe cycle (measured with the
-      // clock64 trace: ~70 clk per barrier try_wait, ~250 clk per job change).  Hence the barriers of piece q+1 are
-      // probed (non-blocking test_wait) BEFORE the MMAs of piece q are issued; the blocking wait only runs when the
-      // probe failed.
-      bool ready = false;               // barriers of the current piece already seen complete by the previous probe
-      const int n_pieces = 2 * n_jobs;
-      for (int q = 0; q < n_pieces; ++q) {
-        const int jx = q >> 1, pc = q & 1;
+      for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NC, g1, c);
         const int b = c & 1;
-        if (pc == 0) {                  // job-level barrier: S[b] drained (G1) or H[b] written (G2)
-          if (g1) {
-            uint32_t& n_se = b ? n_se1 : n_se0;
-            if (!ready) mbar_wait(s_empty + b, (n_se & 1) ^ 1);
-            ++n_se;
-          } else {
-            uint32_t& n_hf = b ? n_hf1 : n_hf0;
-            if (!ready) mbar_wait(h_full + b, n_hf & 1);
-            ++n_hf;
-          }
-        }
-        if (!ready) mbar_wait(w_full + stage, phase);
-        tc_fence_after();
-        // ---- probe piece q+1
-        const int nstage = (stage + 1 == NST) ? 0 : stage + 1;
-        const int nphase = (stage + 1 == NST) ? (phase ^ 1) : phase;
-        bool nready = false;
-        if (q + 1 < n_pieces) {
-          nready = mbar_test(w_full + nstage, nphase);
-          if (pc == 1 && nready) {      // next piece opens a new job: also needs that job's barrier
-            bool ng1; int nc;
-            job_of(jx + 1, NC, ng1, nc);
-            const int nb = nc & 1;
-            if (ng1) nready = mbar_test(s_empty + nb, ((nb ? n_se1 : n_se0) & 1) ^ 1);
-            else     nready = mbar_test(h_full + nb, (nb ? n_hf1 : n_hf0) & 1);
-          }
-        }
-        // ---- issue piece q
-        if (elect_one()) {
-          const uint32_t w_addr = smem_u32(sW + stage * kPiece);
-          if (g1) {
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + jx] = clock64();
+        if (g1) {
+          uint32_t& n_se = b ? n_se1 : n_se0;
+          mbar_wait(s_empty + b, (n_se & 1) ^ 1);         // SiLU stage drained S[b] (two chunks ago)
+          ++n_se;
+          tc_fence_after();
+          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
+          for (int pc = 0; pc < 2; ++pc) {
+            mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t w_addr = smem_u32(sW + stage * kPiece);
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
-              const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
+              for (int a = 0; a < 2; ++a) {
+                const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
+                const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
+              }
+              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              if (pc == 1) umma_commit(s_full + b);
             }
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-            if (pc == 1) umma_commit(s_full + b);
-          } else {
-            const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
-            const uint64_t db = umma_desc_sw128(w_addr);
+            __syncwarp();
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          uint32_t& n_hf = b ? n_hf1 : n_hf0;
+          mbar_wait(h_full + b, n_hf & 1);                // H[b] written (and fenced) by the SiLU stage
+          ++n_hf;
+          tc_fence_after();
+          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
+          for (int pc = 0; pc < 2; ++pc) {                // pc = 64-wide k atom of the hidden chunk
+            mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
+              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-            if (pc == 1) {
-              umma_commit(h_empty + b);
-              if (jx == n_jobs - 1) umma_commit(y_full);
+              for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
+              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              if (pc == 1) {
+                umma_commit(h_empty + b);
+                if (jx == n_jobs - 1) umma_commit(y_full);
+              }
             }
+            __syncwarp();
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
-        __syncwarp();
-        stage = nstage; phase = nphase;
-        ready = nready;
       }
     }
   } else if (warp >= 4) {
