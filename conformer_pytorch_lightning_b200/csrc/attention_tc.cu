@@ -16,6 +16,7 @@
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace cfm {
 namespace {
@@ -36,7 +37,14 @@ struct AttnParams {
   int H, Tq, Tk;
   float scale_log2;     // softmax scale * log2(e)
   int mask_aligned8;
+  long long* trace;   // optional clock64 timeline of CTA (0,0,0) (tools/attn_trace.py); nullptr in production
 };
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // 32 mask bytes -> bitmask (bit c set = visible)
 __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8) {
@@ -83,6 +91,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int i0 = blockIdx.x * QT;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.Tk + KT - 1) / KT;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define ATR(slot) do { if (tr && lane == 0) p.trace[(slot)] = clock64(); } while (0)
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
@@ -110,7 +120,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_3d(sV, &tmV, v_full, h * DK, 0, b);
     }
     __syncwarp();
+    ATR(0);
     mbar_wait(q_full, 0);
+    ATR(1);
     const uint64_t dq = umma_desc_sw128(smem_u32(sQ)), dk = umma_desc_sw128(smem_u32(sK));
     const uint64_t dv = umma_desc_sw128(smem_u32(sV));
     const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dp1 = umma_desc_sw128(smem_u32(sP) + kPBytes / 2);
@@ -118,13 +130,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t ph = j & 1;
       mbar_wait(k_full, ph);
       tc_fence_after();
+      ATR(8 + j * 8 + 0);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
       }
       __syncwarp();
-      mbar_wait(s_full, ph);                       // S done -> K tile may be overwritten
+      ATR(8 + j * 8 + 1);
+      mbar_wait(s_full, ph);
+      ATR(8 + j * 8 + 2);                       // S done -> K tile may be overwritten
       if (j + 1 < n_kv) {
         if (elect_one()) {
           mbar_expect_tx(k_full, kTileBytes);
@@ -133,8 +148,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
       }
       mbar_wait(p_ready, ph);                      // P in smem, S / O_tile drained by the softmax warps
+      ATR(8 + j * 8 + 3);
       mbar_wait(v_full, ph);
       tc_fence_after();
+      ATR(8 + j * 8 + 4);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < KT / 16; ++k) {
@@ -146,7 +163,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(o_full);
       }
       __syncwarp();
+      ATR(8 + j * 8 + 5);
       mbar_wait(o_full, ph);                       // PV done -> V tile and P may be overwritten
+      ATR(8 + j * 8 + 6);
       if (j + 1 < n_kv) {
         if (elect_one()) {
           mbar_expect_tx(v_full, kTileBytes);
@@ -198,36 +217,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           vis[c] = bits;
         }
       }
+      if (warp == 0) ATR(64 + j * 8 + 0);
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row max over visible keys
+      if (warp == 0) ATR(64 + j * 8 + 1);
+      // pass 1: row max over visible keys.  Fast path per 32-key chunk when every key is visible (the common case:
+      // masking only bites on the tail tile / chunk boundaries) -- 1 FMNMX per element instead of shift+and+setp+sel.
       float m_tile = -CUDART_INF_F;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_s + lane_base + c * 32, v);
         tmem_ld_wait();
+        if (vis[c] == 0xffffffffu) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if ((vis[c] >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+        } else if (vis[c] != 0u) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if ((vis[c] >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+        }
       }
+      if (warp == 0) ATR(64 + j * 8 + 2);
       m_tile *= p.scale_log2;                               // scale > 0: max commutes with the scaling
       const float m_new = fmaxf(m_run, m_tile);
       const bool any = m_new != -CUDART_INF_F;
       const float alpha = any ? exp2f(m_run - m_new) : 1.f; // m_run = -inf, m_new finite -> 0
-      const float m_use = any ? m_new : 0.f;
-      // pass 2: p = exp2(s*c - m), P -> smem (bf16, swizzled K-major A operand), row sum
+      const float neg_m = any ? -m_new : 0.f;
+      // pass 2: p = 2^(s*c - m) (one FFMA + one MUFU.EX2 per element; masked keys are turned into -inf first so
+      // they come out as exactly 0), P -> smem as bf16 in the swizzled K-major A-operand layout, row sum
       float l_tile = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_s + lane_base + c * 32, v);
         tmem_ld_wait();
+        if (vis[c] != 0xffffffffu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((vis[c] >> e) & 1u)) v[e] = 0xff800000u;  // -inf
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = ((vis[c] >> e) & 1u) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use)) : 0.f;
-          const float p1 = ((vis[c] >> (e + 1)) & 1u) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use)) : 0.f;
+          const float p0 = ex2_fast(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_m));
+          const float p1 = ex2_fast(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_m));
           l_tile += p0 + p1;
           pk[e >> 1] = pack_bf16x2(p0, p1);
         }
@@ -244,9 +278,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();        // P stores -> visible to the tensor core (async proxy)
       tc_fence_before();               // our TMEM loads of S are complete (wait::ld above)
       mbar_arrive(p_ready);
+      if (warp == 0) ATR(64 + j * 8 + 3);
       // O_tile = P V of this tile, accumulate into registers with the online rescale
       mbar_wait(o_full, ph);
       tc_fence_after();
+      if (warp == 0) ATR(64 + j * 8 + 4);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -256,6 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], alpha, __uint_as_float(v[e]));
       }
       tc_fence_before();
+      if (warp == 0) ATR(64 + j * 8 + 5);
     }
     if (row_ok) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;     // fully masked row -> 0 (attention.py:92)
@@ -313,6 +350,8 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   p.mask = mask; p.mask_bs = mask_bs; p.mask_rs = mask_rs;
   p.H = H; p.Tq = Tq; p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = nullptr;
+  if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + QT - 1) / QT, H, B);
   attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, p);
