@@ -20,7 +20,8 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 # every symbol include/cfm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
-    "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu",
+    "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
+    "cfm_subsample_conv",
 ]
 
 _lib = None
@@ -45,9 +46,12 @@ def _declare(lib):
     lib.cfm_dwconv.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]
     lib.cfm_bn_stats.argtypes = [_p, _i, _i, _p, _p, _p]
     lib.cfm_bn_apply_silu.argtypes = [_p, _i, _i, _p, _p, _p, _p, _p, _i, _p]
+    lib.cfm_subsample_ws_bytes.argtypes = [_i, _i, _i, _i]
+    lib.cfm_subsample_ws_bytes.restype = _i64
+    lib.cfm_subsample_conv.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version"):
+        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version", "cfm_subsample_ws_bytes"):
             fn.restype = _i
 
 

@@ -1,4 +1,6 @@
 """Drop-in for the reference's src/convolution.py."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -59,6 +61,8 @@ class ConvolutionSubSampling(nn.Module):
                 outputs = self.conv(inputs.unsqueeze(1))
             b, c, t, f = outputs.size()
             outputs = self.out(outputs.transpose(1, 2).contiguous().view(b, t, c * f))
+        elif inputs.is_cuda and self._native_ok(inputs):
+            outputs = self._native_forward(inputs)
         elif inputs.is_cuda:
             # bf16 compute path: the (B, d, T/2, 39) activation of the first conv is the largest tensor of the whole
             # encoder (1.3 GB in fp32 at B=64 x 10 s); bf16 autocast halves its HBM traffic.  Still PyTorch/cuDNN:
@@ -75,5 +79,44 @@ class ConvolutionSubSampling(nn.Module):
         outputs, pos_embed = self.pos_enc(outputs, offset)
         return outputs, pos_embed, inputs_pad_mask[:, :, 2::2][:, :, 2::2]
 
+    # (the PyTorch paths above remain the fp32 / tiny-input / training implementation)
+
     def position_encoding(self, offset, size):
         return self.pos_enc.position_encoding(offset, size)
+
+    # ------------------------------------------------------------------ native bf16 front-end (scope row f1)
+    def _native_ok(self, inputs):
+        c = self.conv[0].out_channels
+        return (os.environ.get("CFM_B200_NATIVE_SUBSAMPLE", "1") != "0" and not self.training and inputs.dim() == 3
+                and inputs.dtype == torch.float32 and c % 256 == 0 and inputs.size(1) >= 7
+                and inputs.size(0) * (((inputs.size(1) - 3) // 2 + 1 - 3) // 2 + 1) >= 64)
+
+    def _native_weights(self, dtype):
+        if not hasattr(self, "_derived"):
+            self._derived = engine.Derived()
+
+        def build(_dt):
+            c = self.conv[0].out_channels
+            f2 = self.out[0].in_features // c
+            w3 = self.out[0].weight.detach().view(-1, c, f2).permute(0, 2, 1).reshape(-1, f2 * c)
+            return {"w1": self.conv[0].weight.detach().float().reshape(c, 9).contiguous(),
+                    "b1": self.conv[0].bias.detach().float().contiguous(),
+                    "w2": self.conv[2].weight.detach().permute(0, 2, 3, 1).reshape(c, 9 * c).to(torch.bfloat16).contiguous(),
+                    "b2": self.conv[2].bias.detach().float().contiguous(),
+                    "w3": w3.to(torch.bfloat16).contiguous(), "b3": self.out[0].bias.detach().float().contiguous()}
+        return self._derived.get(self, dtype, build)
+
+    def _native_forward(self, inputs):
+        """conv1 (CUDA cores) -> conv2 (tcgen05 implicit GEMM, TMA-gathered taps) -> Linear (tcgen05 GEMM)."""
+        W = self._native_weights(torch.bfloat16)
+        B, tin, idim = inputs.shape
+        c = W["w1"].shape[0]
+        t2 = ((tin - 3) // 2 + 1 - 3) // 2 + 1
+        f2 = W["w3"].shape[1] // c
+        ws = engine.thread_workspace()
+        scratch = ws.get("subsample_ws", (ops.subsample_ws_bytes(B, tin, idim, c),), torch.uint8, inputs.device)
+        act = ws.get("subsample_act", (B * t2, f2 * c), torch.bfloat16, inputs.device)
+        ops.subsample_conv(inputs.contiguous(), W["w1"], W["b1"], W["w2"], W["b2"], scratch, act)
+        out = torch.zeros((B * t2, c), dtype=torch.float32, device=inputs.device)
+        ops.gemm(act, W["w3"], W["b3"], out, ops.N.EPI_RESIDUAL, residual=out, alpha=1.0)
+        return out.view(B, t2, c)

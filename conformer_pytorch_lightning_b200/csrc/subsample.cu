@@ -1,0 +1,319 @@
+// Conv2d sub-sampling front-end (row f1 of the scope table; reference src/convolution.py:52-76):
+//     Conv2d(1 -> C, 3, stride 2) + ReLU  ->  Conv2d(C -> C, 3, stride 2) + ReLU  ->  (Linear is a plain cfm_gemm)
+// on the bf16 path.  PyTorch/cuDNN needs ~3 ms for this at B = 64 x 10 s (the (B,C,T/2,39) activation alone is
+// 1.3 GB in fp32), more than the whole 12-layer stack on the tcgen05 kernels.
+//
+//   subsample_conv1_kernel   CUDA cores (9 MACs per output).  One warp per output position, lane = 8 channels,
+//                            512-byte coalesced bf16 stores.  Output layout is channels-last and PARITY-SPLIT:
+//                                P[b][pt][pf][th][fh][c]   with  t1 = 2*th + pt,  f1 = 2*fh + pf
+//                            so that the stride-2 gather of the second convolution becomes, per filter tap (i,j), a
+//                            dense box of plane (i%2, j%2) shifted by (i/2, j/2) -- i.e. a plain 5-D TMA load.
+//   subsample_conv2_kernel   tcgen05 implicit GEMM:  D[(t2,f2), co] = sum_{tap, ci} P[tap-shifted (t2,f2), ci] * W[co, tap, ci]
+//                            M tile = TL time rows x F2 frequency bins (6 x 19 = 114 of the 128 MMA rows), N = 256,
+//                            K = 9 taps x C in 64-wide blocks.  A tiles come straight from P through TMA (no im2col
+//                            buffer), B tiles from the (co, tap*C + ci) K-major weight; persistent, warp-specialised,
+//                            TMEM double buffered, bias + ReLU epilogue, bf16 TMA store into O[b][t2][f2][c]
+//                            (= the (B*T2, F2*C) row-major A operand of the Linear, whose weight columns the host
+//                            permutes from the reference's c*F2+f order to f*C+c).
+#include "cfm_common.cuh"
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace cfm {
+namespace {
+
+using namespace tc;
+
+// ------------------------------------------------------------------ conv1 + ReLU
+__global__ void __launch_bounds__(256)
+subsample_conv1_kernel(const float* __restrict__ x,      // (B, Tin, idim) fp32
+                       const float* __restrict__ w,      // (C, 9) fp32  [co][i*3+j]
+                       const float* __restrict__ bias,   // (C)
+                       __nv_bfloat16* __restrict__ P,    // (B, 2, 2, T1h, F1h, C) bf16
+                       int B, int Tin, int idim, int C, int T1, int F1, int T1h, int F1h) {
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.y;                  // group of 256 channels
+  const int c0 = cg * 256 + lane * 8;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    br[u] = bias[c0 + u];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[u][k] = w[(c0 + u) * 9 + k];
+  }
+  const long long n_pos = (long long)B * T1 * F1;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pos < n_pos; pos += warps) {
+    const int f1 = (int)(pos % F1);
+    const int t1 = (int)((pos / F1) % T1);
+    const int b = (int)(pos / ((long long)F1 * T1));
+    const float* xin = x + ((size_t)b * Tin + 2 * t1) * idim + 2 * f1;
+    float in[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) in[i * 3 + j] = __ldg(xin + i * idim + j);
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float a = br[u];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(in[k], wr[u][k], a);
+      o[u] = fmaxf(a, 0.f);
+    }
+    const int pt = t1 & 1, th = t1 >> 1, pf = f1 & 1, fh = f1 >> 1;
+    const size_t off = (((((size_t)b * 2 + pt) * 2 + pf) * T1h + th) * F1h + fh) * C + c0;
+    *reinterpret_cast<uint4*>(P + off) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// ------------------------------------------------------------------ conv2 + ReLU (implicit GEMM on tcgen05)
+constexpr int BK = 64, BN = 256;
+constexpr int kABytes = 128 * BK * 2;          // 16 KB slot (TL*F2 rows used)
+constexpr int kBBytes = BN * BK * 2;           // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStages = 3;
+constexpr int kBuf = 128 * 128;                // staging tile
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kBuf + BN * 4 + 256;
+static_assert(kSmemBytes <= 232448, "smem budget");
+
+struct Conv2Params {
+  const float* bias;
+  int B, C, T2, F2, TL;        // TL = time rows per tile (TL*F2 <= 128)
+  int tiles_per_utt, n_blocks; // n_blocks = C / 256
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+subsample_conv2_kernel(const __grid_constant__ CUtensorMap tmP,   // P as (C, F1h, T1h, 4 planes, B), box (64, F2, TL, 1, 1)
+                       const __grid_constant__ CUtensorMap tmW,   // W (C, 9*C) K-major, box (64, 256)
+                       const __grid_constant__ CUtensorMap tmO,   // O as (C, F2, T2, B), box (64, F2, TL, 1)
+                       const Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + kStages * kStageBytes;
+  float* sbias = reinterpret_cast<float*>(ring + 4 * kBuf);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + BN);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.B * p.tiles_per_utt * p.n_blocks;
+  const int kb_per_tap = p.C / BK;
+  const int kb_count = 9 * kb_per_tap;
+  const uint32_t a_bytes = (uint32_t)(p.TL * p.F2) * 128u;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmP); prefetch_tmap(&tmW); prefetch_tmap(&tmO); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 256); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t -> (n block, utterance, time-tile); n fastest so that neighbouring CTAs share the A tiles in L2
+  auto decode = [&](int t, int& nb, int& b, int& t20) {
+    nb = t % p.n_blocks;
+    const int mt = t / p.n_blocks;
+    b = mt / p.tiles_per_utt;
+    t20 = (mt % p.tiles_per_utt) * p.TL;
+  };
+
+  if (warp == 0) {
+    int stage = 0, phase = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int nb, b, t20;
+      decode(t, nb, b, t20);
+      for (int kb = 0; kb < kb_count; ++kb) {
+        const int tap = kb / kb_per_tap, kc = kb % kb_per_tap;
+        const int i = tap / 3, j = tap % 3;
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_expect_tx(full_bar + stage, a_bytes + kBBytes);
+          // plane (i%2, j%2) shifted by (i/2, j/2): rows (t2,f2) of the tile, 64 input channels
+          tma_load_5d(sa, &tmP, full_bar + stage, kc * BK, j >> 1, t20 + (i >> 1), (i & 1) * 2 + (j & 1), b);
+          tma_load_2d(sa + kABytes, &tmW, full_bar + stage, tap * p.C + kc * BK, nb * BN);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    int stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < kb_count; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar + stage);
+          if (kb == kb_count - 1) umma_commit(tfull_bar + acc);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // epilogue: two warpgroups x 128 columns, thread = tile row (rows >= TL*F2 are padding and never stored)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int grp = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128 - grp * 128;
+    const bool elected = (et == 0);
+    const int bar_id = 1 + grp;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    int sub_cnt = 0, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      int nb, b, t20;
+      decode(t, nb, b, t20);
+      sbias[grp * 128 + et] = p.bias[nb * BN + grp * 128 + et];
+      const uint32_t taddr = tmem_base + lane_base + acc * BN;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ss = 0; ss < 2; ++ss, ++sub_cnt) {
+        const int sub = grp * 2 + ss;
+        uint8_t* buf = ring + (grp * 2 + (sub_cnt & 1)) * kBuf;
+        if (elected) bulk_wait_read<1>();
+        named_bar_sync(bar_id, 128);
+        uint32_t v[64];
+        {
+          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          tmem_ld32(taddr + sub * 64, v0);
+          tmem_ld32(taddr + sub * 64 + 32, v1);
+        }
+        tmem_ld_wait();
+        const float* bs = sbias + sub * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * j + e]) + bs[8 * j + e], 0.f);
+          *reinterpret_cast<uint4*>(buf + r * 128 + (((j ^ r) & 7) << 4)) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (elected) {
+          tma_store_4d(&tmO, buf, nb * BN + sub * 64, 0, t20, b);   // box (64, F2, TL, 1): rows past T2 are clipped
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + acc);
+    }
+    if (elected) bulk_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+int make_map_nd(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
+  EncodeTiledFn fn = tc::encode_tiled_fn();
+  CFM_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r);
+  return 0;
+}
+
+}  // namespace
+}  // namespace cfm
+
+extern "C" int64_t cfm_subsample_ws_bytes(int B, int Tin, int idim, int C) {
+  const int T1 = (Tin - 3) / 2 + 1, F1 = (idim - 3) / 2 + 1;
+  const int64_t T1h = (T1 + 1) / 2, F1h = (F1 + 1) / 2;
+  return (int64_t)B * 4 * T1h * F1h * C * 2;
+}
+
+extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, const float* w1, const float* b1,
+                                  const void* w2, const float* b2, int C, void* ws, void* out, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(x && w1 && b1 && w2 && b2 && ws && out, "cfm_subsample_conv: null pointer");
+  CFM_CHECK_ARG(C % 256 == 0, "cfm_subsample_conv: C=%d must be a multiple of 256", C);
+  CFM_CHECK_ARG(Tin >= 7 && idim >= 7, "cfm_subsample_conv: input too small");
+  const int T1 = (Tin - 3) / 2 + 1, F1 = (idim - 3) / 2 + 1;
+  const int T2 = (T1 - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1;
+  CFM_CHECK_ARG(F2 >= 1 && F2 <= 128, "cfm_subsample_conv: F2=%d unsupported", F2);
+  if (B <= 0) return 0;
+  const int T1h = (T1 + 1) / 2, F1h = (F1 + 1) / 2;
+  const int TL = 128 / F2;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    const long long n_pos = (long long)B * T1 * F1;
+    const int blocks = (int)std::min<long long>((n_pos + 7) / 8, (long long)num_sms() * 16);
+    dim3 grid(blocks, C / 256);
+    subsample_conv1_kernel<<<grid, 256, 0, st>>>(x, w1, b1, (__nv_bfloat16*)ws, B, Tin, idim, C, T1, F1, T1h, F1h);
+    CFM_LAUNCHED();
+  }
+  CUtensorMap tmP, tmW, tmO;
+  int rc;
+  {
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)F1h, (uint64_t)T1h, 4, (uint64_t)B};
+    const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)F1h * C * 2, (uint64_t)T1h * F1h * C * 2, (uint64_t)4 * T1h * F1h * C * 2};
+    const uint32_t box[5] = {64, (uint32_t)F2, (uint32_t)TL, 1, 1};
+    if ((rc = make_map_nd(&tmP, ws, 5, dims, str, box)) != 0) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C};
+    const uint64_t str[1] = {(uint64_t)9 * C * 2};
+    const uint32_t box[2] = {64, 256};
+    if ((rc = make_map_nd(&tmW, w2, 2, dims, str, box)) != 0) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)F2, (uint64_t)T2, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)F2 * C * 2, (uint64_t)T2 * F2 * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)F2, (uint32_t)TL, 1};
+    if ((rc = make_map_nd(&tmO, out, 4, dims, str, box)) != 0) return rc;
+  }
+  Conv2Params p{b2, B, C, T2, F2, TL, (T2 + TL - 1) / TL, C / 256};
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFM_CUDA_OK(cudaFuncSetAttribute(subsample_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int total = B * p.tiles_per_utt * p.n_blocks;
+  const int grid = total < num_sms() ? total : num_sms();
+  subsample_conv2_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmP, tmW, tmO, p);
+  CFM_LAUNCHED();
+  return 0;
+}

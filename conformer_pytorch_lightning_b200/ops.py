@@ -160,3 +160,23 @@ def bn_apply_silu(x, mean, rstd, gamma, beta, y):
     N.check(N.lib().cfm_bn_apply_silu(x.data_ptr(), rows, d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                       beta.data_ptr(), y.data_ptr(), _DT[y.dtype], _stream(x)))
     return y
+
+
+def subsample_conv(x, w1, b1, w2, b2, ws, out):
+    """x (B,Tin,idim) fp32 -> out (B,T2,F2,C) bf16 = relu(conv2(relu(conv1(x)))); see cfm_subsample_conv."""
+    _req(x, "subsample_conv.x", torch.float32)
+    _req(w2, "subsample_conv.w2", torch.bfloat16)
+    _req(out, "subsample_conv.out", torch.bfloat16)
+    B, Tin, idim = x.shape
+    C = w1.shape[0]
+    ensure_init(x)
+    need = N.lib().cfm_subsample_ws_bytes(B, Tin, idim, C)
+    if ws.numel() * ws.element_size() < need:
+        raise RuntimeError("subsample_conv: workspace too small")
+    N.check(N.lib().cfm_subsample_conv(x.data_ptr(), B, Tin, idim, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                       b2.data_ptr(), C, ws.data_ptr(), out.data_ptr(), _stream(x)))
+    return out
+
+
+def subsample_ws_bytes(B, Tin, idim, C):
+    return int(N.lib().cfm_subsample_ws_bytes(B, Tin, idim, C))

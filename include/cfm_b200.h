@@ -158,6 +158,20 @@ int cfm_bn_stats(const float* x, int rows, int d, float* sum, float* sumsq, void
 int cfm_bn_apply_silu(const float* x, int rows, int d, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, void* y, int dtype, void* stream);
 
+/*
+ * Conv2d sub-sampling front-end on the bf16 path (scope row f1; convolution.py:52-76 without the final Linear, which
+ * is a cfm_gemm):  out = relu(conv2(relu(conv1(x)))), both convolutions 3x3 stride 2, no padding.
+ *   x   : (B, Tin, idim) fp32                     w1 : (C, 9) fp32 = conv.0.weight (C,1,3,3), b1 (C) fp32
+ *   w2  : (C, 9*C) bf16 with k = (i*3+j)*C + ci   (= conv.2.weight.permute(0,2,3,1)), b2 (C) fp32
+ *   ws  : scratch of cfm_subsample_ws_bytes() bytes (the parity-split channels-last conv1 activation)
+ *   out : (B, T2, F2, C) bf16, i.e. the (B*T2, F2*C) row-major input of the Linear with columns ordered f*C + c
+ *         (the reference orders them c*F2 + f: permute the Linear weight accordingly).
+ * T1 = (Tin-3)/2+1, T2 = (T1-3)/2+1, F1 = (idim-3)/2+1, F2 = (F1-3)/2+1.  C % 256 == 0.
+ */
+int64_t cfm_subsample_ws_bytes(int B, int Tin, int idim, int C);
+int cfm_subsample_conv(const float* x, int B, int Tin, int idim, const float* w1, const float* b1,
+                       const void* w2, const float* b2, int C, void* ws, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
