@@ -348,3 +348,25 @@ def test_ffn_fused_tcgen05(M, F, mode):
         yio = yin.clone()
         ops.ffn(yio, w1, b1, w2, b2, x, alpha=0.5, ln={"y": yio, "g1": g1, "b1": be1, "y_row_valid": yv}, engine=N.ENGINE_TC)
         assert rel_err(x, x_ref) < 2e-3 and rel_err(yio.float(), y_ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,Tin,C", [(2, 200, 256), (64, 998, 256), (3, 131, 512), (1, 67, 256)])
+def test_native_subsampling_frontend(B, Tin, C):
+    """conv1 (CUDA cores) + conv2 (tcgen05 implicit GEMM with TMA-gathered taps) vs torch conv2d on the same weights."""
+    torch.manual_seed(0)
+    idim = 80
+    x = rnd(B, Tin, idim)
+    conv1 = torch.nn.Conv2d(1, C, 3, 2).to(DEV)
+    conv2 = torch.nn.Conv2d(C, C, 3, 2).to(DEV)
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        h = torch.relu(conv1(x.unsqueeze(1)))
+        ref = torch.relu(torch.nn.functional.conv2d(h.bfloat16().float(), conv2.weight.bfloat16().float(), conv2.bias, stride=2))
+    T2, F2 = ref.shape[2], ref.shape[3]
+    w1 = conv1.weight.detach().reshape(C, 9).contiguous()
+    w2 = conv2.weight.detach().permute(0, 2, 3, 1).reshape(C, 9 * C).bfloat16().contiguous()
+    ws = torch.empty(ops.subsample_ws_bytes(B, Tin, idim, C), dtype=torch.uint8, device=DEV)
+    out = torch.full((B, T2, F2, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.subsample_conv(x, w1, conv1.bias.detach(), w2, conv2.bias.detach(), ws, out)
+    got = out.float().permute(0, 3, 1, 2)          # (B, C, T2, F2)
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 1.5e-2
