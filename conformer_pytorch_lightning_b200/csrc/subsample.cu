@@ -25,46 +25,64 @@ namespace {
 using namespace tc;
 
 // ------------------------------------------------------------------ conv1 + ReLU
-__global__ void __launch_bounds__(256)
+// packed fp32 FMA (Blackwell): two independent fp32 FMAs per instruction
+__device__ __forceinline__ void ffma2(float2& d, float2 a, float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
+// One warp per (b, t1) output row: the three input rows it needs (3 x idim floats) are staged in shared memory once,
+// then the warp walks the F1 frequency bins; lane = 8 output channels (16-byte store, 512 B per warp and position).
+// 9 broadcast LDS + 36 packed FMAs per position -- the kernel is bound by the 650 MB it writes, not by issue.
+constexpr int kC1Warps = 8;
+__global__ void __launch_bounds__(kC1Warps * 32)
 subsample_conv1_kernel(const float* __restrict__ x,      // (B, Tin, idim) fp32
                        const float* __restrict__ w,      // (C, 9) fp32  [co][i*3+j]
                        const float* __restrict__ bias,   // (C)
                        __nv_bfloat16* __restrict__ P,    // (B, 2, 2, T1h, F1h, C) bf16
                        int B, int Tin, int idim, int C, int T1, int F1, int T1h, int F1h) {
-  const int lane = threadIdx.x & 31;
-  const int cg = blockIdx.y;                  // group of 256 channels
-  const int c0 = cg * 256 + lane * 8;
-  float wr[8][9], br[8];
+  extern __shared__ float srow[];             // [kC1Warps][3][idim]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float2 wr[4][9], br[4];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    br[u] = bias[c0 + u];
+  for (int u = 0; u < 4; ++u) {
+    br[u] = make_float2(bias[c0 + 2 * u], bias[c0 + 2 * u + 1]);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[u][k] = w[(c0 + u) * 9 + k];
+    for (int k = 0; k < 9; ++k) wr[u][k] = make_float2(w[(c0 + 2 * u) * 9 + k], w[(c0 + 2 * u + 1) * 9 + k]);
   }
-  const long long n_pos = (long long)B * T1 * F1;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long pos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pos < n_pos; pos += warps) {
-    const int f1 = (int)(pos % F1);
-    const int t1 = (int)((pos / F1) % T1);
-    const int b = (int)(pos / ((long long)F1 * T1));
-    const float* xin = x + ((size_t)b * Tin + 2 * t1) * idim + 2 * f1;
-    float in[9];
+  float* my = srow + warp * 3 * idim;
+  const int n_rows = B * T1;
+  for (int row = blockIdx.x * kC1Warps + warp; row < n_rows; row += gridDim.x * kC1Warps) {
+    const int b = row / T1, t1 = row % T1;
+    const float* xin = x + ((size_t)b * Tin + 2 * t1) * idim;
+    __syncwarp();
+    for (int i = lane; i < 3 * idim; i += 32) my[i] = __ldg(xin + i);
+    __syncwarp();
+    const int pt = t1 & 1, th = t1 >> 1;
+    __nv_bfloat16* prow0 = P + ((((size_t)b * 2 + pt) * 2 + 0) * T1h + th) * (size_t)F1h * C + c0;
+    __nv_bfloat16* prow1 = P + ((((size_t)b * 2 + pt) * 2 + 1) * T1h + th) * (size_t)F1h * C + c0;
+    for (int f1 = 0; f1 < F1; ++f1) {
+      float in[9];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) in[i * 3 + j] = __ldg(xin + i * idim + j);
-    float o[8];
+        for (int j = 0; j < 3; ++j) in[i * 3 + j] = my[i * idim + 2 * f1 + j];
+      float2 o[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float a = br[u];
+      for (int u = 0; u < 4; ++u) {
+        o[u] = br[u];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(in[k], wr[u][k], a);
-      o[u] = fmaxf(a, 0.f);
+        for (int k = 0; k < 9; ++k) ffma2(o[u], make_float2(in[k], in[k]), wr[u][k]);
+      }
+      __nv_bfloat16* dst = ((f1 & 1) ? prow1 : prow0) + (size_t)(f1 >> 1) * C;
+      *reinterpret_cast<uint4*>(dst) =
+          make_uint4(pack_bf16x2(fmaxf(o[0].x, 0.f), fmaxf(o[0].y, 0.f)), pack_bf16x2(fmaxf(o[1].x, 0.f), fmaxf(o[1].y, 0.f)),
+                     pack_bf16x2(fmaxf(o[2].x, 0.f), fmaxf(o[2].y, 0.f)), pack_bf16x2(fmaxf(o[3].x, 0.f), fmaxf(o[3].y, 0.f)));
     }
-    const int pt = t1 & 1, th = t1 >> 1, pf = f1 & 1, fh = f1 >> 1;
-    const size_t off = (((((size_t)b * 2 + pt) * 2 + pf) * T1h + th) * F1h + fh) * C + c0;
-    *reinterpret_cast<uint4*>(P + off) =
-        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
   }
 }
 
@@ -279,10 +297,12 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
   const int TL = 128 / F2;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const long long n_pos = (long long)B * T1 * F1;
-    const int blocks = (int)std::min<long long>((n_pos + 7) / 8, (long long)num_sms() * 16);
+    const int n_rows = B * T1;
+    const int blocks = std::min((n_rows + kC1Warps - 1) / kC1Warps, num_sms() * 8);
     dim3 grid(blocks, C / 256);
-    subsample_conv1_kernel<<<grid, 256, 0, st>>>(x, w1, b1, (__nv_bfloat16*)ws, B, Tin, idim, C, T1, F1, T1h, F1h);
+    const size_t sm = (size_t)kC1Warps * 3 * idim * sizeof(float);
+    CFM_CHECK_ARG(sm <= 48 * 1024, "cfm_subsample_conv: idim=%d too large", idim);
+    subsample_conv1_kernel<<<grid, kC1Warps * 32, sm, st>>>(x, w1, b1, (__nv_bfloat16*)ws, B, Tin, idim, C, T1, F1, T1h, F1h);
     CFM_LAUNCHED();
   }
   CUtensorMap tmP, tmW, tmO;
