@@ -172,6 +172,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     constexpr uint32_t idesc1 = umma_idesc_bf16(BM, 128);   // G1: N = 128 hidden units
     constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 256);   // G2: N = 256 outputs
     int stage = 0, phase = 0, it = 0;
+    bool have = false;   // w_full of the current slot already seen complete by the probe issued before the previous MMAs
     uint32_t n_se0 = 0, n_se1 = 0, n_hf0 = 0, n_hf1 = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
@@ -182,16 +183,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         bool g1; int c;
         job_of(jx, NC, g1, c);
         const int b = c & 1;
-        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + jx] = clock64();
         if (g1) {
           uint32_t& n_se = b ? n_se1 : n_se0;
           mbar_wait(s_empty + b, (n_se & 1) ^ 1);         // SiLU stage drained S[b] (two chunks ago)
           ++n_se;
           tc_fence_after();
-          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
           for (int pc = 0; pc < 2; ++pc) {
-            mbar_wait(w_full + stage, phase);
+            if (!have) mbar_wait(w_full + stage, phase);
             tc_fence_after();
+            {   // probe the next slot now; the result is consumed after this piece's MMAs have been issued
+              const int ns = (stage + 1 == NST) ? 0 : stage + 1;
+              have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
+            }
             if (elect_one()) {
               const uint32_t w_addr = smem_u32(sW + stage * kPiece);
 #pragma unroll
@@ -213,10 +216,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           mbar_wait(h_full + b, n_hf & 1);                // H[b] written (and fenced) by the SiLU stage
           ++n_hf;
           tc_fence_after();
-          if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + jx] = clock64();
           for (int pc = 0; pc < 2; ++pc) {                // pc = 64-wide k atom of the hidden chunk
-            mbar_wait(w_full + stage, phase);
+            if (!have) mbar_wait(w_full + stage, phase);
             tc_fence_after();
+            {   // probe the next slot now; the result is consumed after this piece's MMAs have been issued
+              const int ns = (stage + 1 == NST) ? 0 : stage + 1;
+              have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
+            }
             if (elect_one()) {
               const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
               const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));

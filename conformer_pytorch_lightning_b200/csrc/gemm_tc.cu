@@ -180,14 +180,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     int stage = 0, phase = 0, it = 0;
+    bool have = false;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        if (!have) mbar_wait(full_bar + stage, phase);
         tc_fence_after();
+        {   // probe the next slot; consumed after this stage's MMAs have been issued
+          const int ns = (stage + 1 == C::kStages) ? 0 : stage + 1;
+          have = mbar_test(full_bar + ns, (stage + 1 == C::kStages) ? (phase ^ 1) : phase);
+        }
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + C::kABytes);

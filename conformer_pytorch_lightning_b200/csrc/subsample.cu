@@ -181,14 +181,19 @@ subsample_conv2_kernel(const __grid_constant__ CUtensorMap tmP,   // P as (C, F1
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
     int stage = 0, phase = 0, it = 0;
+    bool have = false;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        if (!have) mbar_wait(full_bar + stage, phase);
         tc_fence_after();
+        {   // probe the next slot; consumed after this stage's MMAs have been issued
+          const int ns = (stage + 1 == kStages) ? 0 : stage + 1;
+          have = mbar_test(full_bar + ns, (stage + 1 == kStages) ? (phase ^ 1) : phase);
+        }
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
