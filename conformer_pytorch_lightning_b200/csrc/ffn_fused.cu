@@ -138,34 +138,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kAtom, &tmA, a_full, ka * 64, m0);
       }
       __syncwarp();
-      // L2 prefetch of weight pieces kPF slots ahead of the ring (a few CTAs do it for everybody: all CTAs walk the
-      // same weights in near lock-step).  Weights are cold in L2 inside a forward pass, and three 32 KB slots cannot
-      // cover HBM latency at the 55 GB/s per SM this kernel consumes.
-      constexpr int kPF = 10;
-      const bool prefetcher = blockIdx.x < 4 * CL;
-      auto prefetch_piece = [&](int q) {
-        bool pg1; int pcn;
-        job_of(q >> 1, NC, pg1, pcn);
-        const int ppc = q & 1;
-        if (pg1) {
-          tma_prefetch_2d(&tmW1, ppc * 128, pcn * HC);
-          tma_prefetch_2d(&tmW1, ppc * 128 + 64, pcn * HC);
-        } else {
-          tma_prefetch_2d(&tmW2, pcn * HC + ppc * 64, 0);
-          tma_prefetch_2d(&tmW2, pcn * HC + ppc * 64, 128);
-        }
-      };
-      if (prefetcher && elect_one()) {
-        for (int q = 0; q < kPF && q < 2 * n_jobs; ++q) prefetch_piece(q);
-      }
-      __syncwarp();
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NC, g1, c);
         for (int pc = 0; pc < 2; ++pc) {
           mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
           if (elect_one()) {
-            if (prefetcher && 2 * jx + pc + kPF < 2 * n_jobs) prefetch_piece(2 * jx + pc + kPF);
             uint8_t* dst = sW + stage * kPiece;
             mbar_expect_tx(w_full + stage, kPiece);
             if (g1) {          // W1_c[:, pc*128 .. +128): atoms a = 0,1 at k = pc*128 + a*64

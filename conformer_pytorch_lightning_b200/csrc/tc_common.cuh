@@ -107,14 +107,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// TMA prefetch of a box into L2 only (no shared memory, no barrier): used to run ahead of a latency-bound ring when
-// the operand is cold in L2 (weights are touched once per forward pass and the pass streams more than L2 holds)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-
 // multicast variant: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each of
 // those CTAs gets the complete_tx on ITS mbarrier at the same offset
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
