@@ -354,7 +354,6 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + QT - 1) / QT, H, B);
-  CFM_MAX_CARVEOUT(attention_tc_kernel);
   attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, p);
   CFM_LAUNCHED();
   return 0;

@@ -101,18 +101,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Every kernel of the layer stack asks for the maximum shared-memory carve-out, including the ones that need little:
-// consecutive kernels with different carve-outs make the SMs drain and re-partition L1/shared memory at each launch
-// boundary (measured as ~4 us per launch inside the CUDA graph of the layer stack).
-#define CFM_MAX_CARVEOUT(kernel)                                                                         \
-  do {                                                                                                   \
-    static bool _done = false;                                                                           \
-    if (!_done) {                                                                                        \
-      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      _done = true;                                                                                      \
-    }                                                                                                    \
-  } while (0)
-
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -129,9 +129,6 @@ int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, 
   dim3 grid((Tlen + kDwTT - 1) / kDwTT, d / kDwCG, B);
   const size_t smem = (size_t)(kDwTT + k - 1) * kDwCG * sizeof(float);
   const T* xx = (const T*)x;
-  CFM_MAX_CARVEOUT((dwconv_kernel<T, 15, SILU>));
-  CFM_MAX_CARVEOUT((dwconv_kernel<T, 31, SILU>));
-  CFM_MAX_CARVEOUT((dwconv_kernel<T, 0, SILU>));
   if (k == 15) dwconv_kernel<T, 15, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);
   else if (k == 31) dwconv_kernel<T, 31, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);
   else dwconv_kernel<T, 0, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);

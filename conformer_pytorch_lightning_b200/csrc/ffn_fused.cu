@@ -346,8 +346,6 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
     CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   const int CL = cl_env;
-  CFM_MAX_CARVEOUT(ffn_fused_kernel<1>);
-  CFM_MAX_CARVEOUT(ffn_fused_kernel<2>);
   CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
   int rc;
   if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;

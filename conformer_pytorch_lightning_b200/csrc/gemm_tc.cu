@@ -316,7 +316,6 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
     CFM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  CFM_MAX_CARVEOUT((gemm_tc_kernel<BN, EPI>));
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();

@@ -78,8 +78,6 @@ template <int NV>
 int launch_ln(const float* x, int rows, const float* g1, const float* b1, float* x_out, const float* g2,
               const float* b2, void* y, int y_dtype, const uint8_t* rv, float eps, cudaStream_t st) {
   const int blocks = max(1, min((rows + 7) / 8, num_sms() * 8));
-  CFM_MAX_CARVEOUT((layernorm_kernel<NV, float>));
-  CFM_MAX_CARVEOUT((layernorm_kernel<NV, __nv_bfloat16>));
   if (y_dtype == CFM_F32)
     layernorm_kernel<NV, float><<<blocks, 256, 0, st>>>(x, rows, g1, b1, x_out, g2, b2, (float*)y, rv, eps);
   else

@@ -336,8 +336,6 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
     CFM_CUDA_OK(cudaFuncSetAttribute(subsample_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  CFM_MAX_CARVEOUT(subsample_conv2_kernel);
-  CFM_MAX_CARVEOUT(subsample_conv1_kernel);
   const int total = B * p.tiles_per_utt * p.n_blocks;
   const int grid = total < num_sms() ? total : num_sms();
   subsample_conv2_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmP, tmW, tmO, p);
