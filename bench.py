@@ -268,6 +268,10 @@ def run_ours(args):
     pk = peaks()
     n_tok, d, F = B * T, cfg["encoder_dim"], cfg["hidden_dim"]
     ev = {"ffn": [], "dw": []}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.workload == "C2":      # ncu captures were taken on the C2 shapes
+        traffic = json.load(open(tpath))
 
     def wrap(mod, name, key):
         orig = getattr(mod, name)
@@ -304,14 +308,18 @@ def run_ours(args):
     roofline = {"bound": "tensor",
                 "kernel": f"ffn_fused_kernel (w_1+SiLU+w_2+residual+LayerNorm in one kernel) M={n_tok} d={d} F={F}",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "launch_us": t_ffn * 1e3, "launches_per_step": n_ffn,
+                "traffic": (traffic["ffn_fused_kernel"]["dram_read_bytes"] + traffic["ffn_fused_kernel"]["dram_write_bytes"])
+                if "ffn_fused_kernel" in traffic else None,
+                "launch_us": t_ffn * 1e3, "launches_per_step": n_ffn,
                 "share_of_step": n_ffn * t_ffn / ms_per_step,
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside the step)"}
     dw_bytes = 2.0 * n_tok * d * 2                    # read + write one bf16 (N,d) tensor
     ach_dw = dw_bytes / (t_dw * 1e-3) / 1e9
     roofline_hbm = {"bound": "hbm", "kernel": f"dwconv_kernel k={cfg['kernel_size']} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
                     "achieved": ach_dw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_dw / pk["hbm_gbs"],
-                    "traffic": None, "launch_us": t_dw * 1e3, "launches_per_step": cfg["encoder_num_layers"],
+                    "traffic": (traffic["dwconv_kernel"]["dram_read_bytes"] + traffic["dwconv_kernel"]["dram_write_bytes"])
+                    if "dwconv_kernel" in traffic else None,
+                    "launch_us": t_dw * 1e3, "launches_per_step": cfg["encoder_num_layers"],
                     "peak_source": pk["source"]}
 
     if rank == 0:
