@@ -101,9 +101,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                   // nothing above touches global memory produced by the previous kernel
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
@@ -354,7 +356,7 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + QT - 1) / QT, H, B);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  CFM_CUDA_OK(launch_pdl(attention_tc_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
   CFM_LAUNCHED();
   return 0;
 }

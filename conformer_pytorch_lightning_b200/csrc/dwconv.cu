@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(128)
 dwconv_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
               void* __restrict__ y, int Tlen, int d, int k_rt) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = (K > 0) ? K : k_rt;
   const int pad = (k - 1) / 2;
   const int t0 = blockIdx.x * kDwTT;
@@ -129,9 +131,9 @@ int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, 
   dim3 grid((Tlen + kDwTT - 1) / kDwTT, d / kDwCG, B);
   const size_t smem = (size_t)(kDwTT + k - 1) * kDwCG * sizeof(float);
   const T* xx = (const T*)x;
-  if (k == 15) dwconv_kernel<T, 15, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);
-  else if (k == 31) dwconv_kernel<T, 31, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);
-  else dwconv_kernel<T, 0, SILU><<<grid, 128, smem, st>>>(xx, w, bias, y, Tlen, d, k);
+  if (k == 15) CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 15, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
+  else if (k == 31) CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 31, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
+  else CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 0, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
   CFM_LAUNCHED();
   return 0;
 }

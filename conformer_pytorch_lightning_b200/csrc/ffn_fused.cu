@@ -119,10 +119,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
 
@@ -359,21 +361,10 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
   const int m_tiles = ((M + BM - 1) / BM + CL - 1) / CL * CL;
   const int max_ctas = num_sms() / CL * CL;
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
-  if (CL == 1) {
-    ffn_fused_kernel<1><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmW1, tmW2, tmX, tmX, tmY, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, ffn_fused_kernel<2>, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
-  }
+  if (CL == 1)
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
+  else
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
   CFM_LAUNCHED();
   return 0;
 }

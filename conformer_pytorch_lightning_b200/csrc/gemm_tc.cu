@@ -148,9 +148,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -319,7 +321,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, EPI><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmA, tmW, tmC, tmR, tmY, p);
+  CFM_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmA, tmW, tmC, tmR, tmY, p));
   CFM_LAUNCHED();
   return 0;
 }

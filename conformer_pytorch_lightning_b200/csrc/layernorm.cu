@@ -40,6 +40,8 @@ layernorm_kernel(const float* x, int rows, const float* __restrict__ g1,
                  const float* __restrict__ g2, const float* __restrict__ b2, TY* __restrict__ y,
                  const uint8_t* __restrict__ row_valid, float eps) {
   constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps_per_grid) {
@@ -79,10 +81,11 @@ int launch_ln(const float* x, int rows, const float* g1, const float* b1, float*
               const float* b2, void* y, int y_dtype, const uint8_t* rv, float eps, cudaStream_t st) {
   const int blocks = max(1, min((rows + 7) / 8, num_sms() * 8));
   if (y_dtype == CFM_F32)
-    layernorm_kernel<NV, float><<<blocks, 256, 0, st>>>(x, rows, g1, b1, x_out, g2, b2, (float*)y, rv, eps);
+    CFM_CUDA_OK(launch_pdl(layernorm_kernel<NV, float>, dim3(blocks), dim3(256), 0, st, 1, x, rows, g1, b1, x_out, g2, b2,
+                           (float*)y, rv, eps));
   else
-    layernorm_kernel<NV, __nv_bfloat16><<<blocks, 256, 0, st>>>(x, rows, g1, b1, x_out, g2, b2,
-                                                               (__nv_bfloat16*)y, rv, eps);
+    CFM_CUDA_OK(launch_pdl(layernorm_kernel<NV, __nv_bfloat16>, dim3(blocks), dim3(256), 0, st, 1, x, rows, g1, b1, x_out,
+                           g2, b2, (__nv_bfloat16*)y, rv, eps));
   CFM_LAUNCHED();
   return 0;
 }

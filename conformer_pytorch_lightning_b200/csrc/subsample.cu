@@ -45,6 +45,8 @@ subsample_conv1_kernel(const float* __restrict__ x,      // (B, Tin, idim) fp32
                        __nv_bfloat16* __restrict__ P,    // (B, 2, 2, T1h, F1h, C) bf16
                        int B, int Tin, int idim, int C, int T1, int F1, int T1h, int F1h) {
   extern __shared__ float srow[];             // [kC1Warps][3][idim]
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.y * 256 + lane * 8;
   float2 wr[4][9], br[4];
@@ -145,9 +147,11 @@ subsample_conv2_kernel(const __grid_constant__ CUtensorMap tmP,   // P as (C, F1
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   // tile t -> (n block, utterance, time-tile); n fastest so that neighbouring CTAs share the A tiles in L2
@@ -307,7 +311,8 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
     dim3 grid(blocks, C / 256);
     const size_t sm = (size_t)kC1Warps * 3 * idim * sizeof(float);
     CFM_CHECK_ARG(sm <= 48 * 1024, "cfm_subsample_conv: idim=%d too large", idim);
-    subsample_conv1_kernel<<<grid, kC1Warps * 32, sm, st>>>(x, w1, b1, (__nv_bfloat16*)ws, B, Tin, idim, C, T1, F1, T1h, F1h);
+    CFM_CUDA_OK(launch_pdl(subsample_conv1_kernel, grid, dim3(kC1Warps * 32), sm, st, 1, x, w1, b1, (__nv_bfloat16*)ws, B, Tin,
+                           idim, C, T1, F1, T1h, F1h));
     CFM_LAUNCHED();
   }
   CUtensorMap tmP, tmW, tmO;
@@ -338,7 +343,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
   }
   const int total = B * p.tiles_per_utt * p.n_blocks;
   const int grid = total < num_sms() ? total : num_sms();
-  subsample_conv2_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmP, tmW, tmO, p);
+  CFM_CUDA_OK(launch_pdl(subsample_conv2_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmP, tmW, tmO, p));
   CFM_LAUNCHED();
   return 0;
 }
