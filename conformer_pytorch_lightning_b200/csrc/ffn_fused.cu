@@ -181,66 +181,85 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       mbar_wait(a_full, it & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
-      for (int jx = 0; jx < n_jobs; ++jx) {
-        bool g1; int c;
-        job_of(jx, NC, g1, c);
+      // The issuing warp runs in lock-step with the tensor pipe (it accepts only a few MMAs ahead), so every cycle
+      // between two issue blocks is an idle pipe cycle.  The job sequence  G1(0) G1(1) | G2(c) G1(c+2) ... | G2 G2  is
+      // therefore written out without any per-job decoding, and the barrier of the NEXT issue block (ring slot or
+      // S/H hand-over) is probed non-blockingly before the current block's MMAs are issued.
+      bool job_ready = false;           // the next job's S/H barrier was already seen complete
+      auto next_slot_probe = [&]() {
+        const int ns = (stage + 1 == NST) ? 0 : stage + 1;
+        have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
+      };
+      auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
+      // probe used while issuing the last piece of a job: is the barrier of the following job complete?
+      auto probe_g1 = [&](int c) { const int b = c & 1; return mbar_test(s_empty + b, ((b ? n_se1 : n_se0) & 1) ^ 1); };
+      auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + b, (b ? n_hf1 : n_hf0) & 1); };
+
+      auto do_g1 = [&](int c, int next_kind, int next_c) {     // next_kind: 1 = G1, 2 = G2, 0 = none
         const int b = c & 1;
-        if (g1) {
-          uint32_t& n_se = b ? n_se1 : n_se0;
-          mbar_wait(s_empty + b, (n_se & 1) ^ 1);         // SiLU stage drained S[b] (two chunks ago)
-          ++n_se;
+        uint32_t& n_se = b ? n_se1 : n_se0;
+        if (!job_ready) mbar_wait(s_empty + b, (n_se & 1) ^ 1);     // SiLU stage drained S[b] (two chunks ago)
+        ++n_se;
+        tc_fence_after();
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          if (!have) mbar_wait(w_full + stage, phase);
           tc_fence_after();
-          for (int pc = 0; pc < 2; ++pc) {
-            if (!have) mbar_wait(w_full + stage, phase);
-            tc_fence_after();
-            {   // probe the next slot now; the result is consumed after this piece's MMAs have been issued
-              const int ns = (stage + 1 == NST) ? 0 : stage + 1;
-              have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
-            }
-            if (elect_one()) {
-              const uint32_t w_addr = smem_u32(sW + stage * kPiece);
+          next_slot_probe();
+          if (pc == 1) job_ready = (next_kind == 1) ? probe_g1(next_c) : (next_kind == 2 ? probe_g2(next_c) : false);
+          if (elect_one()) {
+            const uint32_t w_addr = smem_u32(sW + stage * kPiece);
 #pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
-                const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
+            for (int a = 0; a < 2; ++a) {
+              const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
+              const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
-              }
-              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-              if (pc == 1) umma_commit(s_full + b);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
             }
-            __syncwarp();
-            if (++stage == NST) { stage = 0; phase ^= 1; }
+            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+            if (pc == 1) umma_commit(s_full + b);
           }
-        } else {
-          uint32_t& n_hf = b ? n_hf1 : n_hf0;
-          mbar_wait(h_full + b, n_hf & 1);                // H[b] written (and fenced) by the SiLU stage
-          ++n_hf;
-          tc_fence_after();
-          for (int pc = 0; pc < 2; ++pc) {                // pc = 64-wide k atom of the hidden chunk
-            if (!have) mbar_wait(w_full + stage, phase);
-            tc_fence_after();
-            {   // probe the next slot now; the result is consumed after this piece's MMAs have been issued
-              const int ns = (stage + 1 == NST) ? 0 : stage + 1;
-              have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
-            }
-            if (elect_one()) {
-              const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
-              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
-              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-              if (pc == 1) {
-                umma_commit(h_empty + b);
-                if (jx == n_jobs - 1) umma_commit(y_full);
-              }
-            }
-            __syncwarp();
-            if (++stage == NST) { stage = 0; phase ^= 1; }
-          }
+          __syncwarp();
+          advance();
         }
+      };
+      auto do_g2 = [&](int c, int next_kind, int next_c, bool last) {
+        const int b = c & 1;
+        uint32_t& n_hf = b ? n_hf1 : n_hf0;
+        if (!job_ready) mbar_wait(h_full + b, n_hf & 1);             // H[b] written (and fenced) by the SiLU stage
+        ++n_hf;
+        tc_fence_after();
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {                             // pc = 64-wide k atom of the hidden chunk
+          if (!have) mbar_wait(w_full + stage, phase);
+          tc_fence_after();
+          next_slot_probe();
+          if (pc == 1) job_ready = (next_kind == 1) ? probe_g1(next_c) : (next_kind == 2 ? probe_g2(next_c) : false);
+          if (elect_one()) {
+            const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
+            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+            if (pc == 1) {
+              umma_commit(h_empty + b);
+              if (last) umma_commit(y_full);
+            }
+          }
+          __syncwarp();
+          advance();
+        }
+      };
+      job_ready = false;
+      do_g1(0, 1, 1);
+      do_g1(1, 2, 0);
+      for (int c = 0; c + 2 < NC; ++c) {
+        do_g2(c, 1, c + 2, false);
+        do_g1(c + 2, 2, c + 1);
       }
+      do_g2(NC - 2, 2, NC - 1, false);
+      do_g2(NC - 1, 0, 0, true);
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
