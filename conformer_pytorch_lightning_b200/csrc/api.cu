@@ -120,6 +120,40 @@ extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1
                      eps, engine == CFM_ENGINE_TC ? CFM_ENGINE_AUTO : engine, stream);
 }
 
+extern "C" int cfm_conv_module(const void* y, const void* W1, const float* b1, const float* dw_w, const float* dw_b,
+                               const void* W2, const float* b2, float* X, int B, int T, int d, int k, int dtype,
+                               const uint8_t* row_valid, const float* g1, const float* be1, void* Y, float eps,
+                               void* glu_ws, void* dw_ws, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(y && W1 && b1 && dw_w && dw_b && W2 && b2 && X, "cfm_conv_module: null pointer");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_conv_module: bad dtype %d", dtype);
+  CFM_CHECK_ARG((g1 == nullptr) == (be1 == nullptr), "cfm_conv_module: inconsistent LayerNorm parameters");
+  CFM_CHECK_ARG(g1 == nullptr || (Y != nullptr && Y != y), "cfm_conv_module: LayerNorm output Y must be a buffer other than y");
+  CFM_CHECK_ARG(B >= 0 && T >= 0 && d > 0 && k > 0 && (k & 1), "cfm_conv_module: bad shape");
+  const int M = B * T;
+  if (M == 0) return 0;
+  // CFM_B200_CONV_MODE: "unfused" = always the three-kernel chain
+  static int unfused_mode = -1;
+  if (unfused_mode < 0) {
+    const char* e = getenv("CFM_B200_CONV_MODE");
+    unfused_mode = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
+  }
+  const bool fused_ok = conv_fused_supported(M, T, d, k, dtype);
+  if (engine == CFM_ENGINE_TC)
+    CFM_CHECK_ARG(fused_ok, "cfm_conv_module: fused tcgen05 path does not support T=%d d=%d k=%d dtype=%d", T, d, k, dtype);
+  if (fused_ok && (engine == CFM_ENGINE_TC || (engine == CFM_ENGINE_AUTO && !unfused_mode)))
+    return conv_fused(y, W1, b1, dw_w, dw_b, W2, b2, X, M, T, row_valid, g1, be1, Y, eps, (cudaStream_t)stream);
+  CFM_CHECK_ARG(glu_ws != nullptr && dw_ws != nullptr, "cfm_conv_module: the unfused path needs glu_ws and dw_ws");
+  int rc = cfm_gemm(y, d, W1, b1, glu_ws, d, M, d, d, dtype, CFM_EPI_BIAS_GLU, nullptr, 1.f, nullptr, engine, stream);
+  if (rc != 0) return rc;
+  rc = cfm_dwconv(glu_ws, dw_w, dw_b, dw_ws, B, T, d, k, dtype, 1, stream);
+  if (rc != 0) return rc;
+  if (g1 == nullptr)
+    return cfm_gemm(dw_ws, d, W2, b2, X, d, M, d, d, dtype, CFM_EPI_RESIDUAL, X, 1.f, row_valid, engine, stream);
+  return cfm_gemm_ln(dw_ws, d, W2, b2, X, d, M, d, d, dtype, 1.f, row_valid, g1, be1, nullptr, nullptr, Y, d, nullptr, eps,
+                     engine, stream);
+}
+
 extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                              const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
                              const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,

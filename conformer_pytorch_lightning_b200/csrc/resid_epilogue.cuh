@@ -38,12 +38,13 @@ __device__ __forceinline__ void resid_stage_params(float* sparam, int et, const 
   }
 }
 
-// issue the TMA loads of the first min(R, BN/32) residual chunks (elected thread only)
-template <int BN, int R>
+// issue the TMA loads of the first min(R, BN/32) residual chunks (elected thread only).  ROWS = rows of the TMA box
+// (128 for GEMM tiles; the fused conv module stores only its 128-(k-1) interior rows).
+template <int BN, int R, int ROWS = 128>
 __device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar, const CUtensorMap* tmR, int n0, int m0) {
 #pragma unroll
   for (int c = 0; c < (BN / 32 < R ? BN / 32 : R); ++c) {
-    mbar_expect_tx(res_bar + c, kBufBytes);
+    mbar_expect_tx(res_bar + c, ROWS * 128);
     tma_load_2d(ring + c * kBufBytes, tmR, res_bar + c, n0 + c * 32, m0);
   }
 }
@@ -52,7 +53,7 @@ __device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar,
 // resid_stage_params + resid_prefetch done.  `taddr` = TMEM address of this thread's row, column 0 of the accumulator.
 // `bar_id` names a 128-thread barrier private to the calling warpgroup.  On return every TMEM access of the thread
 // has completed and all TMA stores have finished READING the ring (it may be overwritten).
-template <int BN, int R>
+template <int BN, int R, int ROWS = 128>
 __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0, int n0, bool elected, int bar_id,
                                                   uint8_t* ring, uint64_t* res_bar, uint32_t& ring_phase,
                                                   const float* sparam, const CUtensorMap* tmX, const CUtensorMap* tmR,
@@ -101,11 +102,11 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
         if (c >= 1 && c - 1 + R < NCH) {
           bulk_wait_read<1>();
           const int pb = (c - 1) % R;
-          mbar_expect_tx(res_bar + pb, kBufBytes);
+          mbar_expect_tx(res_bar + pb, ROWS * 128);
           tma_load_2d(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (c - 1 + R) * 32, m0);
         }
       } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
-        mbar_expect_tx(res_bar + b, kBufBytes);
+        mbar_expect_tx(res_bar + b, ROWS * 128);
         tma_load_2d(buf, tmR, res_bar + b, n0 + (c + R) * 32, m0);
       }
     }

@@ -234,8 +234,14 @@ def conv_into(x, y, B, T, W, row_valid, module, ws, ln=None):
     n, d = y.shape
     dev, dt = y.device, y.dtype
     g = ws.get("conv_glu", (n, d), dt, dev)
-    ops.gemm(y, W["w1"], W["b1"], g, N.EPI_BIAS_GLU)
     c = ws.get("conv_dw", (n, d), dt, dev)
+    if not module.training and y.is_contiguous() and x.is_contiguous() and (ln is None or ln.get("g2") is None):
+        # inference: one library call -- a single fused kernel on the tcgen05 engine (bf16, d=256, k=15), the
+        # GLU-GEMM / depthwise / GEMM(+LN) chain through g, c otherwise
+        ops.conv_module(y, W["w1"], W["b1"], W["dw_w"], W["dw_b"], W["w2"], W["b2"], x, B, T, row_valid=row_valid, ln=ln,
+                        glu_ws=g, dw_ws=c)
+        return
+    ops.gemm(y, W["w1"], W["b1"], g, N.EPI_BIAS_GLU)
     if not module.training:
         ops.dwconv(g.view(B, T, d), W["dw_w"], W["dw_b"], c.view(B, T, d), apply_silu=True)
     else:
@@ -280,6 +286,7 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
     x = torch.empty((n, d), dtype=torch.float32, device=dev)
     x.copy_(inputs.reshape(n, d))
     y = ws.get("ln_y", (n, d), dtype, dev)
+    y2 = ws.get("ln_y2", (n, d), dtype, dev)
     row_valid = _row_valid(pad_mask, B, T)
     attn_mask = _mask_u8(attn_mask)          # normalised once, not per layer
     new_caches = []
@@ -294,15 +301,16 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
         cache = attn_caches[i] if attn_caches is not None else None
         new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws,
                                     ln={"y": y, "g1": Wl["conv_g"], "b1": Wl["conv_b"], "y_row_valid": row_valid}))
+        # the fused convolution module reads a halo of neighbouring rows of y, so its LayerNorm output goes to y2
         conv_into(x, y, B, T, Wl["conv"], row_valid, layer.conv_module, ws,
-                  ln={"y": y, "g1": Wl["ff_g"], "b1": Wl["ff_b"]})
+                  ln={"y": y2, "g1": Wl["ff_g"], "b1": Wl["ff_b"]})
         if i + 1 < len(layers):
             Wn = layers[i + 1].derived_weights(dtype)
             # norm_final of this layer chained with norm_ff_macaron of the next one
-            ffn_into(x, y, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
-                                                  "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})
+            ffn_into(x, y2, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
+                                                   "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})
         else:
-            ffn_into(x, y, Wl["ff"], 0.5, ws)
+            ffn_into(x, y2, Wl["ff"], 0.5, ws)
             if after_norm is not None:
                 out = torch.empty((n, d), dtype=torch.float32, device=dev)
                 ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], g2=_f32(after_norm.weight), b2=_f32(after_norm.bias), y=out)

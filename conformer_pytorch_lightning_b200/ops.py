@@ -99,6 +99,31 @@ def ffn(y_in, w1, b1, w2, b2, x, *, alpha, ln=None, hidden_ws=None, engine=N.ENG
                             engine, _stream(x)))
 
 
+def conv_module(y_in, w1, b1, dw_w, dw_b, w2, b2, x, B, T, *, row_valid=None, ln=None, glu_ws=None, dw_ws=None,
+                engine=N.ENGINE_AUTO):
+    """x += rowmask(w2 silu(dw(glu(w1 y_in + b1))) + b2) (+ fused LayerNorm, ln = dict(y,g1,b1) or None) with folded
+    BatchNorm; see cfm_conv_module in include/cfm_b200.h."""
+    _req(y_in, "conv_module.y_in")
+    _req(w1, "conv_module.w1", y_in.dtype)
+    _req(w2, "conv_module.w2", y_in.dtype)
+    _req(dw_w, "conv_module.dw_w", torch.float32)
+    _req(dw_b, "conv_module.dw_b", torch.float32)
+    _req(x, "conv_module.x", torch.float32)
+    n, d = y_in.shape
+    k = dw_w.shape[0]
+    if n != B * T or x.shape != (n, d) or w1.shape != (2 * d, d) or w2.shape != (d, d) or dw_w.shape != (k, d):
+        raise RuntimeError("conv_module: shape mismatch")
+    ln = ln or {}
+    yo = ln.get("y")
+    if yo is not None:
+        _req(yo, "conv_module.y", y_in.dtype)
+    ensure_init(x)
+    N.check(N.lib().cfm_conv_module(y_in.data_ptr(), w1.data_ptr(), b1.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(),
+                                    w2.data_ptr(), b2.data_ptr(), x.data_ptr(), B, T, d, k, _DT[y_in.dtype],
+                                    _ptr(row_valid), _ptr(ln.get("g1")), _ptr(ln.get("b1")), _ptr(yo), 1e-5,
+                                    _ptr(glu_ws), _ptr(dw_ws), engine, _stream(x)))
+
+
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
     """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
     mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""

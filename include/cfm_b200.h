@@ -150,6 +150,23 @@ int cfm_dwconv(const void* x, const float* w, const float* bias, void* y,
                int B, int T, int d, int k, int dtype, int apply_silu, void* stream);
 
 /*
+ * Whole convolution module (inference: BatchNorm running statistics folded) on the residual stream, in place
+ * (convolution.py:34-49 + encoder_layer.py:64-67):
+ *   X += rowmask( W2 silu( dw( glu( W1 y + b1 ) ) ) + b2 ),  then, if g1 != NULL, Y = LN(X; g1, be1)
+ * y: (B*T,d) act dtype, already zero on padded rows; W1: (2d,d) [value rows; gate rows], W2: (d,d) act dtype;
+ * b1 (2d), b2 (d) fp32; dw_w (k,d) / dw_b (d): folded depthwise taps as in cfm_dwconv; X: (B*T,d) fp32;
+ * row_valid (B*T) or NULL; Y (B*T,d) act dtype, must NOT alias y (tiles re-read a halo of neighbouring rows of y).
+ * On the tcgen05 engine (bf16, d == 256, k == 15, T >= 15) this is ONE kernel: the GLU output and the depthwise
+ * output live in shared memory only.  Otherwise the library runs cfm_gemm (GLU) + cfm_dwconv + cfm_gemm / cfm_gemm_ln
+ * through glu_ws / dw_ws, two caller-provided (B*T,d) act-dtype scratch buffers (may be NULL only if the fused path
+ * applies).
+ */
+int cfm_conv_module(const void* y, const void* W1, const float* b1, const float* dw_w, const float* dw_b,
+                    const void* W2, const float* b2, float* X, int B, int T, int d, int k, int dtype,
+                    const uint8_t* row_valid, const float* g1, const float* be1, void* Y, float eps,
+                    void* glu_ws, void* dw_ws, int engine, void* stream);
+
+/*
  * BatchNorm1d training-mode pieces (convolution.py:44): statistics over all B*T rows, unmasked.
  *   cfm_bn_stats : sum[c] = sum_r x[r,c], sumsq[c] = sum_r (x[r,c])^2   (x fp32 (rows,d); outputs must be zeroed)
  *   cfm_bn_apply_silu : y = silu((x-mean)*rstd*gamma+beta) in act dtype

@@ -350,6 +350,48 @@ def test_ffn_fused_tcgen05(M, F, mode):
         assert rel_err(x, x_ref) < 2e-3 and rel_err(yio.float(), y_ref) < 8e-3
 
 
+@pytest.mark.parametrize("B,T", [(1, 64), (1, 114), (2, 115), (3, 57), (5, 15), (64, 248), (7, 333), (1, 1000)])
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_conv_module_fused_tcgen05(B, T, with_ln):
+    """Whole convolution module (+ LayerNorm) in one kernel vs fp32 torch on the same bf16 operands (intermediates
+    rounded to bf16 as on chip), and vs the unfused three-kernel chain of the library."""
+    dt, d, k = torch.bfloat16, 256, 15
+    M = B * T
+    Fn = torch.nn.functional
+    rv = (torch.arange(M, device=DEV) % 7 != 3).to(torch.uint8)
+    if B > 1:
+        rv.view(B, T)[1, T // 2:] = 0                                    # a padded tail
+    yin = rnd(M, d, dtype=dt) * rv[:, None].to(dt)
+    w1 = rnd(2 * d, d, dtype=dt, scale=1 / 16, seed=1)
+    b1 = rnd(2 * d, seed=2) * 0.5
+    dw = rnd(d, 1, k, scale=0.3, seed=3)
+    db = rnd(d, seed=4) * 0.5
+    w2 = rnd(d, d, dtype=dt, scale=1 / 16, seed=5)
+    b2 = rnd(d, seed=6) * 0.5
+    g1, be1 = rnd(d, seed=7) * 0.1 + 1, rnd(d, seed=8) * 0.1
+    x0 = rnd(M, d, seed=9, scale=2.0)
+    u = yin.float() @ w1.float().t() + b1
+    g = (u[:, :d] * torch.sigmoid(u[:, d:])).to(dt).float()
+    c = Fn.conv1d(g.view(B, T, d).transpose(1, 2), dw, db, padding=(k - 1) // 2, groups=d).transpose(1, 2)
+    c = Fn.silu(c).reshape(M, d).to(dt).float()
+    x_ref = x0 + (c @ w2.float().t() + b2) * rv[:, None]
+    y_ref = Fn.layer_norm(x_ref, (d,), g1, be1, 1e-5)
+    dw_t = dw[:, 0].t().contiguous()
+    res = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_SIMT):
+        x = x0.clone()
+        y = torch.full((M, d), float("nan"), dtype=dt, device=DEV)
+        ln = {"y": y, "g1": g1, "b1": be1} if with_ln else None
+        gws, cws = torch.empty(M, d, dtype=dt, device=DEV), torch.empty(M, d, dtype=dt, device=DEV)
+        ops.conv_module(yin, w1, b1, dw_t, db, w2, b2, x, B, T, row_valid=rv, ln=ln, glu_ws=gws, dw_ws=cws, engine=eng)
+        assert torch.isfinite(x).all()
+        assert rel_err(x, x_ref) < 3e-3, (eng, rel_err(x, x_ref))
+        if with_ln:
+            assert rel_err(y.float(), y_ref) < 8e-3, (eng, rel_err(y.float(), y_ref))
+        res[eng] = x
+    assert rel_err(res[N.ENGINE_TC], res[N.ENGINE_SIMT]) < 3e-3
+
+
 @pytest.mark.parametrize("B,Tin,C", [(2, 200, 256), (64, 998, 256), (3, 131, 512), (1, 67, 256)])
 def test_native_subsampling_frontend(B, Tin, C):
     """conv1 (CUDA cores) + conv2 (tcgen05 implicit GEMM with TMA-gathered taps) vs torch conv2d on the same weights."""
