@@ -3,8 +3,11 @@
 //   ln_mode 0:  X = v
 //   ln_mode 1:  X = v,          y = ymask(LN(v; g1,b1))    (encoder_layer.py:59,63,67)
 //   ln_mode 2:  X = LN(v;g1,b1), y = ymask(LN(X; g2,b2))   (encoder_layer.py:70 chained with :56 of the next layer)
-// 128 threads, thread = output row: tcgen05.ld 32x32b gives each thread 32 consecutive fp32 columns of ITS row, so
-// LayerNorm statistics need no cross-thread reduction.  The fp32 residual arrives through TMA loads into a ring of
+// Thread = output row: tcgen05.ld 32x32b gives each thread 32 consecutive fp32 columns of ITS row, so LayerNorm
+// statistics need no shuffle reduction.  NG = 1: one warpgroup (128 threads) walks all BN columns.  NG = 2: two
+// warpgroups split the columns of every row in halves (a single warp per scheduler cannot hide the tcgen05.ld /
+// shared-memory latencies of this epilogue, two can) and exchange their partial row sums through shared memory; each
+// group owns a staging ring of R tiles, an elected thread and R mbarriers.  The fp32 residual arrives through TMA loads into a ring of
 // 128-byte-swizzled [128 x 128 B] staging tiles, X and y leave through TMA stores from the same ring, and between
 // the passes the pre-norm row is parked in the tile's own TMEM accumulator columns (tcgen05.st).
 #pragma once
@@ -28,10 +31,10 @@ struct ResidParams {
 };
 
 // sparam layout: [0,BN) bias  [BN,2BN) g1  [2BN,3BN) b1  [3BN,4BN) g2  [4BN,5BN) b2
-template <int BN>
+template <int BN, int NTHREADS = 128>
 __device__ __forceinline__ void resid_stage_params(float* sparam, int et, const float* bias, int n0, int ln_mode,
                                                    const float* g1, const float* b1, const float* g2, const float* b2) {
-  for (int i = et; i < BN; i += 128) {
+  for (int i = et; i < BN; i += NTHREADS) {
     sparam[i] = bias ? bias[n0 + i] : 0.f;
     if (ln_mode >= 1) { sparam[BN + i] = g1[i]; sparam[2 * BN + i] = b1[i]; }
     if (ln_mode == 2) { sparam[3 * BN + i] = g2[i]; sparam[4 * BN + i] = b2[i]; }
@@ -40,12 +43,15 @@ __device__ __forceinline__ void resid_stage_params(float* sparam, int et, const 
 
 // issue the TMA loads of the first min(R, BN/32) residual chunks (elected thread only).  ROWS = rows of the TMA box
 // (128 for GEMM tiles; the fused conv module stores only its 128-(k-1) interior rows).
-template <int BN, int R, int ROWS = 128>
-__device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar, const CUtensorMap* tmR, int n0, int m0) {
+// (ring, res_bar: the calling group's own; grp selects the group's column half when NG = 2)
+template <int BN, int R, int ROWS = 128, int NG = 1>
+__device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar, const CUtensorMap* tmR, int n0, int m0,
+                                               int grp = 0) {
+  constexpr int NCHG = BN / 32 / NG;
 #pragma unroll
-  for (int c = 0; c < (BN / 32 < R ? BN / 32 : R); ++c) {
+  for (int c = 0; c < (NCHG < R ? NCHG : R); ++c) {
     mbar_expect_tx(res_bar + c, ROWS * 128);
-    tma_load_2d(ring + c * kBufBytes, tmR, res_bar + c, n0 + c * 32, m0);
+    tma_load_2d(ring + c * kBufBytes, tmR, res_bar + c, n0 + (grp * NCHG + c) * 32, m0);
   }
 }
 
@@ -53,18 +59,22 @@ __device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar,
 // resid_stage_params + resid_prefetch done.  `taddr` = TMEM address of this thread's row, column 0 of the accumulator.
 // `bar_id` names a 128-thread barrier private to the calling warpgroup.  On return every TMEM access of the thread
 // has completed and all TMA stores have finished READING the ring (it may be overwritten).
-template <int BN, int R, int ROWS = 128>
+// NG = 2: `grp` = 0/1, `xbar` names a 256-thread barrier shared by both groups, `xch` = 512 float2 of shared memory;
+// sparam must have been staged by the time every thread passes the first barrier (256-thread barrier here).
+template <int BN, int R, int ROWS = 128, int NG = 1>
 __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0, int n0, bool elected, int bar_id,
                                                   uint8_t* ring, uint64_t* res_bar, uint32_t& ring_phase,
                                                   const float* sparam, const CUtensorMap* tmX, const CUtensorMap* tmR,
-                                                  const CUtensorMap* tmY, const ResidParams& p) {
-  constexpr int NCH = BN / 32;                   // 32-column fp32 chunks per row
+                                                  const CUtensorMap* tmY, const ResidParams& p, int grp = 0, int xbar = 0,
+                                                  float2* xch = nullptr) {
+  constexpr int NCH = BN / 32 / NG;              // 32-column fp32 chunks per row handled by this group
+  const int ch0 = grp * NCH;                     // first chunk of this group
   const int ln = p.ln_mode;
   const int row = m0 + r;
   const bool row_ok = row < p.M;
   const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
   const float a = valid ? p.alpha : 0.f;
-  named_bar_sync(bar_id, 128);                   // sparam visible
+  if (NG == 1) named_bar_sync(bar_id, 128); else named_bar_sync(xbar, 128 * NG);   // sparam visible
   float s1 = 0.f, s2 = 0.f;
   // ---- pass 1: v = R + alpha*(acc + bias)
 #pragma unroll 1
@@ -74,9 +84,9 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
     ring_phase ^= (1u << b);
     uint32_t v[32];
-    tmem_ld32(taddr + c * 32, v);
+    tmem_ld32(taddr + (ch0 + c) * 32, v);
     tmem_ld_wait();
-    const float* bs = sparam + c * 32;
+    const float* bs = sparam + (ch0 + c) * 32;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
@@ -91,28 +101,34 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
       v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
       if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
     }
-    if (ln != 0) tmem_st32(taddr + c * 32, v);   // park the pre-norm row in our accumulator columns
+    if (ln != 0) tmem_st32(taddr + (ch0 + c) * 32, v);   // park the pre-norm row in our accumulator columns
     fence_proxy_async_smem();
     named_bar_sync(bar_id, 128);
     if (elected) {
       if (ln != 2) {
-        tma_store_2d(tmX, buf, n0 + c * 32, m0);
+        tma_store_2d(tmX, buf, n0 + (ch0 + c) * 32, m0);
         bulk_commit();
         // refill the PREVIOUS chunk's buffer once its store has finished reading it
         if (c >= 1 && c - 1 + R < NCH) {
           bulk_wait_read<1>();
           const int pb = (c - 1) % R;
           mbar_expect_tx(res_bar + pb, ROWS * 128);
-          tma_load_2d(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (c - 1 + R) * 32, m0);
+          tma_load_2d(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (ch0 + c - 1 + R) * 32, m0);
         }
       } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
         mbar_expect_tx(res_bar + b, ROWS * 128);
-        tma_load_2d(buf, tmR, res_bar + b, n0 + (c + R) * 32, m0);
+        tma_load_2d(buf, tmR, res_bar + b, n0 + (ch0 + c + R) * 32, m0);
       }
     }
   }
   if (ln != 0) {
     tmem_st_wait();
+    if (NG == 2) {                               // row sums of the other half of the columns
+      xch[grp * 128 + r] = make_float2(s1, s2);
+      named_bar_sync(xbar, 256);
+      const float2 o = xch[(grp ^ 1) * 128 + r];
+      s1 += o.x; s2 += o.y;
+    }
     const float inv_n = 1.0f / BN;
     float mean = s1 * inv_n;
     float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
@@ -127,10 +143,10 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
         uint8_t* buf = ring + (nbuf % R) * kBufBytes;
         if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
         uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
+        tmem_ld32(taddr + (ch0 + c) * 32, v);
         tmem_ld_wait();
-        const float* g = sparam + BN + c * 32;
-        const float* be = sparam + 2 * BN + c * 32;
+        const float* g = sparam + BN + (ch0 + c) * 32;
+        const float* be = sparam + 2 * BN + (ch0 + c) * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 x;
@@ -144,12 +160,18 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
           v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
           *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
         }
-        tmem_st32(taddr + c * 32, v);
+        tmem_st32(taddr + (ch0 + c) * 32, v);
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (elected) { tma_store_2d(tmX, buf, n0 + c * 32, m0); bulk_commit(); }
+        if (elected) { tma_store_2d(tmX, buf, n0 + (ch0 + c) * 32, m0); bulk_commit(); }
       }
       tmem_st_wait();
+      if (NG == 2) {
+        xch[256 + grp * 128 + r] = make_float2(s1, s2);
+        named_bar_sync(xbar, 256);
+        const float2 o = xch[256 + (grp ^ 1) * 128 + r];
+        s1 += o.x; s2 += o.y;
+      }
       mean = s1 * inv_n;
       rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
     }
@@ -158,7 +180,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
     const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
 #pragma unroll 1
-    for (int sub = 0; sub < BN / 64; ++sub, ++nbuf) {
+    for (int sub = grp * (BN / 64 / NG); sub < (grp + 1) * (BN / 64 / NG); ++sub, ++nbuf) {
       uint8_t* buf = ring + (nbuf % R) * kBufBytes;
       if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
       uint32_t v[64];

@@ -101,9 +101,40 @@ def ffn_bench(M=15872, d=256, F=2048):
             print(f"ffn {name:10s} {mode:6s} M={M} F={F}: {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)")
 
 
+def conv_bench(B=64, T=248, d=256, k=15):
+    dev = "cuda"
+    M = B * T
+    y = torch.randn(M, d, device=dev).bfloat16(); y2 = torch.empty_like(y)
+    w1 = (torch.randn(2 * d, d, device=dev) / 16).bfloat16(); b1 = torch.randn(2 * d, device=dev)
+    w2 = (torch.randn(d, d, device=dev) / 16).bfloat16(); b2 = torch.randn(d, device=dev)
+    dw = torch.randn(k, d, device=dev) * 0.3; db = torch.randn(d, device=dev)
+    g = torch.ones(d, device=dev); b = torch.zeros(d, device=dev)
+    x = torch.randn(M, d, device=dev)
+    rv = torch.ones(M, dtype=torch.uint8, device=dev)
+    gws, cws = torch.empty_like(y), torch.empty_like(y)
+    fl = 2.0 * M * d * d * 3
+    for name, eng in (("fused", N.ENGINE_TC), ("3 kernels", N.ENGINE_SIMT + 99)):
+        for mode, ln in (("no LN", None), ("LN", {"y": y2, "g1": g, "b1": b})):
+            if eng == N.ENGINE_TC:
+                fn = lambda: ops.conv_module(y, w1, b1, dw, db, w2, b2, x, B, T, row_valid=rv, ln=ln, engine=N.ENGINE_TC)
+            else:
+                def fn():
+                    ops.gemm(y, w1, b1, gws, N.EPI_BIAS_GLU)
+                    ops.dwconv(gws.view(B, T, d), dw, db, cws.view(B, T, d))
+                    if ln is None:
+                        ops.gemm(cws, w2, b2, x, N.EPI_RESIDUAL, residual=x, alpha=1.0, row_valid=rv)
+                    else:
+                        ops.gemm_ln(cws, w2, b2, x, y2, alpha=1.0, g1=g, b1=b, row_valid=rv)
+            t = timeit(fn)
+            print(f"conv module {name:10s} {mode:6s} B={B} T={T}: {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         small_kernels()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":
+        conv_bench()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ffn":
         ffn_bench()
