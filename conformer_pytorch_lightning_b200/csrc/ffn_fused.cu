@@ -89,9 +89,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* h_full = s_empty + 2;             // [2]  H[b] written by the 256 epilogue threads
   uint64_t* h_empty = h_full + 2;             // [2]  G2 finished reading H[b] (MMA commit)
   uint64_t* y_full = h_empty + 2;             // [1]  all MMAs of the tile complete
-  uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (128 arrivals)
-  uint64_t* res_bar = tile_done + 1;          // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
+  uint64_t* res_bar = tile_done + 1;          // [2 groups][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
@@ -114,8 +114,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       mbar_init(h_full + s, 256); mbar_init(h_empty + s, 1);
     }
     mbar_init(y_full, 1);
-    mbar_init(tile_done, 128);
-    for (int s = 0; s < 4; ++s) mbar_init(res_bar + s, 1);
+    mbar_init(tile_done, 256);
+    for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -275,7 +275,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     int it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
-      if (it > 0 && grp == 1) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
       // ---- SiLU stage: S[b] -> H[b]
       for (int c = 0; c < NC; ++c) {
         const int b = c & 1;
@@ -317,18 +316,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         mbar_arrive(h_full + b);
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + c] = clock64();
       }
-      // ---- final epilogue on Y (warpgroup 0)
-      if (grp == 0) {
-        mbar_wait(y_full, it & 1);
-        tc_fence_after();
-        // every MMA of the tile has retired: the input tile (-> parameters) and H buffers (-> staging ring) are dead
-        resid_stage_params<D>(sparam, et, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
-        if (elected) resid_prefetch<D, 4>(sH, res_bar, &tmR, 0, m0);
-        ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
-        resid_ln_epilogue<D, 4>(tmem_y + lane_base, r, m0, 0, elected, bar_id, sH, res_bar, ring_phase, sparam, &tmX,
-                                &tmR, &tmY, rp);
-        mbar_arrive(tile_done);
-      }
+      // ---- final epilogue on Y: each warpgroup takes 128 of the 256 columns
+      mbar_wait(y_full, it & 1);
+      tc_fence_after();
+      // every MMA of the tile has retired: the input tile (-> parameters, group 1's staging ring) and the H buffers
+      // (-> group 0's ring) are dead
+      resid_stage_params<D, 256>(sparam, threadIdx.x - 128, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
+      uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
+      if (elected) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+      ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
+      resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase, sparam,
+                                      &tmX, &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sA + 8192));
+      mbar_arrive(tile_done);
+      if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
     }
     if (elected) bulk_wait_all<0>();
   }

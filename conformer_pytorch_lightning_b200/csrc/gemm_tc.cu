@@ -7,7 +7,7 @@
 //   warp 1 (1 thread)  MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two TMEM
 //                      accumulator buffers; tcgen05.commit releases the smem slot / publishes the tile
 //   warp 2             TMEM allocator (2 x BN fp32 columns)
-//   warps 4-7          epilogue, thread = output row (tcgen05.ld 32x32b).  All global traffic of the epilogue is
+//   warps 4-11         epilogue, thread = output row x column half (tcgen05.ld 32x32b).  All global traffic of the epilogue is
 //                      bulk-asynchronous: results are written into 128-byte-swizzled staging tiles in shared
 //                      memory and leave through TMA stores; the fp32 residual tile arrives through TMA loads that
 //                      are prefetched while the main loop is still running.
@@ -81,12 +81,12 @@ template <int BN, bool RESID> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // epilogue warps: the residual/LN epilogue keeps one thread per row (row statistics stay thread-local); the
-  // activation epilogues are MUFU/latency bound, so two warpgroups split the tile's columns (2 warps / SMSP)
-  static constexpr int kEpiThreads = RESID ? 128 : 256;
+  // epilogue warps: every epilogue is latency bound with one warp per scheduler, so two warpgroups split the tile's
+  // columns (2 warps / SMSP); the residual/LN epilogue exchanges its partial row sums through shared memory
+  static constexpr int kEpiThreads = 256;
   static constexpr int kThreads = 128 + kEpiThreads;
-  static constexpr int kBufs = 4;                                  // staging ring (2 per warpgroup for F1)
-  static constexpr int kParamFloats = RESID ? 5 * BN : BN;         // bias (+ LN gammas/betas)
+  static constexpr int kBufs = 4;                                  // staging ring (2 per warpgroup)
+  static constexpr int kParamFloats = RESID ? 5 * BN + 1024 : BN;  // bias (+ LN gammas/betas + row-sum exchange)
   static constexpr int kFixed = kBufs * kBufBytes + kParamFloats * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
   static constexpr int kStages = (kMaxSmem - kFixed) / kStageBytes > 6 ? 6 : (kMaxSmem - kFixed) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
@@ -211,10 +211,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (thread = output row; F1: two warpgroups split the columns) ==============
+    // ===================== epilogue (thread = output row; two warpgroups split the columns) ==============
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;                      // row inside the tile
-    const int grp = (warp - 4) >> 2;                  // epilogue warpgroup (always 0 for the residual epilogue)
+    const int grp = (warp - 4) >> 2;                  // epilogue warpgroup
     const int et = threadIdx.x - 128 - grp * 128;     // 0..127 inside the warpgroup
     const bool elected = (et == 0);
     const int bar_id = 1 + grp;
@@ -225,14 +225,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * OUT_BN;
-      const int row = m0 + r;
-      const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + lane_base + acc * BN;
 
       // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync); each warpgroup
       //      stages (and later reads) only the columns it owns
       if constexpr (RESID) {
-        resid_stage_params<BN>(sparam, et, p.bias, n0, p.ln_mode, p.g1, p.b1, p.g2, p.b2);
+        resid_stage_params<BN, 256>(sparam, threadIdx.x - 128, p.bias, n0, p.ln_mode, p.g1, p.b1, p.g2, p.b2);
       } else {
         constexpr int GCOLS = OUT_BN / 2;
         for (int ii = et; ii < GCOLS; ii += 128) {
@@ -292,12 +290,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive(tempty_bar + acc);
       } else {
         // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
-        if (elected) resid_prefetch<BN, C::kBufs>(ring, res_bar, &tmR, n0, m0);   // lands during the main loop
+        constexpr int RG = C::kBufs / 2;                  // staging tiles per warpgroup
+        uint8_t* gring = ring + grp * RG * kBufBytes;
+        if (elected) resid_prefetch<BN, RG, 128, 2>(gring, res_bar + grp * RG, &tmR, n0, m0, grp);   // lands during the main loop
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
         ResidParams rp{p.row_valid, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
-        resid_ln_epilogue<BN, C::kBufs>(taddr, r, m0, n0, elected, bar_id, ring, res_bar, ring_phase, sparam, &tmC, &tmR,
-                                        &tmY, rp);
+        resid_ln_epilogue<BN, RG, 128, 2>(taddr, r, m0, n0, elected, bar_id, gring, res_bar + grp * RG, ring_phase, sparam, &tmC,
+                                          &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sparam + 5 * BN));
         mbar_arrive(tempty_bar + acc);
       }
     }

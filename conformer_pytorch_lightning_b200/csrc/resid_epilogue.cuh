@@ -209,9 +209,10 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     }
   }
   tc_fence_before();
-  // the staging ring must be drained before anything overwrites it (next tile's residual prefetch)
+  // the staging ring must be drained before anything overwrites it (next tile's residual prefetch); with two groups
+  // nobody may restage sparam / xch for the next tile while the other group still reads them
   if (elected) bulk_wait_read<0>();
-  named_bar_sync(bar_id, 128);
+  if (NG == 1) named_bar_sync(bar_id, 128); else named_bar_sync(xbar, 128 * NG);
 }
 
 }  // namespace tc
