@@ -275,10 +275,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     int it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
-      // ---- SiLU stage: S[b] -> H[b]
+      // ---- SiLU stage: S[b] -> H[b].  The b1 slice of chunk c+1 is fetched into a register while chunk c is being
+      //      processed, so its L2 latency never sits between two chunks.
+      float b1_next = (et < 64) ? __ldg(p.b1 + grp * 64 + et) : 0.f;
       for (int c = 0; c < NC; ++c) {
         const int b = c & 1;
-        if (et < 64) sb1[b * HC + grp * 64 + et] = p.b1[c * HC + grp * 64 + et];
+        if (et < 64) {
+          sb1[b * HC + grp * 64 + et] = b1_next;
+          if (c + 1 < NC) b1_next = __ldg(p.b1 + (c + 1) * HC + grp * 64 + et);
+        }
         named_bar_sync(bar_id, 128);
         uint32_t& n_sf = b ? n_sf1 : n_sf0;
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[2 * 64 + c] = clock64();
