@@ -8,9 +8,10 @@ from .convolution import ConvolutionModule, ConvolutionSubSampling
 from .encoder import ConformerEncoder
 from .encoder_layer import ConformerEncoderLayer
 from .feedforward import PositionwiseFeedForwardModule
+from .pipeline import EncoderPipeline
 from .utils import make_attn_mask, make_pad_mask, subsequent_chunk_mask
 
 __all__ = ["ConformerEncoder", "ConformerEncoderLayer", "RelativeMultiHeadSelfAttentionModule",
            "MultiHeadSelfAttentionModule", "RelativePositionalEncoding", "PositionalEncoding", "ConvolutionModule",
            "ConvolutionSubSampling", "PositionwiseFeedForwardModule", "make_pad_mask", "make_attn_mask",
-           "subsequent_chunk_mask"]
+           "subsequent_chunk_mask", "EncoderPipeline"]

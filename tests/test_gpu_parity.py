@@ -206,3 +206,31 @@ def test_cuda_graph_replay_equals_eager(dtype):
         a, _ = enc(feats, lens, **fw)
         b, _ = eager(feats, lens, **fw)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_encoder_pipeline_matches_forward(depth):
+    """EncoderPipeline overlaps the copies of neighbouring batches with compute; every batch must come back exactly as
+    a plain forward call returns it, in order, also when host output buffers are recycled."""
+    from conformer_pytorch_lightning_b200 import EncoderPipeline
+    g = load_golden("m3_static16")
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=torch.bfloat16)
+    feats, lens = torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"])
+    batches = [((feats * (1.0 + 0.1 * i)).pin_memory(), lens) for i in range(7)]
+    want = []
+    with torch.no_grad():
+        for f, l in batches:
+            o, m = enc(f.cuda(), l.cuda(), **g["fw"])
+            want.append((o.cpu(), m.cpu()))
+    pipe = EncoderPipeline(enc, depth=depth)
+    got = pipe.run(batches, **g["fw"])
+    assert len(got) == len(want)
+    for (o, m), (wo, wm) in zip(got, want):
+        assert o.is_pinned() and torch.equal(o, wo) and torch.equal(m.cpu(), wm)
+    bufs = [torch.empty_like(want[0][0]).pin_memory() for _ in range(depth)]
+    n = 0
+    for (o, m), (wo, wm) in zip(pipe.stream(batches, bufs, **g["fw"]), want):
+        assert torch.equal(o, wo), n                  # checked before the buffer is recycled
+        n += 1
+    assert n == len(want)
+    assert max_rel(want[0][0].numpy(), g["out"]) < BF16_TOL
