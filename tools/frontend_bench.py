@@ -20,3 +20,15 @@ w3 = (torch.randn(C, F2 * C, device="cuda") / 70).bfloat16(); b3 = torch.randn(C
 out = torch.zeros(B * T2, C, device="cuda")
 t = timeit(lambda: ops.gemm(act, w3, b3, out, N.EPI_RESIDUAL, residual=out, alpha=1.0), iters=5, per_graph=4)
 print(f"linear K=4864: {t:8.1f} us ({2.0 * B * T2 * C * F2 * C / t / 1e6:6.1f} TF/s)")
+# per-kernel device times (CUPTI)
+from torch.profiler import profile, ProfilerActivity
+for _ in range(2):
+    ops.subsample_conv(x, w1, b1, w2, b2, ws, act)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(5):
+        ops.subsample_conv(x, w1, b1, w2, b2, ws, act)
+    torch.cuda.synchronize()
+for e in prof.key_averages():
+    if e.device_time_total > 0:
+        print(f"{e.key[:70]:70s} {e.device_time_total / max(e.count, 1):9.1f} us x{e.count}")
