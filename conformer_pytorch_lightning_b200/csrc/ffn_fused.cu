@@ -32,7 +32,15 @@ constexpr int kPiece = 32768;   // one weight piece = one ring slot = 512 tensor
 constexpr int NST = 3;          // weight ring depth
 constexpr int kABytes = BM * D * 2;            // 64 KB
 constexpr int kHBytes = BM * HC * 2;           // 32 KB per H buffer
-constexpr int kThreads = 384;
+#ifndef CFM_FFN_SILU_GROUPS
+#define CFM_FFN_SILU_GROUPS 2
+#endif
+constexpr int kSiluGroups = CFM_FFN_SILU_GROUPS;   // SiLU-stage warpgroups (2 or 4)
+constexpr int kSiluCols = HC / kSiluGroups;        // hidden columns per warpgroup and chunk: half of them in each 64-column
+constexpr int kHalfCols = kSiluCols / 2;           // half (= k atom of G2) of the chunk
+static_assert(kSiluGroups == 2 || kSiluGroups == 4, "SiLU stage: 2 or 4 warpgroups");
+constexpr int kSiluThreads = 128 * kSiluGroups;
+constexpr int kThreads = 128 + kSiluThreads;
 constexpr int kParamFloats = 2 * HC;           // double-buffered b1 chunk (the residual-epilogue parameters alias the
                                                // input tile, which is dead by the time they are needed)
 constexpr int kSmemBytes = kABytes + 2 * kHBytes + NST * kPiece + kParamFloats * 4 + 512;
@@ -85,9 +93,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* w_empty = w_full + NST;           // [NST]
   uint64_t* a_full = w_empty + NST;           // [1]
   uint64_t* s_full = a_full + 1;              // [2]  S[b] accumulator complete (MMA commit)
-  uint64_t* s_empty = s_full + 2;             // [2]  S[b] drained by the 256 epilogue threads
-  uint64_t* h_full = s_empty + 2;             // [2]  H[b] written by the 256 epilogue threads
-  uint64_t* h_empty = h_full + 2;             // [2]  G2 finished reading H[b] (MMA commit)
+  uint64_t* s_empty = s_full + 2;             // [2]  S[b] drained by the SiLU threads
+  uint64_t* h_full = s_empty + 2;             // [2][2]  64-column half of H[b] written by the SiLU threads
+  uint64_t* h_empty = h_full + 4;             // [2]  G2 finished reading H[b] (MMA commit)
   uint64_t* y_full = h_empty + 2;             // [1]  all MMAs of the tile complete
   uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
   uint64_t* res_bar = tile_done + 1;          // [2 groups][4]
@@ -110,8 +118,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
     mbar_init(a_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(s_full + s, 1); mbar_init(s_empty + s, 256);
-      mbar_init(h_full + s, 256); mbar_init(h_empty + s, 1);
+      mbar_init(s_full + s, 1); mbar_init(s_empty + s, kSiluThreads);
+      mbar_init(h_full + 2 * s, kSiluThreads); mbar_init(h_full + 2 * s + 1, kSiluThreads); mbar_init(h_empty + s, 1);
     }
     mbar_init(y_full, 1);
     mbar_init(tile_done, 256);
@@ -193,12 +201,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
       // probe used while issuing the last piece of a job: is the barrier of the following job complete?
       auto probe_g1 = [&](int c) { const int b = c & 1; return mbar_test(s_empty + b, ((b ? n_se1 : n_se0) & 1) ^ 1); };
-      auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + b, (b ? n_hf1 : n_hf0) & 1); };
+      auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + 2 * b, (b ? n_hf1 : n_hf0) & 1); };
 
       auto do_g1 = [&](int c, int next_kind, int next_c) {     // next_kind: 1 = G1, 2 = G2, 0 = none
         const int b = c & 1;
         uint32_t& n_se = b ? n_se1 : n_se0;
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + c] = clock64();
         if (!job_ready) mbar_wait(s_empty + b, (n_se & 1) ^ 1);     // SiLU stage drained S[b] (two chunks ago)
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + c] = clock64();
         ++n_se;
         tc_fence_after();
 #pragma unroll
@@ -227,11 +237,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       auto do_g2 = [&](int c, int next_kind, int next_c, bool last) {
         const int b = c & 1;
         uint32_t& n_hf = b ? n_hf1 : n_hf0;
-        if (!job_ready) mbar_wait(h_full + b, n_hf & 1);             // H[b] written (and fenced) by the SiLU stage
-        ++n_hf;
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[6 * 64 + c] = clock64();
+        if (!job_ready) mbar_wait(h_full + 2 * b, n_hf & 1);         // first half of H[b] written (and fenced)
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[7 * 64 + c] = clock64();
         tc_fence_after();
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {                             // pc = 64-wide k atom of the hidden chunk
+          if (pc == 1) {                                             // second half: lands while the first atom's MMAs run
+            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[8 * 64 + c] = clock64();
+            mbar_wait(h_full + 2 * b + 1, n_hf & 1);
+            if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[9 * 64 + c] = clock64();
+          }
           if (!have) mbar_wait(w_full + stage, phase);
           tc_fence_after();
           next_slot_probe();
@@ -250,6 +266,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           __syncwarp();
           advance();
         }
+        ++n_hf;
       };
       job_ready = false;
       do_g1(0, 1, 1);
@@ -277,12 +294,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       const int m0 = t * BM;
       // ---- SiLU stage: S[b] -> H[b].  The b1 slice of chunk c+1 is fetched into a register while chunk c is being
       //      processed, so its L2 latency never sits between two chunks.
-      float b1_next = (et < 64) ? __ldg(p.b1 + grp * 64 + et) : 0.f;
+      if (it > 0 && grp >= 2) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
+      // et < kSiluCols: the hidden columns this warpgroup reads (kHalfCols of each 64-column half)
+      const int bcol = (et / kHalfCols) * 64 + grp * kHalfCols + (et % kHalfCols);
+      float b1_next = (et < kSiluCols) ? __ldg(p.b1 + bcol) : 0.f;
       for (int c = 0; c < NC; ++c) {
         const int b = c & 1;
-        if (et < 64) {
-          sb1[b * HC + grp * 64 + et] = b1_next;
-          if (c + 1 < NC) b1_next = __ldg(p.b1 + (c + 1) * HC + grp * 64 + et);
+        if (et < kSiluCols) {
+          sb1[b * HC + bcol] = b1_next;
+          if (c + 1 < NC) b1_next = __ldg(p.b1 + (c + 1) * HC + bcol);
         }
         named_bar_sync(bar_id, 128);
         uint32_t& n_sf = b ? n_sf1 : n_sf0;
@@ -291,49 +311,55 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         ++n_sf;
         tc_fence_after();
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[3 * 64 + c] = clock64();
-        uint32_t v[64];
-        {
-          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-          tmem_ld32(tmem_base + lane_base + b * HC + grp * 64, v0);
-          tmem_ld32(tmem_base + lane_base + b * HC + grp * 64 + 32, v1);
-        }
+        // two 64-column halves (= the two k atoms of G2): this warpgroup takes kHalfCols columns of each, so that the
+        // first atom of H[b] is complete after half of the chunk's MUFU work and G2 can start on it
+        uint32_t v0[kHalfCols], v1[kHalfCols];
+        tmem_ld(tmem_base + lane_base + b * HC + grp * kHalfCols, v0);
+        tmem_ld(tmem_base + lane_base + b * HC + 64 + grp * kHalfCols, v1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty + b);                         // S[b] may be overwritten by G1(c+2)
-        const float* bs = sb1 + b * HC + grp * 64;
-        uint4 pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[8 * j + e]) + bs[8 * j + e]);
-          pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        }
         uint32_t& n_he = b ? n_he1 : n_he0;
-        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[5 * 64 + c] = clock64();
-        mbar_wait(h_empty + b, (n_he & 1) ^ 1);           // G2(c-2) finished reading H[b]
-        ++n_he;
-        uint8_t* hb = sH + b * kHBytes + grp * kAtom;     // this warpgroup's 64 hidden columns = one swizzle atom
 #pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, j)) = pk[j];
-        fence_proxy_async_smem();
-        mbar_arrive(h_full + b);
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t (&v)[kHalfCols] = half ? v1 : v0;
+          const float* bs = sb1 + b * HC + half * 64 + grp * kHalfCols;
+          uint4 pk[kHalfCols / 8];
+#pragma unroll
+          for (int j = 0; j < kHalfCols / 8; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[8 * j + e]) + bs[8 * j + e]);
+            pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+          if (half == 0) {
+            if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[5 * 64 + c] = clock64();
+            mbar_wait(h_empty + b, (n_he & 1) ^ 1);         // G2(c-2) finished reading H[b]
+            ++n_he;
+          }
+          uint8_t* hb = sH + b * kHBytes + half * kAtom;    // this group's 16-byte chunks of the half's swizzle atom
+#pragma unroll
+          for (int j = 0; j < kHalfCols / 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, grp * (kHalfCols / 8) + j)) = pk[j];
+          fence_proxy_async_smem();
+          mbar_arrive(h_full + 2 * b + half);
+        }
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + c] = clock64();
       }
-      // ---- final epilogue on Y: each warpgroup takes 128 of the 256 columns
-      mbar_wait(y_full, it & 1);
-      tc_fence_after();
-      // every MMA of the tile has retired: the input tile (-> parameters, group 1's staging ring) and the H buffers
-      // (-> group 0's ring) are dead
-      resid_stage_params<D, 256>(sparam, threadIdx.x - 128, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
-      uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
-      if (elected) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
-      ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
-      resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase, sparam,
-                                      &tmX, &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sA + 8192));
-      mbar_arrive(tile_done);
-      if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
+      // ---- final epilogue on Y: warpgroups 0 and 1 take 128 of the 256 columns each
+      if (grp < 2) {
+        mbar_wait(y_full, it & 1);
+        tc_fence_after();
+        // every MMA of the tile has retired: the input tile (-> parameters, group 1's staging ring) and the H buffers
+        // (-> group 0's ring) are dead
+        resid_stage_params<D, 256>(sparam, threadIdx.x - 128, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
+        uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
+        if (elected) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+        ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
+        resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
+                                        sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups, reinterpret_cast<float2*>(sA + 8192));
+        mbar_arrive(tile_done);
+        if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
+      }
     }
     if (elected) bulk_wait_all<0>();
   }
