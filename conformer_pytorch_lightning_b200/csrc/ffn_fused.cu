@@ -2,16 +2,19 @@
 //     X += alpha * ( W2 . silu(W1 . y + b1) + b2 )        [+ the LayerNorm(s) that follow, in the same kernel]
 // replacing w_1 -> SiLU -> w_2 of feedforward.py:16-21 plus encoder_layer.py:58-59 / 69-70,56 of the reference.
 // The (tokens x 2048) hidden activation never leaves the SM: per 128-token tile the hidden dimension is walked in
-// chunks of 128 units,
-//     S_c = y . W1_c^T        tcgen05.mma M=128 N=128 K=256   -> TMEM S[c&1]   (double buffered)
-//     H_c = silu(S_c + b1_c)  8 epilogue warps: tcgen05.ld -> tanh.approx -> bf16 -> swizzled smem (A operand)
-//     Y  += H_c . W2_c^T      tcgen05.mma M=128 N=2x128 K=128 -> TMEM Y (256 columns, lives for the whole tile)
-// and the tensor pipe alternates G1(c+2) / G2(c) so that the SiLU of chunk c+1 overlaps both.  Weights stream
-// through a ring of 16 KB TMA pieces (128 rows x 64 k, 128-byte swizzle); the input tile y (64 KB) is loaded once.
+// chunks of 128 units, two chunks (a pair) per G1 job,
+//     S_p = y . W1_p^T        tcgen05.mma M=128 N=256 K=256   -> TMEM S (256 columns = chunks 2p, 2p+1)
+//     H_c = silu(S_c + b1_c)  8 epilogue warps: tcgen05.ld -> tanh.approx -> bf16 -> swizzled smem (A operand),
+//                             handed over in two 64-column halves (= the k atoms of G2)
+//     Y  += H_c . W2_c^T      tcgen05.mma M=128 N=256 K=128   -> TMEM Y (256 columns, lives for the whole tile)
+// and the tensor pipe runs  G1(p+1) G2(2p) G2(2p+1)  so that the SiLU of pair p+1 overlaps the G2s of pair p and
+// G1(p+2).  Every MMA has N = 256: an N = 128 MMA with both operands in shared memory reads 128 B/clk, the whole SM
+// budget, and was measured 50 % slower than nominal next to the TMA / SiLU traffic.  Weights stream through a ring
+// of 32 KB TMA pieces (256 rows x 64 k, 128-byte swizzle); the input tile y (64 KB) is loaded once.
 // The final epilogue is the shared residual/LayerNorm epilogue (resid_epilogue.cuh) on the Y accumulator; its
-// staging ring aliases the H buffers, which are dead by then.
+// staging rings alias the H buffers and the input tile, which are dead by then.
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-11: epilogue (two warpgroups,
-//   each owning 64 of the 128 hidden columns of a chunk; warpgroup 0 alone runs the final residual epilogue).
+//   each owning 32 columns of both halves of a chunk, and 128 of the 256 output columns in the final epilogue).
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 #include "resid_epilogue.cuh"
@@ -27,8 +30,8 @@ constexpr int HC = 128;         // hidden units per chunk
 constexpr int BM = 128;
 constexpr int kAtom = 16384;    // one swizzle atom tile: 128 rows x 64 k bf16
 constexpr int kPiece = 32768;   // one weight piece = one ring slot = 512 tensor-pipe cycles of MMA work per barrier wait
-                                //   G1: W1 rows [c*128,+128) x 128 k  (two atoms side by side, 8 MMAs N=128)
-                                //   G2: W2 rows [0,256) x 64 hidden-k  (one 256-row tile,      4 MMAs N=256)
+                                //   G1: W1 rows [256 p,+256) x 64 k   (4 MMAs N=256)
+                                //   G2: W2 rows [0,256) x 64 hidden-k (4 MMAs N=256)
 constexpr int NST = 3;          // weight ring depth
 constexpr int kABytes = BM * D * 2;            // 64 KB
 constexpr int kHBytes = BM * HC * 2;           // 32 KB per H buffer
@@ -58,13 +61,18 @@ struct FfnParams {
   long long* trace;   // optional per-event clock64 timestamps of CTA 0 (tools/ffn_trace.py); nullptr in production
 };
 
-// job jx of a tile: G1(c) or G2(c), ordered so the tensor pipe always has independent work while SiLU(c) runs:
-//   G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(NC-3) G1(NC-1) | G2(NC-2) G2(NC-1)
-__device__ __forceinline__ void job_of(int jx, int NC, bool& g1, int& c) {
-  if (jx < 2) { g1 = true; c = jx; }
-  else if (jx >= 2 * NC - 2) { g1 = false; c = jx - NC; }
-  else if (jx & 1) { g1 = true; c = (jx + 1) >> 1; }
-  else { g1 = false; c = (jx - 2) >> 1; }
+// job jx of a tile.  G1(p) computes S for the PAIR p of hidden chunks (N = 256: with N = 128 a tcgen05.mma reads
+// 128 B of shared memory per cycle, the whole SM budget, and every TMA / SiLU store slows it down), G2(c) consumes
+// chunk c.  Order:  G1(0) | G1(1) G2(0) G2(1) | G1(2) G2(2) G2(3) | ... | G1(NP-1) G2(2NP-4) G2(2NP-3) | G2(2NP-2) G2(2NP-1)
+// so that the SiLU of pair p overlaps G1(p+1) and the G2s of pair p-1.  idx = pair (G1) or chunk (G2).
+__device__ __forceinline__ void job_of(int jx, int NP, bool& g1, int& idx) {
+  if (jx == 0) { g1 = true; idx = 0; return; }
+  const int q = (jx - 1) / 3, r = (jx - 1) % 3;
+  if (q < NP - 1) {
+    if (r == 0) { g1 = true; idx = q + 1; } else { g1 = false; idx = 2 * q + r - 1; }
+  } else {
+    g1 = false; idx = 2 * (NP - 1) + (jx - 1 - 3 * (NP - 1));
+  }
 }
 
 // CL = thread-block cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on adjacent
@@ -92,9 +100,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* w_full = bars;                    // [NST]
   uint64_t* w_empty = w_full + NST;           // [NST]
   uint64_t* a_full = w_empty + NST;           // [1]
-  uint64_t* s_full = a_full + 1;              // [2]  S[b] accumulator complete (MMA commit)
-  uint64_t* s_empty = s_full + 2;             // [2]  S[b] drained by the SiLU threads
-  uint64_t* h_full = s_empty + 2;             // [2][2]  64-column half of H[b] written by the SiLU threads
+  uint64_t* s_full = a_full + 1;              // [1]  S accumulator of a chunk pair complete (MMA commit)
+  uint64_t* s_empty = s_full + 1;             // [1]  S read by all SiLU threads
+  uint64_t* h_full = s_empty + 1;             // [2][2]  64-column half of H[b] written by the SiLU threads
   uint64_t* h_empty = h_full + 4;             // [2]  G2 finished reading H[b] (MMA commit)
   uint64_t* y_full = h_empty + 2;             // [1]  all MMAs of the tile complete
   uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
@@ -106,7 +114,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   // zero-fills their loads and clips their stores) so that the shared weight ring stays in lock-step
   const int m_tiles = ((p.M + BM - 1) / BM + CL - 1) / CL * CL;
   const int NC = p.F / HC;
-  const int n_jobs = 2 * NC;
+  const int NP = NC / 2;                     // pairs of hidden chunks (F % 256 == 0)
+  const int n_jobs = 3 * NP;
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (1u << CL) - 1u;
 
@@ -117,8 +126,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
     mbar_init(a_full, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, kSiluThreads);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(s_full + s, 1); mbar_init(s_empty + s, kSiluThreads);
       mbar_init(h_full + 2 * s, kSiluThreads); mbar_init(h_full + 2 * s + 1, kSiluThreads); mbar_init(h_empty + s, 1);
     }
     mbar_init(y_full, 1);
@@ -150,26 +159,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       __syncwarp();
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
-        job_of(jx, NC, g1, c);
-        for (int pc = 0; pc < 2; ++pc) {
+        job_of(jx, NP, g1, c);
+        const int n_pc = g1 ? 4 : 2;
+        for (int pc = 0; pc < n_pc; ++pc) {
           mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
           if (elect_one()) {
             uint8_t* dst = sW + stage * kPiece;
             mbar_expect_tx(w_full + stage, kPiece);
-            if (g1) {          // W1_c[:, pc*128 .. +128): atoms a = 0,1 at k = pc*128 + a*64
-              if constexpr (CL == 1) {
-                tma_load_2d(dst, &tmW1, w_full + stage, pc * 128, c * HC);
-                tma_load_2d(dst + kAtom, &tmW1, w_full + stage, pc * 128 + 64, c * HC);
-              } else {         // each CTA fetches one atom and multicasts it
-                tma_load_2d_mc(dst + crank * kAtom, &tmW1, w_full + stage, pc * 128 + crank * 64, c * HC, kMask);
-              }
-            } else {           // W2[:, c*128 + pc*64 .. +64): 256 output rows
-              if constexpr (CL == 1) {
-                tma_load_2d(dst, &tmW2, w_full + stage, c * HC + pc * 64, 0);
-                tma_load_2d(dst + kAtom, &tmW2, w_full + stage, c * HC + pc * 64, 128);
-              } else {         // each CTA fetches 128 of the 256 rows and multicasts them
-                tma_load_2d_mc(dst + crank * kAtom, &tmW2, w_full + stage, c * HC + pc * 64, crank * 128, kMask);
-              }
+            // G1: W1 rows [256 c, +256) x k [64 pc, +64);  G2: W2 rows [0,256) x hidden k [128 c + 64 pc, +64)
+            const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
+            const int col = g1 ? pc * 64 : c * HC + pc * 64;
+            const int row = g1 ? c * 256 : 0;
+            if constexpr (CL == 1) {
+              tma_load_2d(dst, tm, w_full + stage, col, row);
+              tma_load_2d(dst + kAtom, tm, w_full + stage, col, row + 128);
+            } else {           // each CTA fetches 128 of the 256 rows and multicasts them
+              tma_load_2d_mc(dst + crank * kAtom, tm, w_full + stage, col, row + crank * 128, kMask);
             }
           }
           __syncwarp();
@@ -179,20 +184,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-    constexpr uint32_t idesc1 = umma_idesc_bf16(BM, 128);   // G1: N = 128 hidden units
-    constexpr uint32_t idesc2 = umma_idesc_bf16(BM, 256);   // G2: N = 256 outputs
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, 256);    // G1: 256 hidden units of a chunk pair, G2: 256 outputs
     int stage = 0, phase = 0, it = 0;
     bool have = false;   // w_full of the current slot already seen complete by the probe issued before the previous MMAs
-    uint32_t n_se0 = 0, n_se1 = 0, n_hf0 = 0, n_hf1 = 0;
+    uint32_t n_se = 0, n_hf0 = 0, n_hf1 = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
       mbar_wait(a_full, it & 1);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
       // The issuing warp runs in lock-step with the tensor pipe (it accepts only a few MMAs ahead), so every cycle
-      // between two issue blocks is an idle pipe cycle.  The job sequence  G1(0) G1(1) | G2(c) G1(c+2) ... | G2 G2  is
-      // therefore written out without any per-job decoding, and the barrier of the NEXT issue block (ring slot or
-      // S/H hand-over) is probed non-blockingly before the current block's MMAs are issued.
+      // between two issue blocks is an idle pipe cycle.  The job sequence is therefore written out without any per-job
+      // decoding, and the barrier of the NEXT issue block (ring slot or S/H hand-over) is probed non-blockingly
+      // before the current block's MMAs are issued.
       bool job_ready = false;           // the next job's S/H barrier was already seen complete
       auto next_slot_probe = [&]() {
         const int ns = (stage + 1 == NST) ? 0 : stage + 1;
@@ -200,35 +204,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       };
       auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
       // probe used while issuing the last piece of a job: is the barrier of the following job complete?
-      auto probe_g1 = [&](int c) { const int b = c & 1; return mbar_test(s_empty + b, ((b ? n_se1 : n_se0) & 1) ^ 1); };
+      auto probe_g1 = [&]() { return mbar_test(s_empty, (n_se & 1) ^ 1); };
       auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + 2 * b, (b ? n_hf1 : n_hf0) & 1); };
 
-      auto do_g1 = [&](int c, int next_kind, int next_c) {     // next_kind: 1 = G1, 2 = G2, 0 = none
-        const int b = c & 1;
-        uint32_t& n_se = b ? n_se1 : n_se0;
-        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + c] = clock64();
-        if (!job_ready) mbar_wait(s_empty + b, (n_se & 1) ^ 1);     // SiLU stage drained S[b] (two chunks ago)
-        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + c] = clock64();
+      auto do_g1 = [&](int pr, int next_kind, int next_c) {    // next_kind: 1 = G1, 2 = G2, 0 = none
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + pr] = clock64();
+        if (!job_ready) mbar_wait(s_empty, (n_se & 1) ^ 1);         // SiLU stage has read S of the previous pair
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + pr] = clock64();
         ++n_se;
         tc_fence_after();
 #pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
+        for (int pc = 0; pc < 4; ++pc) {                             // pc = 64-wide k atom of the input tile
           if (!have) mbar_wait(w_full + stage, phase);
           tc_fence_after();
           next_slot_probe();
-          if (pc == 1) job_ready = (next_kind == 1) ? probe_g1(next_c) : (next_kind == 2 ? probe_g2(next_c) : false);
+          if (pc == 3) job_ready = (next_kind == 1) ? probe_g1() : (next_kind == 2 ? probe_g2(next_c) : false);
           if (elect_one()) {
-            const uint32_t w_addr = smem_u32(sW + stage * kPiece);
+            const uint64_t da = umma_desc_sw128(a_addr + pc * kAtom);
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              const uint64_t da = umma_desc_sw128(a_addr + (2 * pc + a) * kAtom);
-              const uint64_t db = umma_desc_sw128(w_addr + a * kAtom);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + b * HC, da + 2 * k, db + 2 * k, idesc1, (pc | a | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
             if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-            if (pc == 1) umma_commit(s_full + b);
+            if (pc == 3) umma_commit(s_full);
           }
           __syncwarp();
           advance();
@@ -251,12 +248,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (!have) mbar_wait(w_full + stage, phase);
           tc_fence_after();
           next_slot_probe();
-          if (pc == 1) job_ready = (next_kind == 1) ? probe_g1(next_c) : (next_kind == 2 ? probe_g2(next_c) : false);
+          if (pc == 1) job_ready = (next_kind == 1) ? probe_g1() : (next_kind == 2 ? probe_g2(next_c) : false);
           if (elect_one()) {
             const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
             const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc2, (c | pc | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc, (c | pc | k) != 0);
             if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
             if (pc == 1) {
               umma_commit(h_empty + b);
@@ -269,11 +266,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         ++n_hf;
       };
       job_ready = false;
-      do_g1(0, 1, 1);
-      do_g1(1, 2, 0);
-      for (int c = 0; c + 2 < NC; ++c) {
-        do_g2(c, 1, c + 2, false);
-        do_g1(c + 2, 2, c + 1);
+      do_g1(0, NP > 1 ? 1 : 2, 0);
+      for (int pr = 0; pr + 1 < NP; ++pr) {
+        do_g1(pr + 1, 2, 2 * pr);
+        do_g2(2 * pr, 2, 2 * pr + 1, false);
+        do_g2(2 * pr + 1, pr + 2 < NP ? 1 : 2, 2 * pr + 2, false);
       }
       do_g2(NC - 2, 2, NC - 1, false);
       do_g2(NC - 1, 0, 0, true);
@@ -288,62 +285,67 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     const int bar_id = 1 + grp;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ring_phase = 0;
-    uint32_t n_sf0 = 0, n_sf1 = 0, n_he0 = 0, n_he1 = 0;
+    uint32_t n_sf = 0, n_he0 = 0, n_he1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
-      // ---- SiLU stage: S[b] -> H[b].  The b1 slice of chunk c+1 is fetched into a register while chunk c is being
-      //      processed, so its L2 latency never sits between two chunks.
+      // ---- SiLU stage: S (chunk pair) -> H[0], H[1].  The b1 slice of the next pair is fetched into registers while
+      //      this pair is being processed, so its L2 latency never sits between two pairs.
       if (it > 0 && grp >= 2) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
       // et < kSiluCols: the hidden columns this warpgroup reads (kHalfCols of each 64-column half)
       const int bcol = (et / kHalfCols) * 64 + grp * kHalfCols + (et % kHalfCols);
-      float b1_next = (et < kSiluCols) ? __ldg(p.b1 + bcol) : 0.f;
-      for (int c = 0; c < NC; ++c) {
-        const int b = c & 1;
+      float b1_n0 = 0.f, b1_n1 = 0.f;
+      if (et < kSiluCols) { b1_n0 = __ldg(p.b1 + bcol); b1_n1 = __ldg(p.b1 + HC + bcol); }
+      for (int pr = 0; pr < NP; ++pr) {
+        named_bar_sync(bar_id, 128);                      // the group has finished reading the previous pair's b1
         if (et < kSiluCols) {
-          sb1[b * HC + bcol] = b1_next;
-          if (c + 1 < NC) b1_next = __ldg(p.b1 + (c + 1) * HC + bcol);
+          sb1[bcol] = b1_n0;
+          sb1[HC + bcol] = b1_n1;
+          if (pr + 1 < NP) { b1_n0 = __ldg(p.b1 + (2 * pr + 2) * HC + bcol); b1_n1 = __ldg(p.b1 + (2 * pr + 3) * HC + bcol); }
         }
         named_bar_sync(bar_id, 128);
-        uint32_t& n_sf = b ? n_sf1 : n_sf0;
-        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[2 * 64 + c] = clock64();
-        mbar_wait(s_full + b, n_sf & 1);
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[2 * 64 + 2 * pr] = clock64();
+        mbar_wait(s_full, n_sf & 1);                      // S holds both chunks of the pair
         ++n_sf;
         tc_fence_after();
-        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[3 * 64 + c] = clock64();
-        // two 64-column halves (= the two k atoms of G2): this warpgroup takes kHalfCols columns of each, so that the
-        // first atom of H[b] is complete after half of the chunk's MUFU work and G2 can start on it
-        uint32_t v0[kHalfCols], v1[kHalfCols];
-        tmem_ld(tmem_base + lane_base + b * HC + grp * kHalfCols, v0);
-        tmem_ld(tmem_base + lane_base + b * HC + 64 + grp * kHalfCols, v1);
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[3 * 64 + 2 * pr] = clock64();
+        // S is read out completely first so that the next pair's G1 can start; v[b][half] = this warpgroup's kHalfCols
+        // columns of 64-column half `half` (= k atom of G2) of chunk 2 pr + b
+        uint32_t v[2][2][kHalfCols];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) tmem_ld(tmem_base + lane_base + b * HC + half * 64 + grp * kHalfCols, v[b][half]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(s_empty + b);                         // S[b] may be overwritten by G1(c+2)
-        uint32_t& n_he = b ? n_he1 : n_he0;
+        mbar_arrive(s_empty);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t (&v)[kHalfCols] = half ? v1 : v0;
-          const float* bs = sb1 + b * HC + half * 64 + grp * kHalfCols;
-          uint4 pk[kHalfCols / 8];
+        for (int b = 0; b < 2; ++b) {
+          uint32_t& n_he = b ? n_he1 : n_he0;
 #pragma unroll
-          for (int j = 0; j < kHalfCols / 8; ++j) {
-            float f[8];
+          for (int half = 0; half < 2; ++half) {
+            const float* bs = sb1 + b * HC + half * 64 + grp * kHalfCols;
+            uint4 pk[kHalfCols / 8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[8 * j + e]) + bs[8 * j + e]);
-            pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            for (int j = 0; j < kHalfCols / 8; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = silu_fast(__uint_as_float(v[b][half][8 * j + e]) + bs[8 * j + e]);
+              pk[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            }
+            if (half == 0) {
+              if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[5 * 64 + 2 * pr + b] = clock64();
+              mbar_wait(h_empty + b, (n_he & 1) ^ 1);       // G2 of two chunks ago finished reading H[b]
+              ++n_he;
+            }
+            uint8_t* hb = sH + b * kHBytes + half * kAtom;  // this group's 16-byte chunks of the half's swizzle atom
+#pragma unroll
+            for (int j = 0; j < kHalfCols / 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, grp * (kHalfCols / 8) + j)) = pk[j];
+            fence_proxy_async_smem();
+            mbar_arrive(h_full + 2 * b + half);
           }
-          if (half == 0) {
-            if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[5 * 64 + c] = clock64();
-            mbar_wait(h_empty + b, (n_he & 1) ^ 1);         // G2(c-2) finished reading H[b]
-            ++n_he;
-          }
-          uint8_t* hb = sH + b * kHBytes + half * kAtom;    // this group's 16-byte chunks of the half's swizzle atom
-#pragma unroll
-          for (int j = 0; j < kHalfCols / 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, grp * (kHalfCols / 8) + j)) = pk[j];
-          fence_proxy_async_smem();
-          mbar_arrive(h_full + 2 * b + half);
+          if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + 2 * pr + b] = clock64();
         }
-        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + c] = clock64();
       }
       // ---- final epilogue on Y: warpgroups 0 and 1 take 128 of the 256 columns each
       if (grp < 2) {
@@ -381,7 +383,7 @@ int make_2d_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols,
 
 bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, int dtype, int ln_mode) {
   if (dtype != CFM_BF16 || tc::encode_tiled_fn() == nullptr) return false;
-  if (d != D || F % HC != 0 || F < 2 * HC || M < 64) return false;
+  if (d != D || F % (2 * HC) != 0 || M < 64) return false;
   if (ld_in % 8 != 0 || ldx % 4 != 0) return false;
   if (ln_mode != 0 && ld_out % 8 != 0) return false;
   return true;

@@ -21,4 +21,5 @@ print("chunk | MMA warp: G1 start, after s_empty wait | G2 start, after h_full[0
       " SiLU thread: begin-wait s_full, got s_full, first half computed, arrived h_full[1]   [cycles since G1(0)]")
 for c in range(NC):
     r = lambda i: int(t[i, c]) - t0
-    print(f"  {c:2d} | {r(0):6d} {r(1):6d} | {r(6):6d} {r(7):6d} {r(8):6d} {r(9):6d} | {r(2):6d} {r(3):6d} {r(5):6d} {r(4):6d}")
+    g = lambda i: int(t[i, c // 2]) - t0          # G1 stamps are per chunk PAIR
+    print(f"  {c:2d} | {g(0):6d} {g(1):6d} | {r(6):6d} {r(7):6d} {r(8):6d} {r(9):6d} | {int(t[2, c - (c & 1)]) - t0:6d} {int(t[3, c - (c & 1)]) - t0:6d} {r(5):6d} {r(4):6d}")
