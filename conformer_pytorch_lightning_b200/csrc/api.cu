@@ -120,6 +120,42 @@ extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1
                      eps, engine == CFM_ENGINE_TC ? CFM_ENGINE_AUTO : engine, stream);
 }
 
+extern "C" int cfm_mhsa_out(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
+                            const void* v, int64_t v_bs, int64_t v_ts, int B, int H, int Tq, int Tk, const uint8_t* mask,
+                            int64_t mask_bs, int64_t mask_rs, const float* key_bias, float scale, const void* Wo,
+                            const float* bo, float* X, int dtype, const float* g1, const float* be1, void* Y,
+                            const uint8_t* y_row_valid, float eps, void* ctx_ws, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(q && k && v && Wo && bo && X, "cfm_mhsa_out: null pointer");
+  CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_mhsa_out: bad dtype %d", dtype);
+  CFM_CHECK_ARG((g1 == nullptr) == (be1 == nullptr), "cfm_mhsa_out: inconsistent LayerNorm parameters");
+  CFM_CHECK_ARG(g1 == nullptr || Y != nullptr, "cfm_mhsa_out: LayerNorm requested but Y is null");
+  CFM_CHECK_ARG(B >= 0 && H > 0 && Tq >= 0 && Tk >= 0, "cfm_mhsa_out: bad shape");
+  if (B == 0 || Tq == 0) return 0;
+  const int d = H * 64, M = B * Tq;
+  // CFM_B200_MHSA_MODE: "unfused" = always attention kernel + residual GEMM
+  static int unfused_mode = -1;
+  if (unfused_mode < 0) {
+    const char* e = getenv("CFM_B200_MHSA_MODE");
+    unfused_mode = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
+  }
+  const bool fused_ok = scale > 0.f && mhsa_fused_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, d, dtype,
+                                                            key_bias != nullptr);
+  if (engine == CFM_ENGINE_TC)
+    CFM_CHECK_ARG(fused_ok, "cfm_mhsa_out: fused tcgen05 path does not support H=%d Tq=%d Tk=%d dtype=%d", H, Tq, Tk, dtype);
+  if (fused_ok && (engine == CFM_ENGINE_TC || (engine == CFM_ENGINE_AUTO && !unfused_mode)))
+    return mhsa_fused(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, B, Tq, mask, mask_bs, mask_rs, scale, Wo, bo, X, g1, be1, Y,
+                      y_row_valid, eps, (cudaStream_t)stream);
+  CFM_CHECK_ARG(ctx_ws != nullptr, "cfm_mhsa_out: the unfused path needs ctx_ws");
+  int rc = cfm_attention(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, ctx_ws, B, H, Tq, Tk, mask, mask_bs, mask_rs, key_bias,
+                         scale, dtype, engine, stream);
+  if (rc != 0) return rc;
+  if (g1 == nullptr)
+    return cfm_gemm(ctx_ws, d, Wo, bo, X, d, M, d, d, dtype, CFM_EPI_RESIDUAL, X, 1.f, nullptr, engine, stream);
+  return cfm_gemm_ln(ctx_ws, d, Wo, bo, X, d, M, d, d, dtype, 1.f, nullptr, g1, be1, nullptr, nullptr, Y, d, y_row_valid, eps,
+                     engine, stream);
+}
+
 extern "C" int cfm_conv_module(const void* y, const void* W1, const float* b1, const float* dw_w, const float* dw_b,
                                const void* W2, const float* b2, float* X, int B, int T, int d, int k, int dtype,
                                const uint8_t* row_valid, const float* g1, const float* be1, void* Y, float eps,

@@ -184,6 +184,12 @@ int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const
              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st);
 
+bool mhsa_fused_supported(int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts, int B, int H,
+                          int Tq, int Tk, int d, int dtype, bool has_key_bias);
+int mhsa_fused(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts, const void* v,
+               int64_t v_bs, int64_t v_ts, int B, int T, const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, float scale,
+               const void* Wo, const float* bo, float* X, const float* g1, const float* be1, void* Y,
+               const uint8_t* y_row_valid, float eps, cudaStream_t st);
 bool conv_fused_supported(int M, int T, int d, int k, int dtype);
 int conv_fused(const void* y_in, const void* W1, const float* b1, const float* dw_w, const float* dw_b, const void* W2,
                const float* b2, float* X, int M, int T, const uint8_t* row_valid, const float* g1, const float* be1,

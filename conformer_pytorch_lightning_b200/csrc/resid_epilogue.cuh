@@ -22,6 +22,16 @@ constexpr int kBufBytes = 128 * 128;   // one staging tile: 128 rows x 128 bytes
 // byte offset of 16-byte chunk j of row r inside a 128B-swizzled [128 x 128 B] tile
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return r * 128 + (((j ^ r) & 7) << 4); }
 
+// 2-D tensor maps address rows of the flattened (tokens, N) matrix; with z >= 0 the maps are 3-D (N, T, B) and the tile
+// is rows [m0, m0+ROWS) of utterance z, so that rows past the utterance's end are clipped instead of running into the
+// next utterance.
+__device__ __forceinline__ void resid_tma_load(void* dst, const CUtensorMap* tm, uint64_t* bar, int c, int m0, int z) {
+  if (z < 0) tma_load_2d(dst, tm, bar, c, m0); else tma_load_3d(dst, tm, bar, c, m0, z);
+}
+__device__ __forceinline__ void resid_tma_store(const CUtensorMap* tm, const void* src, int c, int m0, int z) {
+  if (z < 0) tma_store_2d(tm, src, c, m0); else tma_store_3d(tm, src, c, m0, z);
+}
+
 struct ResidParams {
   const uint8_t* row_valid;     // rows whose GEMM result is forced to 0 (pad mask)
   const uint8_t* y_row_valid;   // rows of y forced to 0
@@ -46,12 +56,12 @@ __device__ __forceinline__ void resid_stage_params(float* sparam, int et, const 
 // (ring, res_bar: the calling group's own; grp selects the group's column half when NG = 2)
 template <int BN, int R, int ROWS = 128, int NG = 1>
 __device__ __forceinline__ void resid_prefetch(uint8_t* ring, uint64_t* res_bar, const CUtensorMap* tmR, int n0, int m0,
-                                               int grp = 0) {
+                                               int grp = 0, int z = -1) {
   constexpr int NCHG = BN / 32 / NG;
 #pragma unroll
   for (int c = 0; c < (NCHG < R ? NCHG : R); ++c) {
     mbar_expect_tx(res_bar + c, ROWS * 128);
-    tma_load_2d(ring + c * kBufBytes, tmR, res_bar + c, n0 + (grp * NCHG + c) * 32, m0);
+    resid_tma_load(ring + c * kBufBytes, tmR, res_bar + c, n0 + (grp * NCHG + c) * 32, m0, z);
   }
 }
 
@@ -66,11 +76,11 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
                                                   uint8_t* ring, uint64_t* res_bar, uint32_t& ring_phase,
                                                   const float* sparam, const CUtensorMap* tmX, const CUtensorMap* tmR,
                                                   const CUtensorMap* tmY, const ResidParams& p, int grp = 0, int xbar = 0,
-                                                  float2* xch = nullptr) {
+                                                  float2* xch = nullptr, int z = -1, int grow0 = -1) {
   constexpr int NCH = BN / 32 / NG;              // 32-column fp32 chunks per row handled by this group
   const int ch0 = grp * NCH;                     // first chunk of this group
   const int ln = p.ln_mode;
-  const int row = m0 + r;
+  const int row = (grow0 >= 0 ? grow0 : m0) + r;   // row of the flattened (tokens, N) matrix: mask lookups
   const bool row_ok = row < p.M;
   const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
   const float a = valid ? p.alpha : 0.f;
@@ -106,18 +116,18 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     named_bar_sync(bar_id, 128);
     if (elected) {
       if (ln != 2) {
-        tma_store_2d(tmX, buf, n0 + (ch0 + c) * 32, m0);
+        resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z);
         bulk_commit();
         // refill the PREVIOUS chunk's buffer once its store has finished reading it
         if (c >= 1 && c - 1 + R < NCH) {
           bulk_wait_read<1>();
           const int pb = (c - 1) % R;
           mbar_expect_tx(res_bar + pb, ROWS * 128);
-          tma_load_2d(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (ch0 + c - 1 + R) * 32, m0);
+          resid_tma_load(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (ch0 + c - 1 + R) * 32, m0, z);
         }
       } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
         mbar_expect_tx(res_bar + b, ROWS * 128);
-        tma_load_2d(buf, tmR, res_bar + b, n0 + (ch0 + c + R) * 32, m0);
+        resid_tma_load(buf, tmR, res_bar + b, n0 + (ch0 + c + R) * 32, m0, z);
       }
     }
   }
@@ -163,7 +173,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
         tmem_st32(taddr + (ch0 + c) * 32, v);
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (elected) { tma_store_2d(tmX, buf, n0 + (ch0 + c) * 32, m0); bulk_commit(); }
+        if (elected) { resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z); bulk_commit(); }
       }
       tmem_st_wait();
       if (NG == 2) {
@@ -205,7 +215,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
       }
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
-      if (elected) { tma_store_2d(tmY, buf, sub * 64, m0); bulk_commit(); }
+      if (elected) { resid_tma_store(tmY, buf, sub * 64, m0, z); bulk_commit(); }
     }
   }
   tc_fence_before();

@@ -222,6 +222,12 @@ def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws, ln=
             raise RuntimeError(f"pos_embed gives {P} position rows per batch element; expected 1 or Tk={Tk}")
         # P == 1 (batched forward): matrix_bd is constant along keys -> softmax-invariant
     ctx = ws.get("attn_ctx", (n, d), dt, dev)
+    if x.is_contiguous() and (ln is None or ln.get("g2") is None):
+        # one library call: a single fused kernel per 128 query rows on the tcgen05 engine (bf16, 4 heads, T <= 256),
+        # attention kernel -> ctx -> residual GEMM(+LN) otherwise
+        ops.mhsa_out(q, k_use, v, W["wo"], W["bo"], x, mask=_mask_u8(attn_mask), key_bias=key_bias,
+                     scale=1.0 / math.sqrt(64.0), ln=ln, ctx_ws=ctx)
+        return new_cache
     ops.attention(q, k_use, v, ctx.view(B, T, d), mask=_mask_u8(attn_mask), key_bias=key_bias,
                   scale=1.0 / math.sqrt(64.0))
     _residual_gemm(ctx, W["wo"], W["bo"], x, 1.0, None, ln)

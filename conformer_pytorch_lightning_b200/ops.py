@@ -151,6 +151,43 @@ def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_
     return out
 
 
+def mhsa_out(q, k, v, wo, bo, x, *, mask=None, key_bias=None, scale, ln=None, ctx_ws=None, engine=N.ENGINE_AUTO):
+    """x += wo . attention(q, k, v, mask) + bo (+ fused LayerNorm, ln = dict(y, g1, b1, y_row_valid) or None);
+    q (B,Tq,H,64), k/v (B,Tk,H,64) views as in ``attention``; x (B*Tq, H*64) fp32; see cfm_mhsa_out."""
+    _req(q, "mhsa_out.q", contiguous=False)
+    B, Tq, H, dk = q.shape
+    Tk = k.shape[1]
+    if dk != 64:
+        raise RuntimeError(f"mhsa_out: head dim {dk} unsupported (kernels are specialised for d_k = 64)")
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if t.stride(3) != 1 or t.stride(2) != 64 or t.dtype != q.dtype:
+            raise RuntimeError(f"mhsa_out.{n}: need (H,64) contiguous tail and a common dtype")
+    d = H * 64
+    _req(wo, "mhsa_out.wo", q.dtype)
+    _req(x, "mhsa_out.x", torch.float32)
+    if x.shape != (B * Tq, d) or wo.shape != (d, d):
+        raise RuntimeError("mhsa_out: shape mismatch")
+    mbs = mrs = 0
+    if mask is not None:
+        _req(mask, "mhsa_out.mask", contiguous=False)
+        if mask.dtype not in (torch.uint8, torch.bool) or mask.stride(2) != 1 or mask.shape[2] != Tk:
+            raise RuntimeError("mhsa_out.mask: need uint8/bool with contiguous key axis of length Tk")
+        mbs = 0 if mask.shape[0] == 1 else mask.stride(0)
+        mrs = 0 if mask.shape[1] == 1 else mask.stride(1)
+    ln = ln or {}
+    yo = ln.get("y")
+    if yo is not None:
+        _req(yo, "mhsa_out.y", q.dtype)
+    if ctx_ws is not None:
+        _req(ctx_ws, "mhsa_out.ctx_ws", q.dtype)
+    ensure_init(q)
+    N.check(N.lib().cfm_mhsa_out(q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1),
+                                 v.data_ptr(), v.stride(0), v.stride(1), B, H, Tq, Tk, _ptr(mask), mbs, mrs,
+                                 _ptr(key_bias), float(scale), wo.data_ptr(), bo.data_ptr(), x.data_ptr(), _DT[q.dtype],
+                                 _ptr(ln.get("g1")), _ptr(ln.get("b1")), _ptr(yo), _ptr(ln.get("y_row_valid")), 1e-5,
+                                 _ptr(ctx_ws), engine, _stream(q)))
+
+
 def relpos_keys(k, p, u, vb, k_out, key_bias):
     """k (B,Tk,H,64) view, p (Bp,Tk,H*64) contiguous with Bp in {1,B}; see cfm_relpos_keys."""
     B, Tk, H, _ = k.shape

@@ -150,6 +150,23 @@ int cfm_dwconv(const void* x, const float* w, const float* bias, void* y,
                int B, int T, int d, int k, int dtype, int apply_silu, void* stream);
 
 /*
+ * Self-attention core + output projection on the residual stream, in place (attention.py:84-99 + encoder_layer.py:60-63):
+ *   ctx = cfm_attention(q, k, v, mask, key_bias, scale)   (all H heads, head dim 64, d = 64 H)
+ *   X  += Wo ctx + bo,  then, if g1 != NULL, Y = ymask(LN(X; g1, be1))
+ * q, k, v, mask, key_bias, scale: exactly as in cfm_attention (q: (B,Tq,H,64) view, k/v: (B,Tk,H,64) views);
+ * Wo: (d,d) act dtype, bo (d) fp32; X: (B*Tq, d) fp32 contiguous; Y: (B*Tq, d) act dtype contiguous.
+ * On the tcgen05 engine (bf16, H == 4, Tq == Tk <= 256, no key_bias) this is ONE kernel per 128 query rows and the
+ * context never touches HBM; otherwise the library runs cfm_attention into ctx_ws ((B*Tq, d) act dtype, may be NULL
+ * only if the fused path applies) followed by cfm_gemm / cfm_gemm_ln.
+ */
+int cfm_mhsa_out(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
+                 const void* v, int64_t v_bs, int64_t v_ts, int B, int H, int Tq, int Tk,
+                 const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias, float scale,
+                 const void* Wo, const float* bo, float* X, int dtype,
+                 const float* g1, const float* be1, void* Y, const uint8_t* y_row_valid, float eps,
+                 void* ctx_ws, int engine, void* stream);
+
+/*
  * Whole convolution module (inference: BatchNorm running statistics folded) on the residual stream, in place
  * (convolution.py:34-49 + encoder_layer.py:64-67):
  *   X += rowmask( W2 silu( dw( glu( W1 y + b1 ) ) ) + b2 ),  then, if g1 != NULL, Y = LN(X; g1, be1)

@@ -350,6 +350,57 @@ def test_ffn_fused_tcgen05(M, F, mode):
         assert rel_err(x, x_ref) < 2e-3 and rel_err(yio.float(), y_ref) < 8e-3
 
 
+@pytest.mark.parametrize("B,T", [(1, 64), (2, 128), (3, 129), (64, 248), (5, 256), (2, 100)])
+@pytest.mark.parametrize("mask_kind", ["none", "pad", "full"])
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_mhsa_out_fused_tcgen05(B, T, mask_kind, with_ln):
+    """Attention over all heads + output projection + residual (+ LayerNorm) in one kernel vs fp32 torch on the same
+    bf16 operands, and vs the unfused attention + GEMM chain of the library."""
+    dt, H, d = torch.bfloat16, 4, 256
+    qkv = rnd(B, T, 3, H, 64, dtype=dt, scale=1.5)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    wo = rnd(d, d, dtype=dt, scale=1 / 16, seed=1)
+    bo = rnd(d, seed=2) * 0.5
+    g1, be1 = rnd(d, seed=3) * 0.1 + 1, rnd(d, seed=4) * 0.1
+    x0 = rnd(B * T, d, seed=5, scale=2.0)
+    yv = (torch.arange(B * T, device=DEV) % 5 != 2).to(torch.uint8)
+    mask = None
+    if mask_kind == "pad":
+        lens = torch.tensor([T - (7 * i) % max(T // 2, 1) for i in range(B)], device=DEV)
+        mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).unsqueeze(1)            # (B,1,T)
+    elif mask_kind == "full":
+        idx = torch.arange(T, device=DEV)
+        mask = ((idx[None, :] // 16) <= (idx[:, None] // 16)).unsqueeze(0).expand(B, T, T).contiguous()   # chunk-causal
+        mask[:, T // 3, :] = False                                                                # a fully masked row
+    Fn = torch.nn.functional
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = qf @ kf.transpose(-1, -2) * 0.125
+    if mask is not None:
+        m4 = mask.unsqueeze(1)
+        s = s.masked_fill(~m4, float("-inf"))
+        pr = torch.softmax(s, -1).masked_fill(~m4, 0.0)
+        pr = torch.nan_to_num(pr, nan=0.0)
+    else:
+        pr = torch.softmax(s, -1)
+    ctx = (pr @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
+    x_ref = x0 + ctx.to(dt).float() @ wo.float().t() + bo
+    y_ref = Fn.layer_norm(x_ref, (d,), g1, be1, 1e-5) * yv[:, None]
+    res = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_SIMT):
+        x = x0.clone()
+        y = torch.full((B * T, d), float("nan"), dtype=dt, device=DEV)
+        ln = {"y": y, "g1": g1, "b1": be1, "y_row_valid": yv} if with_ln else None
+        cws = torch.empty(B * T, d, dtype=dt, device=DEV)
+        ops.mhsa_out(q, k, v, wo, bo, x, mask=mask, scale=0.125, ln=ln, ctx_ws=cws, engine=eng)
+        assert torch.isfinite(x).all()
+        assert rel_err(x, x_ref) < 4e-3, (eng, rel_err(x, x_ref))
+        if with_ln:
+            assert rel_err(y.float(), y_ref) < 8e-3, (eng, rel_err(y.float(), y_ref))
+            assert float(y.float()[yv == 0].abs().max()) == 0.0
+        res[eng] = x
+    assert rel_err(res[N.ENGINE_TC], res[N.ENGINE_SIMT]) < 4e-3
+
+
 @pytest.mark.parametrize("B,T", [(1, 64), (1, 114), (2, 115), (3, 57), (5, 15), (64, 248), (7, 333), (1, 1000)])
 @pytest.mark.parametrize("with_ln", [False, True])
 def test_conv_module_fused_tcgen05(B, T, with_ln):

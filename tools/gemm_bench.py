@@ -129,9 +129,33 @@ def conv_bench(B=64, T=248, d=256, k=15):
             print(f"conv module {name:10s} {mode:6s} B={B} T={T}: {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)")
 
 
+def mhsa_bench(B=64, T=248, H=4, d=256):
+    dev = "cuda"
+    qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    wo = (torch.randn(d, d, device=dev) / 16).bfloat16(); bo = torch.randn(d, device=dev)
+    g = torch.ones(d, device=dev); b = torch.zeros(d, device=dev)
+    x = torch.randn(B * T, d, device=dev)
+    y = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+    ctx = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+    mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
+    ln = {"y": y, "g1": g, "b1": b}
+    fl = 4.0 * B * T * T * d + 2.0 * B * T * d * d
+    t = timeit(lambda: ops.mhsa_out(q, k, v, wo, bo, x, mask=mask, scale=0.125, ln=ln, engine=N.ENGINE_TC))
+    print(f"mhsa_out fused   (B={B},T={T}): {t:7.1f} us ({fl / t / 1e6:6.1f} TF/s)")
+    def unfused():
+        ops.attention(q, k, v, ctx.view(B, T, d), mask=mask, scale=0.125)
+        ops.gemm_ln(ctx, wo, bo, x, y, alpha=1.0, g1=g, b1=b)
+    t = timeit(unfused)
+    print(f"attention + Wo/LN GEMM       : {t:7.1f} us ({fl / t / 1e6:6.1f} TF/s)")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         small_kernels()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mhsa":
+        mhsa_bench()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "conv":
         conv_bench()
