@@ -34,7 +34,7 @@ constexpr int kQBytes = kAtom, kKBytes = 2 * kAtom, kVBytes = 2 * kAtom;
 constexpr int kStage = kQBytes + kKBytes + kVBytes;          // 80 KB
 constexpr int kPBytes = 4 * kAtom;                            // 64 KB: P (4 key atoms) / ctx (4 head atoms)
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = 2 * kStage + kPBytes + 1024 /*max exchange*/ + 512;
+constexpr int kSmemBytes = 2 * kStage + kPBytes + 2048 /*row max / row sum exchange*/ + 512;
 static_assert(kSmemBytes <= 232448, "smem budget");
 
 struct MhsaParams {
@@ -89,7 +89,8 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sStage = smem;                       // 2 x {Q 16 KB, K 32 KB, V 32 KB}; later W_o pieces, staging rings, parameters
   uint8_t* sP = smem + 2 * kStage;              // P tile -> ctx tile
   float* xch_m = reinterpret_cast<float*>(sP + kPBytes);        // [2][128] partial row maxima
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_m + 256);
+  float* xch_l = xch_m + 256;                                   // [2][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_l + 256);
   uint64_t* kv_full = bars;                     // [2]
   uint64_t* kv_empty = kv_full + 2;             // [2] P_h V_h retired: stage (and P tile) free
   uint64_t* s_full = kv_empty + 2;              // S_h complete
@@ -248,8 +249,10 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
     const uint32_t tmem_srow = tmem_base + lane_base + grp * 128;
-    float lsum[NH];
-#pragma unroll
+    // (the head loop is deliberately NOT unrolled: the kernel runs once per layer between other large kernels, so its
+    //  code is fetched cold and straight-line copies of the two passes cost more than they save)
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;              // complete row sums per head
+#pragma unroll 1
     for (int h = 0; h < NH; ++h) {
       if (tid == 0) MTR(8 + 4 * h);
       mbar_wait(s_full, h & 1);
@@ -306,23 +309,22 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
         }
       }
-      lsum[h] = l;
+      xch_l[grp * 128 + r] = l;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
       if (tid == 0) MTR(11 + 4 * h);
+      named_bar_sync(3, 256);
+      const float lt = l + xch_l[(grp ^ 1) * 128 + r];
+      l0 = h == 0 ? lt : l0; l1 = h == 1 ? lt : l1; l2 = h == 2 ? lt : l2; l3 = h == 3 ? lt : l3;
     }
     // ---- context: O_h / l_h -> bf16 A operand (head h = k atom h); this warpgroup takes 32 of each head's 64 columns
     mbar_wait(pv_done, (NH - 1) & 1);
     tc_fence_after();
     if (tid == 0) MTR(24);
-    float* xch_l = reinterpret_cast<float*>(sStage);        // [4][2][128] over the dead Q slot of stage 0
-#pragma unroll
-    for (int h = 0; h < NH; ++h) xch_l[(h * 2 + grp) * 128 + r] = lsum[h];
-    named_bar_sync(3, 256);
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
-      const float lt = lsum[h] + xch_l[(h * 2 + (grp ^ 1)) * 128 + r];
+      const float lt = h == 0 ? l0 : (h == 1 ? l1 : (h == 2 ? l2 : l3));
       const float inv = lt > 0.f ? 1.f / lt : 0.f;          // fully masked row -> 0 (attention.py:92)
       uint32_t v[32];
       tmem_ld32(tmem_o + lane_base + h * DK + grp * 32, v);
