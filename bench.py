@@ -17,7 +17,7 @@ e2e   : the same metric through the public API with pinned HOST fbank features: 
         synchronous forward call with both copies.
 roofline : dominant kernel = the fused feed-forward kernel (w_1 + SiLU + w_2 + residual + LayerNorm, ~half of
         the step), timed in-step with CUDA events around each of its 24 launches; `roofline_hbm` is the same
-        for the HBM-bound depthwise-conv + BatchNorm + SiLU kernel.
+        for the HBM-bound depthwise-conv kernel when it runs (unfused convolution path only; null otherwise).
 cpu_baseline / --impl reference : the ATen-CPU oracle port of the reference's CPU path (the reference is
         Python and cannot travel to the GPU box) on a bounded sample of the same workload.
 """
@@ -342,7 +342,9 @@ def run_ours(args):
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside the step)"}
     dw_bytes = 2.0 * n_tok * d * 2                    # read + write one bf16 (N,d) tensor
     ach_dw = dw_bytes / (t_dw * 1e-3) / 1e9
-    roofline_hbm = {"bound": "hbm", "kernel": f"dwconv_kernel k={cfg['kernel_size']} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
+    # the stand-alone depthwise kernel only runs on the unfused path (CFM_B200_CONV_MODE=unfused, fp32, d != 256):
+    # in conv_fused_kernel the GLU and depthwise tensors never reach HBM, so there is nothing to put on an HBM roofline
+    roofline_hbm = None if not ev["dw"] else {"bound": "hbm", "kernel": f"dwconv_kernel k={cfg['kernel_size']} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
                     "achieved": ach_dw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_dw / pk["hbm_gbs"],
                     "traffic": (traffic["dwconv_kernel"]["dram_read_bytes"] + traffic["dwconv_kernel"]["dram_write_bytes"])
                     if "dwconv_kernel" in traffic else None,
