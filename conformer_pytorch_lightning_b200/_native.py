@@ -21,7 +21,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 EXPORTS = [
     "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
-    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out",
+    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain",
 ]
 
 _lib = None
@@ -40,6 +40,8 @@ def _declare(lib):
     lib.cfm_gemm.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _p, _i, _p]
     lib.cfm_gemm_ln.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _f, _i, _p]
     lib.cfm_ffn.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p, _f, _p, _i, _p]
+    lib.cfm_ffn_chain.argtypes = ([_p, _i, _i, _i, _i] + [_p, _p, _p, _p, _f, _p, _p, _p, _p] * 2 +
+                                  [_p, _p, _p, _f, _p, _i, _p])
     lib.cfm_mhsa_out.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _f,
                                  _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p]
     lib.cfm_conv_module.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]

@@ -190,6 +190,35 @@ extern "C" int cfm_conv_module(const void* y, const void* W1, const float* b1, c
                      engine, stream);
 }
 
+extern "C" int cfm_ffn_chain(const void* y, int M, int d, int F, int dtype, const void* W1a, const float* b1a, const void* W2a,
+                             const float* b2a, float alpha_a, const float* g1a, const float* be1a, const float* g2a,
+                             const float* be2a, const void* W1b, const float* b1b, const void* W2b, const float* b2b,
+                             float alpha_b, const float* g1b, const float* be1b, const float* g2b, const float* be2b, float* X,
+                             void* Y, const uint8_t* y_row_valid, float eps, void* hidden_ws, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(y && W1a && b1a && W2a && b2a && W1b && b1b && W2b && b2b && X && Y, "cfm_ffn_chain: null pointer");
+  CFM_CHECK_ARG(g1a != nullptr && be1a != nullptr, "cfm_ffn_chain: the first module needs a LayerNorm (its output feeds the second)");
+  CFM_CHECK_ARG(M >= 0 && d > 0 && F > 0, "cfm_ffn_chain: bad shape");
+  if (M == 0) return 0;
+  // CFM_B200_FFN_CHAIN=0: always two cfm_ffn calls
+  static int chain_off = -1;
+  if (chain_off < 0) {
+    const char* e = getenv("CFM_B200_FFN_CHAIN");
+    chain_off = (e && e[0] == '0') ? 1 : 0;
+  }
+  const FfnModule a{W1a, b1a, W2a, b2a, alpha_a, g1a, be1a, g2a, be2a};
+  const FfnModule b{W1b, b1b, W2b, b2b, alpha_b, g1b, be1b, g2b, be2b};
+  const bool ok = (dtype == CFM_BF16) && ffn_chain_supported(M, d, F, dtype, a, b);
+  if (engine == CFM_ENGINE_TC) CFM_CHECK_ARG(ok, "cfm_ffn_chain: chained tcgen05 path does not support M=%d d=%d F=%d", M, d, F);
+  if (ok && (engine == CFM_ENGINE_TC || (engine == CFM_ENGINE_AUTO && !chain_off)))
+    return ffn_chain(y, a, b, X, M, F, Y, y_row_valid, eps, (cudaStream_t)stream);
+  int rc = cfm_ffn(y, d, W1a, b1a, W2a, b2a, X, d, M, d, F, dtype, alpha_a, g1a, be1a, g2a, be2a, Y, d, nullptr, eps, hidden_ws,
+                   engine, stream);
+  if (rc != 0) return rc;
+  return cfm_ffn(Y, d, W1b, b1b, W2b, b2b, X, d, M, d, F, dtype, alpha_b, g1b, be1b, g2b, be2b, Y, d, y_row_valid, eps, hidden_ws,
+                 engine, stream);
+}
+
 extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,
                              const void* v, int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk,
                              const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,

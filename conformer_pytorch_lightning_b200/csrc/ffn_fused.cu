@@ -51,13 +51,19 @@ static_assert(5 * D * 4 <= kABytes, "residual parameters alias the input tile");
 static_assert(kSmemBytes <= 232448, "smem budget");
 static_assert(2 * kHBytes == 4 * kBufBytes, "residual staging ring aliases the two H buffers");
 
-struct FfnParams {
+struct FfnStage {                  // one feed-forward module
   const float* b1;
   const float* b2;
   const float* g1; const float* be1; const float* g2; const float* be2;
-  const uint8_t* y_row_valid;
-  float alpha, eps;
-  int M, F, ln_mode;
+  float alpha;
+  int ln_mode;
+};
+struct FfnParams {
+  FfnStage st[2];
+  int n_stages;                    // 2: two modules chained on the same tile (X and y of the first stay on chip)
+  const uint8_t* y_row_valid;      // row mask of the LAST stage's y
+  float eps;
+  int M, F;
   long long* trace;   // optional per-event clock64 timestamps of CTA 0 (tools/ffn_trace.py); nullptr in production
 };
 
@@ -83,6 +89,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16, box 64 x 128
                  const __grid_constant__ CUtensorMap tmW1,   // W1 (F, 256) bf16, box 64 x 128
                  const __grid_constant__ CUtensorMap tmW2,   // W2 (256, F) bf16, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmW1b,  // second module of a chain (same shapes)
+                 const __grid_constant__ CUtensorMap tmW2b,
                  const __grid_constant__ CUtensorMap tmX,    // X  (M, 256) fp32 store, box 32 x 128
                  const __grid_constant__ CUtensorMap tmR,    // residual load (same tensor as X)
                  const __grid_constant__ CUtensorMap tmY,    // y out (M, 256) bf16 store, box 64 x 128
@@ -107,7 +115,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* y_full = h_empty + 2;             // [1]  all MMAs of the tile complete
   uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
   uint64_t* res_bar = tile_done + 1;          // [2 groups][4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* a_ready = res_bar + 8;            // [1]  chain: y of the first module written into sA (256 arrivals)
+  uint64_t* epi_done = a_ready + 1;           // [1]  chain: first module's epilogue no longer uses the weight ring (CL arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
@@ -122,6 +132,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
     prefetch_tmap(&tmX); prefetch_tmap(&tmR); prefetch_tmap(&tmY);
+    if (p.n_stages > 1) { prefetch_tmap(&tmW1b); prefetch_tmap(&tmW2b); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
@@ -133,6 +144,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     mbar_init(y_full, 1);
     mbar_init(tile_done, 256);
     for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
+    mbar_init(a_ready, 256); mbar_init(epi_done, CL);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -157,6 +169,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kAtom, &tmA, a_full, ka * 64, m0);
       }
       __syncwarp();
+      for (int sg = 0; sg < p.n_stages; ++sg) {
+      // chain: the first module's epilogue borrows the (then idle) weight ring of BOTH CTAs of a cluster as scratch
+      if (sg > 0) mbar_wait(epi_done, it & 1);
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NP, g1, c);
@@ -167,7 +182,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             uint8_t* dst = sW + stage * kPiece;
             mbar_expect_tx(w_full + stage, kPiece);
             // G1: W1 rows [256 c, +256) x k [64 pc, +64);  G2: W2 rows [0,256) x hidden k [128 c + 64 pc, +64)
-            const CUtensorMap* tm = g1 ? &tmW1 : &tmW2;
+            const CUtensorMap* tm = g1 ? (sg ? &tmW1b : &tmW1) : (sg ? &tmW2b : &tmW2);
             const int col = g1 ? pc * 64 : c * HC + pc * 64;
             const int row = g1 ? c * 256 : 0;
             if constexpr (CL == 1) {
@@ -181,6 +196,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -190,9 +206,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     uint32_t n_se = 0, n_hf0 = 0, n_hf1 = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
-      mbar_wait(a_full, it & 1);
-      tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
+      for (int sg = 0; sg < p.n_stages; ++sg) {
+      // input tile: from TMA (first module) or written by the first module's epilogue, which also left X / alpha in Y
+      if (sg == 0) mbar_wait(a_full, it & 1); else mbar_wait(a_ready, it & 1);
+      tc_fence_after();
+      const uint32_t y_acc0 = sg;                         // chained module: accumulate onto the parked residual
       // The issuing warp runs in lock-step with the tensor pipe (it accepts only a few MMAs ahead), so every cycle
       // between two issue blocks is an idle pipe cycle.  The job sequence is therefore written out without any per-job
       // decoding, and the barrier of the NEXT issue block (ring slot or S/H hand-over) is probed non-blockingly
@@ -253,7 +272,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
             const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc, (c | pc | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc, (y_acc0 | c | pc | k) != 0);
             if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
             if (pc == 1) {
               umma_commit(h_empty + b);
@@ -274,6 +293,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       }
       do_g2(NC - 2, 2, NC - 1, false);
       do_g2(NC - 1, 0, 0, true);
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
@@ -289,19 +309,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     int it = 0;
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       const int m0 = t * BM;
+      if (it > 0 && grp >= 2) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
+      for (int sg = 0; sg < p.n_stages; ++sg) {
+      const FfnStage& fs = p.st[sg];
       // ---- SiLU stage: S (chunk pair) -> H[0], H[1].  The b1 slice of the next pair is fetched into registers while
       //      this pair is being processed, so its L2 latency never sits between two pairs.
-      if (it > 0 && grp >= 2) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
       // et < kSiluCols: the hidden columns this warpgroup reads (kHalfCols of each 64-column half)
       const int bcol = (et / kHalfCols) * 64 + grp * kHalfCols + (et % kHalfCols);
       float b1_n0 = 0.f, b1_n1 = 0.f;
-      if (et < kSiluCols) { b1_n0 = __ldg(p.b1 + bcol); b1_n1 = __ldg(p.b1 + HC + bcol); }
+      if (et < kSiluCols) { b1_n0 = __ldg(fs.b1 + bcol); b1_n1 = __ldg(fs.b1 + HC + bcol); }
       for (int pr = 0; pr < NP; ++pr) {
         named_bar_sync(bar_id, 128);                      // the group has finished reading the previous pair's b1
         if (et < kSiluCols) {
           sb1[bcol] = b1_n0;
           sb1[HC + bcol] = b1_n1;
-          if (pr + 1 < NP) { b1_n0 = __ldg(p.b1 + (2 * pr + 2) * HC + bcol); b1_n1 = __ldg(p.b1 + (2 * pr + 3) * HC + bcol); }
+          if (pr + 1 < NP) { b1_n0 = __ldg(fs.b1 + (2 * pr + 2) * HC + bcol); b1_n1 = __ldg(fs.b1 + (2 * pr + 3) * HC + bcol); }
         }
         named_bar_sync(bar_id, 128);
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[2 * 64 + 2 * pr] = clock64();
@@ -347,20 +369,49 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + 2 * pr + b] = clock64();
         }
       }
-      // ---- final epilogue on Y: warpgroups 0 and 1 take 128 of the 256 columns each
+      // ---- epilogue on Y: warpgroups 0 and 1 take 128 of the 256 columns each
       if (grp < 2) {
-        mbar_wait(y_full, it & 1);
+        mbar_wait(y_full, (it * p.n_stages + sg) & 1);
         tc_fence_after();
-        // every MMA of the tile has retired: the input tile (-> parameters, group 1's staging ring) and the H buffers
-        // (-> group 0's ring) are dead
-        resid_stage_params<D, 256>(sparam, threadIdx.x - 128, p.b2, 0, p.ln_mode, p.g1, p.be1, p.g2, p.be2);
-        uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
-        if (elected) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
-        ResidParams rp{nullptr, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
-        resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
-                                        sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups, reinterpret_cast<float2*>(sA + 8192));
-        mbar_arrive(tile_done);
-        if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
+        const bool last = sg + 1 == p.n_stages;
+        ResidOpts ro;
+        ro.no_residual = sg > 0;                 // a chained module found X / alpha in its accumulator
+        if (last) {
+          // every MMA of the tile has retired: the input tile (-> parameters, group 1's staging ring) and the H buffers
+          // (-> group 0's ring) are dead
+          resid_stage_params<D, 256>(sparam, threadIdx.x - 128, fs.b2, 0, fs.ln_mode, fs.g1, fs.be1, fs.g2, fs.be2);
+          uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
+          if (elected && sg == 0) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+          ResidParams rp{nullptr, p.y_row_valid, fs.alpha, p.eps, fs.ln_mode, p.M};
+          resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
+                                          sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
+                                          reinterpret_cast<float2*>(sA + 8192), -1, -1, ro);
+          mbar_arrive(tile_done);
+          if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
+        } else {
+          // first module of a chain: X and y stay on chip.  y goes straight into the input tile sA (A operand of the
+          // next module), X / alpha_next stays in the accumulator columns, nothing is stored.  The idle weight ring
+          // (the producer waits for epi_done) provides the residual staging tiles and the parameter space.
+          float* cparam = reinterpret_cast<float*>(sW + 2 * kPiece);
+          resid_stage_params<D, 256>(cparam, threadIdx.x - 128, fs.b2, 0, fs.ln_mode, fs.g1, fs.be1, fs.g2, fs.be2);
+          uint8_t* ring = sW + grp * kPiece;
+          if (elected) resid_prefetch<D, 2, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+          ro.store_x = false;
+          ro.y_smem = sA;
+          ro.park_scale = 1.0f / p.st[sg + 1].alpha;
+          ResidParams rp{nullptr, nullptr, fs.alpha, p.eps, fs.ln_mode, p.M};
+          resid_ln_epilogue<D, 2, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
+                                          cparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
+                                          reinterpret_cast<float2*>(sW + 2 * kPiece + 8192), -1, -1, ro);
+          // (the epilogue ends with a 256-thread barrier: both groups are done with the ring and the parameters)
+          if (threadIdx.x == 128) {
+            if constexpr (CL == 1) mbar_arrive(epi_done);
+            else
+              for (uint32_t rk = 0; rk < CL; ++rk) mbar_arrive_cluster(mapa_u32(smem_u32(epi_done), rk));
+          }
+          mbar_arrive(a_ready);                  // y in sA (fenced), X / alpha parked in Y (tcgen05.wait::st done)
+        }
+      }
       }
     }
     if (elected) bulk_wait_all<0>();
@@ -389,9 +440,8 @@ bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, in
   return true;
 }
 
-int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
-              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
-              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
+static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n, float* X, int ldx, int M, int F,
+                      void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
   static int cl_env = -1;
   if (cl_env < 0) {
     const char* e = getenv("CFM_B200_FFN_CLUSTER");
@@ -400,25 +450,59 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
     CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   const int CL = cl_env;
-  CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
+  CUtensorMap tmA, tmW1[2], tmW2[2], tmX, tmY;
   int rc;
   if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW1, false, W1, F, D, D)) != 0) return rc;
-  if ((rc = make_2d_map(&tmW2, false, W2, D, F, F)) != 0) return rc;
+  for (int i = 0; i < n; ++i) {
+    if ((rc = make_2d_map(&tmW1[i], false, mods[i].W1, F, D, D)) != 0) return rc;
+    if ((rc = make_2d_map(&tmW2[i], false, mods[i].W2, D, F, F)) != 0) return rc;
+  }
+  if (n == 1) { tmW1[1] = tmW1[0]; tmW2[1] = tmW2[0]; }
   if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
   tmY = tmA;
-  if (ln_mode != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
-  FfnParams p{b1, b2, g1, be1, g2, be2, y_row_valid, alpha, eps, M, F, ln_mode, nullptr};
+  const int ln_last = mods[n - 1].g1 ? (mods[n - 1].g2 ? 2 : 1) : 0;
+  if (ln_last != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
+  FfnParams p;
+  for (int i = 0; i < 2; ++i) {
+    const FfnModule& m = mods[i < n ? i : n - 1];
+    p.st[i] = FfnStage{m.b1, m.b2, m.g1, m.be1, m.g2, m.be2, m.alpha, m.g1 ? (m.g2 ? 2 : 1) : 0};
+  }
+  p.n_stages = n; p.y_row_valid = y_row_valid; p.eps = eps; p.M = M; p.F = F; p.trace = nullptr;
   if (const char* e = getenv("CFM_B200_FFN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   const int m_tiles = ((M + BM - 1) / BM + CL - 1) / CL * CL;
   const int max_ctas = num_sms() / CL * CL;
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
   if (CL == 1)
-    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1[0], tmW2[0], tmW1[1],
+                           tmW2[1], tmX, tmX, tmY, p));
   else
-    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],
+                           tmW2[1], tmX, tmX, tmY, p));
   CFM_LAUNCHED();
   return 0;
+}
+
+int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
+              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
+              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
+  (void)ln_mode;
+  const FfnModule m{W1, b1, W2, b2, alpha, g1, be1, g2, be2};
+  return ffn_launch(y_in, ld_in, &m, 1, X, ldx, M, F, y_out, ld_out, y_row_valid, eps, st);
+}
+
+// Two modules on the same tiles, chained inside one kernel: the first one's X and y never leave the SM.
+bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule& a, const FfnModule& b) {
+  if (!ffn_fused_supported(d, d, d, M, d, F, dtype, 1)) return false;
+  if (a.g1 == nullptr) return false;                       // the second module's input is the first one's LayerNorm output
+  // X / alpha_next is parked in the accumulator: exact only for power-of-two alpha
+  int ex;
+  return b.alpha > 0.f && frexpf(b.alpha, &ex) == 0.5f;
+}
+
+int ffn_chain(const void* y_in, const FfnModule& a, const FfnModule& b, float* X, int M, int F, void* y_out,
+              const uint8_t* y_row_valid, float eps, cudaStream_t st) {
+  const FfnModule mods[2] = {a, b};
+  return ffn_launch(y_in, D, mods, 2, X, D, M, F, y_out, D, y_row_valid, eps, st);
 }
 
 }  // namespace cfm

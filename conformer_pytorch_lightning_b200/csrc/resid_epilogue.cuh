@@ -32,6 +32,15 @@ __device__ __forceinline__ void resid_tma_store(const CUtensorMap* tm, const voi
   if (z < 0) tma_store_2d(tm, src, c, m0); else tma_store_3d(tm, src, c, m0, z);
 }
 
+// Variations used when two feed-forward modules are chained inside one kernel (ffn_fused.cu):
+struct ResidOpts {
+  bool store_x = true;          // false: X is not written to global memory (it is consumed on chip)
+  uint8_t* y_smem = nullptr;    // != nullptr: y is written here as four [128 x 64] bf16 A-operand atoms instead of stored
+  float park_scale = 1.f;       // the X row left in the TMEM accumulator columns is multiplied by this (it becomes the
+                                // initial value of the next module's accumulator: X / alpha_next)
+  bool no_residual = false;     // the accumulator already contains the residual: v = alpha * (acc + bias)
+};
+
 struct ResidParams {
   const uint8_t* row_valid;     // rows whose GEMM result is forced to 0 (pad mask)
   const uint8_t* y_row_valid;   // rows of y forced to 0
@@ -76,7 +85,8 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
                                                   uint8_t* ring, uint64_t* res_bar, uint32_t& ring_phase,
                                                   const float* sparam, const CUtensorMap* tmX, const CUtensorMap* tmR,
                                                   const CUtensorMap* tmY, const ResidParams& p, int grp = 0, int xbar = 0,
-                                                  float2* xch = nullptr, int z = -1, int grow0 = -1) {
+                                                  float2* xch = nullptr, int z = -1, int grow0 = -1,
+                                                  const ResidOpts o = ResidOpts()) {
   constexpr int NCH = BN / 32 / NG;              // 32-column fp32 chunks per row handled by this group
   const int ch0 = grp * NCH;                     // first chunk of this group
   const int ln = p.ln_mode;
@@ -91,8 +101,13 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
   for (int c = 0; c < NCH; ++c) {
     const int b = c % R;
     uint8_t* buf = ring + b * kBufBytes;
-    mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
-    ring_phase ^= (1u << b);
+    if (!o.no_residual) {
+      mbar_wait(res_bar + b, (ring_phase >> b) & 1u);
+      ring_phase ^= (1u << b);
+    } else if (c >= R) {                         // no load orders the re-use of the buffer: wait for its last store
+      if (elected) bulk_wait_read<R - 1>();
+      named_bar_sync(bar_id, 128);
+    }
     uint32_t v[32];
     tmem_ld32(taddr + (ch0 + c) * 32, v);
     tmem_ld_wait();
@@ -100,32 +115,34 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
-      float4 x = *cell;
+      float4 x = o.no_residual ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
       x.x = fmaf(a, __uint_as_float(v[4 * j]) + bs[4 * j], x.x);
       x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], x.y);
       x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], x.z);
       x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], x.w);
       s1 += (x.x + x.y) + (x.z + x.w);
       s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-      v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
-      v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+      // ln 1: what stays parked is X itself (scaled for a chained module); ln 2: the pre-norm row, unscaled
+      const float ps = ln == 1 ? o.park_scale : 1.f;
+      v[4 * j] = __float_as_uint(x.x * ps); v[4 * j + 1] = __float_as_uint(x.y * ps);
+      v[4 * j + 2] = __float_as_uint(x.z * ps); v[4 * j + 3] = __float_as_uint(x.w * ps);
       if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
     }
-    if (ln != 0) tmem_st32(taddr + (ch0 + c) * 32, v);   // park the pre-norm row in our accumulator columns
+    if (ln != 0) tmem_st32(taddr + (ch0 + c) * 32, v);   // park the row in our accumulator columns
     fence_proxy_async_smem();
     named_bar_sync(bar_id, 128);
     if (elected) {
-      if (ln != 2) {
+      if (ln != 2 && o.store_x) {
         resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z);
         bulk_commit();
         // refill the PREVIOUS chunk's buffer once its store has finished reading it
-        if (c >= 1 && c - 1 + R < NCH) {
+        if (!o.no_residual && c >= 1 && c - 1 + R < NCH) {
           bulk_wait_read<1>();
           const int pb = (c - 1) % R;
           mbar_expect_tx(res_bar + pb, ROWS * 128);
           resid_tma_load(ring + pb * kBufBytes, tmR, res_bar + pb, n0 + (ch0 + c - 1 + R) * 32, m0, z);
         }
-      } else if (c + R < NCH) {                  // nothing is stored in pass 1: buffer b is free right away
+      } else if (!o.no_residual && c + R < NCH) {   // nothing is stored in pass 1: buffer b is free right away
         mbar_expect_tx(res_bar + b, ROWS * 128);
         resid_tma_load(buf, tmR, res_bar + b, n0 + (ch0 + c + R) * 32, m0, z);
       }
@@ -151,7 +168,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++nbuf) {
         uint8_t* buf = ring + (nbuf % R) * kBufBytes;
-        if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
+        if (o.store_x && nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
         uint32_t v[32];
         tmem_ld32(taddr + (ch0 + c) * 32, v);
         tmem_ld_wait();
@@ -166,14 +183,16 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
           x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g[4 * j + 3], be[4 * j + 3]);
           s1 += (x.x + x.y) + (x.z + x.w);
           s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-          v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
-          v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
-          *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
+          v[4 * j] = __float_as_uint(x.x * o.park_scale); v[4 * j + 1] = __float_as_uint(x.y * o.park_scale);
+          v[4 * j + 2] = __float_as_uint(x.z * o.park_scale); v[4 * j + 3] = __float_as_uint(x.w * o.park_scale);
+          if (o.store_x) *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
         }
         tmem_st32(taddr + (ch0 + c) * 32, v);
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (elected) { resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z); bulk_commit(); }
+        if (o.store_x) {
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (elected) { resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z); bulk_commit(); }
+        }
       }
       tmem_st_wait();
       if (NG == 2) {
@@ -189,10 +208,12 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     const float* g = sparam + (ln == 2 ? 3 * BN : BN);
     const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
     const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
+    const float unpark = 1.f / o.park_scale;     // exact: park_scale is a power of two (1 / alpha)
+    if (!o.store_x) nbuf = 0;                    // nothing of pass 2 went through the ring
 #pragma unroll 1
     for (int sub = grp * (BN / 64 / NG); sub < (grp + 1) * (BN / 64 / NG); ++sub, ++nbuf) {
-      uint8_t* buf = ring + (nbuf % R) * kBufBytes;
-      if (nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
+      uint8_t* buf = o.y_smem ? o.y_smem + sub * kBufBytes : ring + (nbuf % R) * kBufBytes;
+      if (!o.y_smem && nbuf >= R) { if (elected) bulk_wait_read<R - 1>(); named_bar_sync(bar_id, 128); }
       uint32_t v[64];
       {
         uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -207,15 +228,17 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int col = sub * 64 + 8 * j + e;
-          const float y = fmaf((__uint_as_float(v[8 * j + e]) - mean) * rstd, g[col], be[col]);
+          const float y = fmaf((__uint_as_float(v[8 * j + e]) * unpark - mean) * rstd, g[col], be[col]);
           f[e] = ykeep ? y : 0.f;
         }
         *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
             make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       }
       fence_proxy_async_smem();
-      named_bar_sync(bar_id, 128);
-      if (elected) { resid_tma_store(tmY, buf, sub * 64, m0, z); bulk_commit(); }
+      if (!o.y_smem) {
+        named_bar_sync(bar_id, 128);
+        if (elected) { resid_tma_store(tmY, buf, sub * 64, m0, z); bulk_commit(); }
+      }
     }
   }
   tc_fence_before();

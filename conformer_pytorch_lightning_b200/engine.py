@@ -297,13 +297,15 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
     attn_mask = _mask_u8(attn_mask)          # normalised once, not per layer
     new_caches = []
     out = x
+    ffm_done = False                         # the first feed-forward of layer i was already applied by layer i-1's chain
     for i, layer in enumerate(layers):
         Wl = layer.derived_weights(dtype)
         H = layer.self_attn.num_heads
         if i == 0:
             ops.layernorm(x, Wl["ffm_g"], Wl["ffm_b"], y=y)
         # every residual GEMM carries the LayerNorm that feeds the next module in its epilogue
-        ffn_into(x, y, Wl["ffm"], 0.5, ws, ln={"y": y, "g1": Wl["mha_g"], "b1": Wl["mha_b"]})
+        if not ffm_done:
+            ffn_into(x, y, Wl["ffm"], 0.5, ws, ln={"y": y, "g1": Wl["mha_g"], "b1": Wl["mha_b"]})
         cache = attn_caches[i] if attn_caches is not None else None
         new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws,
                                     ln={"y": y, "g1": Wl["conv_g"], "b1": Wl["conv_b"], "y_row_valid": row_valid}))
@@ -312,9 +314,18 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
                   ln={"y": y2, "g1": Wl["ff_g"], "b1": Wl["ff_b"]})
         if i + 1 < len(layers):
             Wn = layers[i + 1].derived_weights(dtype)
-            # norm_final of this layer chained with norm_ff_macaron of the next one
-            ffn_into(x, y2, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
-                                                   "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})
+            # this layer's second feed-forward (+ norm_final chained with norm_ff_macaron of the next layer) and the next
+            # layer's first feed-forward (+ its attention LayerNorm) act on the same rows: one library call, one kernel
+            # on the tcgen05 engine (the residual stream and the LayerNorm output in between stay on chip)
+            ffm_done = Wl["ff"]["w1"].shape == Wn["ffm"]["w1"].shape
+            if ffm_done:
+                a = dict(Wl["ff"], alpha=0.5, g1=Wl["fin_g"], be1=Wl["fin_b"], g2=Wn["ffm_g"], be2=Wn["ffm_b"])
+                b = dict(Wn["ffm"], alpha=0.5, g1=Wn["mha_g"], be1=Wn["mha_b"])
+                h = ws.get("ffn_h", (n, a["w1"].shape[0]), y.dtype, dev)
+                ops.ffn_chain(y2, a, b, x, y, hidden_ws=h)
+            else:
+                ffn_into(x, y2, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
+                                                       "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})
         else:
             ffn_into(x, y2, Wl["ff"], 0.5, ws)
             if after_norm is not None:

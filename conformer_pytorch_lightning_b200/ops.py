@@ -124,6 +124,30 @@ def conv_module(y_in, w1, b1, dw_w, dw_b, w2, b2, x, B, T, *, row_valid=None, ln
                                     _ptr(glu_ws), _ptr(dw_ws), engine, _stream(x)))
 
 
+def ffn_chain(y_in, a, b, x, y_out, *, y_row_valid=None, hidden_ws=None, engine=N.ENGINE_AUTO):
+    """Two feed-forward modules back to back on the same rows (see cfm_ffn_chain).  a, b: dicts with w1, b1, w2, b2,
+    alpha, g1, be1 and optionally g2, be2; module a's LayerNorm output is module b's input."""
+    _req(y_in, "ffn_chain.y_in")
+    _req(x, "ffn_chain.x", torch.float32)
+    _req(y_out, "ffn_chain.y_out", y_in.dtype)
+    M, d = y_in.shape
+    F = a["w1"].shape[0]
+    for m in (a, b):
+        _req(m["w1"], "ffn_chain.w1", y_in.dtype)
+        _req(m["w2"], "ffn_chain.w2", y_in.dtype)
+        if m["w1"].shape != (F, d) or m["w2"].shape != (d, F):
+            raise RuntimeError("ffn_chain: both modules must have the same (F, d)")
+    if x.shape != (M, d) or y_out.shape != (M, d):
+        raise RuntimeError("ffn_chain: shape mismatch")
+
+    def mod(m):
+        return [m["w1"].data_ptr(), m["b1"].data_ptr(), m["w2"].data_ptr(), m["b2"].data_ptr(), float(m["alpha"]),
+                _ptr(m.get("g1")), _ptr(m.get("be1")), _ptr(m.get("g2")), _ptr(m.get("be2"))]
+    ensure_init(x)
+    N.check(N.lib().cfm_ffn_chain(y_in.data_ptr(), M, d, F, _DT[y_in.dtype], *mod(a), *mod(b), x.data_ptr(), y_out.data_ptr(),
+                                  _ptr(y_row_valid), 1e-5, _ptr(hidden_ws), engine, _stream(x)))
+
+
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
     """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
     mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""

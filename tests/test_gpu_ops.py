@@ -350,6 +350,53 @@ def test_ffn_fused_tcgen05(M, F, mode):
         assert rel_err(x, x_ref) < 2e-3 and rel_err(yio.float(), y_ref) < 8e-3
 
 
+@pytest.mark.parametrize("M,F", [(128, 2048), (333, 2048), (15872, 2048), (200, 256), (20000, 512)])
+@pytest.mark.parametrize("a_mode", [1, 2])
+def test_ffn_chain_tcgen05(M, F, a_mode):
+    """Two feed-forward modules chained in one kernel (X and the LayerNorm output in between stay on chip) vs the two
+    cfm_ffn calls they replace and vs fp32 torch."""
+    dt, d = torch.bfloat16, 256
+    yin = rnd(M, d, dtype=dt)
+    mods = []
+    for i in range(2):
+        mods.append({"w1": rnd(F, d, dtype=dt, scale=1 / 16, seed=10 * i + 1), "b1": rnd(F, seed=10 * i + 2) * 0.5,
+                     "w2": rnd(d, F, dtype=dt, scale=1 / math.sqrt(F), seed=10 * i + 3), "b2": rnd(d, seed=10 * i + 4) * 0.5,
+                     "alpha": 0.5, "g1": rnd(d, seed=10 * i + 5) * 0.1 + 1, "be1": rnd(d, seed=10 * i + 6) * 0.1})
+    if a_mode == 2:
+        mods[0].update(g2=rnd(d, seed=7) * 0.1 + 1, be2=rnd(d, seed=8) * 0.1)
+    x0 = rnd(M, d, seed=9, scale=2.0)
+    yv = (torch.arange(M, device=DEV) % 5 != 2).to(torch.uint8)
+    Fn = torch.nn.functional
+
+    def ref_mod(y, x, m, mode):
+        h = Fn.silu(y.float() @ m["w1"].float().t() + m["b1"]).to(dt).float()
+        v = x + 0.5 * (h @ m["w2"].float().t() + m["b2"])
+        if mode == 1:
+            return v, Fn.layer_norm(v, (d,), m["g1"], m["be1"], 1e-5)
+        xn = Fn.layer_norm(v, (d,), m["g1"], m["be1"], 1e-5)
+        return xn, Fn.layer_norm(xn, (d,), m["g2"], m["be2"], 1e-5)
+    x1, y1 = ref_mod(yin, x0, mods[0], a_mode)
+    x_ref, y_ref = ref_mod(y1.to(dt), x1, mods[1], 1)
+    y_ref = y_ref * yv[:, None]
+    res = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_SIMT):
+        x = x0.clone()
+        y = torch.full((M, d), float("nan"), dtype=dt, device=DEV)
+        hws = torch.empty(M, F, dtype=dt, device=DEV)
+        ops.ffn_chain(yin, mods[0], mods[1], x, y, y_row_valid=yv, hidden_ws=hws, engine=eng)
+        assert torch.isfinite(x).all()
+        assert rel_err(x, x_ref) < 4e-3, (eng, rel_err(x, x_ref))
+        assert rel_err(y.float(), y_ref) < 1e-2, (eng, rel_err(y.float(), y_ref))
+        assert float(y.float()[yv == 0].abs().max()) == 0.0
+        res[eng] = x
+    assert rel_err(res[N.ENGINE_TC], res[N.ENGINE_SIMT]) < 4e-3
+    # in place on the LayerNorm buffer (how the layer chain uses it)
+    x = x0.clone()
+    yio = yin.clone()
+    ops.ffn_chain(yio, mods[0], mods[1], x, yio, y_row_valid=yv, engine=N.ENGINE_TC)
+    assert rel_err(x, x_ref) < 4e-3 and rel_err(yio.float(), y_ref) < 1e-2
+
+
 @pytest.mark.parametrize("B,T", [(1, 64), (2, 128), (3, 129), (64, 248), (5, 256), (2, 100)])
 @pytest.mark.parametrize("mask_kind", ["none", "pad", "full"])
 @pytest.mark.parametrize("with_ln", [False, True])

@@ -99,6 +99,10 @@ def ffn_bench(M=15872, d=256, F=2048):
                         ops.gemm_ln(h, w2, b2, x, y, alpha=0.5, g1=ln["g1"], b1=ln["b1"], g2=ln.get("g2"), b2=ln.get("b2"))
             t = timeit(fn)
             print(f"ffn {name:10s} {mode:6s} M={M} F={F}: {t:7.1f} us ({fl / t / 1e6:7.1f} TF/s)")
+    a = {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "alpha": 0.5, "g1": g, "be1": b, "g2": g, "be2": b}
+    bm = {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "alpha": 0.5, "g1": g, "be1": b}
+    t = timeit(lambda: ops.ffn_chain(y, a, bm, x, y, engine=N.ENGINE_TC))
+    print(f"ffn chain (2xLN module + LN module in one kernel): {t:7.1f} us ({2 * fl / t / 1e6:7.1f} TF/s)")
 
 
 def conv_bench(B=64, T=248, d=256, k=15):
