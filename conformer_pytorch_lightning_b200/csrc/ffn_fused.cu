@@ -116,8 +116,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
   uint64_t* res_bar = tile_done + 1;          // [2 groups][4]
   uint64_t* a_ready = res_bar + 8;            // [1]  chain: y of the first module written into sA (256 arrivals)
-  uint64_t* epi_done = a_ready + 1;           // [1]  chain: first module's epilogue no longer uses the weight ring (CL arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
@@ -144,7 +143,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     mbar_init(y_full, 1);
     mbar_init(tile_done, 256);
     for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
-    mbar_init(a_ready, 256); mbar_init(epi_done, CL);
+    mbar_init(a_ready, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -170,8 +169,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       }
       __syncwarp();
       for (int sg = 0; sg < p.n_stages; ++sg) {
-      // chain: the first module's epilogue borrows the (then idle) weight ring of BOTH CTAs of a cluster as scratch
-      if (sg > 0) mbar_wait(epi_done, it & 1);
       for (int jx = 0; jx < n_jobs; ++jx) {
         bool g1; int c;
         job_of(jx, NP, g1, c);
@@ -330,6 +327,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         mbar_wait(s_full, n_sf & 1);                      // S holds both chunks of the pair
         ++n_sf;
         tc_fence_after();
+        // chain: the last G1 of the first module has retired, so the input tile is dead: start fetching the residual
+        // rows of its epilogue into it now (2 x 16 KB per warpgroup), while the remaining G2 jobs run
+        if (pr == NP - 1 && sg + 1 < p.n_stages && elected && grp < 2)
+          resid_prefetch<D, 2, 128, 2>(sA + grp * 2 * kBufBytes, res_bar + grp * 4, &tmR, 0, m0, grp);
         if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[3 * 64 + 2 * pr] = clock64();
         // S is read out completely first so that the next pair's G1 can start; v[b][half] = this warpgroup's kHalfCols
         // columns of 64-column half `half` (= k atom of G2) of chunk 2 pr + b
@@ -390,25 +391,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
         } else {
           // first module of a chain: X and y stay on chip.  y goes straight into the input tile sA (A operand of the
-          // next module), X / alpha_next stays in the accumulator columns, nothing is stored.  The idle weight ring
-          // (the producer waits for epi_done) provides the residual staging tiles and the parameter space.
-          float* cparam = reinterpret_cast<float*>(sW + 2 * kPiece);
+          // next module), X / alpha_next stays in the accumulator columns, nothing is stored.  The residual rows arrive
+          // in sA (each warpgroup's half; prefetch issued in the SiLU loop above) and are overwritten by y afterwards;
+          // the parameters sit in the dead H buffers, so the weight ring keeps prefetching the next module's pieces.
+          float* cparam = reinterpret_cast<float*>(sH);
           resid_stage_params<D, 256>(cparam, threadIdx.x - 128, fs.b2, 0, fs.ln_mode, fs.g1, fs.be1, fs.g2, fs.be2);
-          uint8_t* ring = sW + grp * kPiece;
-          if (elected) resid_prefetch<D, 2, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+          uint8_t* ring = sA + grp * 2 * kBufBytes;
           ro.store_x = false;
           ro.y_smem = sA;
           ro.park_scale = 1.0f / p.st[sg + 1].alpha;
           ResidParams rp{nullptr, nullptr, fs.alpha, p.eps, fs.ln_mode, p.M};
           resid_ln_epilogue<D, 2, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
                                           cparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
-                                          reinterpret_cast<float2*>(sW + 2 * kPiece + 8192), -1, -1, ro);
+                                          reinterpret_cast<float2*>(sH + 8192), -1, -1, ro);
           // (the epilogue ends with a 256-thread barrier: both groups are done with the ring and the parameters)
-          if (threadIdx.x == 128) {
-            if constexpr (CL == 1) mbar_arrive(epi_done);
-            else
-              for (uint32_t rk = 0; rk < CL; ++rk) mbar_arrive_cluster(mapa_u32(smem_u32(epi_done), rk));
-          }
           mbar_arrive(a_ready);                  // y in sA (fenced), X / alpha parked in Y (tcgen05.wait::st done)
         }
       }
