@@ -292,7 +292,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
       if (tid == 0) CONV_STAMP(14);
       if (t + (int)gridDim.x < n_tiles) mbar_wait(tile_done, it & 1);   // sb1 / sY / sG are re-used by the next tile
     }
-    if (elected) bulk_wait_all<0>();
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
   tc_fence_before();
   __syncthreads();

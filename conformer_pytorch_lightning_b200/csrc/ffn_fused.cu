@@ -410,7 +410,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       }
       }
     }
-    if (elected) bulk_wait_all<0>();
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
 
   tc_fence_before();

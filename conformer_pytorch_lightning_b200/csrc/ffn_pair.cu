@@ -272,7 +272,7 @@ ffn_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16,
         mbar_arrive_cluster(pair_done_ldr);
       }
     }
-    if (elected) bulk_wait_all<0>();
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
 
   tc_fence_before();

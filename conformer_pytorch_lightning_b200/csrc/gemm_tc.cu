@@ -301,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive(tempty_bar + acc);
       }
     }
-    if (elected) bulk_wait_all<0>();                   // all bulk stores complete before the CTA retires
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
 
   tc_fence_before();

@@ -46,6 +46,8 @@ struct MhsaParams {
   float scale_log2, eps;
   int B, T, ln_mode, mask_aligned8;
   long long* trace;
+  unsigned long long* gtrace;   // optional [launch][cta][4] %globaltimer stamps (tools/launch_timeline.py)
+  int gslot;
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -76,6 +78,13 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8)
 }
 
 #define MTR(i) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 3) p.trace[i] = clock64(); } while (0)
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GTR(i) do { if (p.gtrace && threadIdx.x == 0) \
+  p.gtrace[((size_t)p.gslot * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 4 + (i)] = gtimer(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -86,6 +95,7 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   const __grid_constant__ CUtensorMap tmY,      // y out (256, T, B) bf16, box 64 x 128 x 1
                   const MhsaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  GTR(0);
   uint8_t* sStage = smem;                       // 2 x {Q 16 KB, K 32 KB, V 32 KB}; later W_o pieces, staging rings, parameters
   uint8_t* sP = smem + 2 * kStage;              // P tile -> ctx tile
   float* xch_m = reinterpret_cast<float*>(sP + kPBytes);        // [2][128] partial row maxima
@@ -123,7 +133,9 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  GTR(1);
   pdl_wait();
+  GTR(2);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
 
@@ -356,10 +368,11 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                    &tmX, &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sStage + kStage + 8192), b,
                                    b * p.T + i0);
     if (tid == 0) MTR(27);
-    if (elected) bulk_wait_all<0>();
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
+  GTR(3);
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
@@ -419,7 +432,12 @@ int mhsa_fused(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t
   p.scale_log2 = scale * 1.4426950408889634f; p.eps = eps;
   p.B = B; p.T = T; p.ln_mode = g1 ? 1 : 0;
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
-  p.trace = nullptr;
+  p.trace = nullptr; p.gtrace = nullptr; p.gslot = 0;
+  if (const char* e = getenv("CFM_B200_MHSA_GTRACE_PTR")) {
+    static int slot = 0;
+    p.gtrace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+    p.gslot = slot++ % 64;
+  }
   if (const char* e = getenv("CFM_B200_MHSA_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   dim3 grid((T + QT - 1) / QT, B);
   CFM_CUDA_OK(launch_pdl(mhsa_fused_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, tmWo, tmX, tmX, tmY, p));

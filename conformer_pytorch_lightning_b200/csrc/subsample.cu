@@ -261,7 +261,7 @@ subsample_conv2_kernel(const __grid_constant__ CUtensorMap tmP,   // P as (C, F1
       tc_fence_before();
       mbar_arrive(tempty_bar + acc);
     }
-    if (elected) bulk_wait_all<0>();
+    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
