@@ -41,7 +41,7 @@ def _declare(lib):
     lib.cfm_gemm_ln.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _f, _i, _p]
     lib.cfm_ffn.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p, _f, _p, _i, _p]
     lib.cfm_ffn_chain.argtypes = ([_p, _i, _i, _i, _i] + [_p, _p, _p, _p, _f, _p, _p, _p, _p] * 2 +
-                                  [_p, _p, _p, _f, _p, _i, _p])
+                                  [_p, _p, _p, _p, _p, _p, _i, _f, _p, _i, _p])
     lib.cfm_mhsa_out.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _f,
                                  _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p]
     lib.cfm_conv_module.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]

@@ -194,13 +194,17 @@ extern "C" int cfm_ffn_chain(const void* y, int M, int d, int F, int dtype, cons
                              const float* b2a, float alpha_a, const float* g1a, const float* be1a, const float* g2a,
                              const float* be2a, const void* W1b, const float* b1b, const void* W2b, const float* b2b,
                              float alpha_b, const float* g1b, const float* be1b, const float* g2b, const float* be2b, float* X,
-                             void* Y, const uint8_t* y_row_valid, float eps, void* hidden_ws, int engine, void* stream) {
+                             void* Y, const uint8_t* y_row_valid, const void* Wp, const float* bp, void* P, int Np, float eps,
+                             void* hidden_ws, int engine, void* stream) {
   using namespace cfm;
-  CFM_CHECK_ARG(y && W1a && b1a && W2a && b2a && W1b && b1b && W2b && b2b && X && Y, "cfm_ffn_chain: null pointer");
-  CFM_CHECK_ARG(g1a != nullptr && be1a != nullptr, "cfm_ffn_chain: the first module needs a LayerNorm (its output feeds the second)");
+  const bool has_a = W1a != nullptr;
+  CFM_CHECK_ARG(y && W1b && b1b && W2b && b2b && X && Y, "cfm_ffn_chain: null pointer");
+  CFM_CHECK_ARG(!has_a || (b1a && W2a && b2a && g1a && be1a),
+                "cfm_ffn_chain: the first module needs all its tensors and a LayerNorm (its output feeds the second)");
+  CFM_CHECK_ARG((Wp == nullptr) || (bp && P && Np > 0 && g1b), "cfm_ffn_chain: projection needs bp, P, Np and a final LayerNorm");
   CFM_CHECK_ARG(M >= 0 && d > 0 && F > 0, "cfm_ffn_chain: bad shape");
   if (M == 0) return 0;
-  // CFM_B200_FFN_CHAIN=0: always two cfm_ffn calls
+  // CFM_B200_FFN_CHAIN=0: always separate cfm_ffn / cfm_gemm calls
   static int chain_off = -1;
   if (chain_off < 0) {
     const char* e = getenv("CFM_B200_FFN_CHAIN");
@@ -208,15 +212,22 @@ extern "C" int cfm_ffn_chain(const void* y, int M, int d, int F, int dtype, cons
   }
   const FfnModule a{W1a, b1a, W2a, b2a, alpha_a, g1a, be1a, g2a, be2a};
   const FfnModule b{W1b, b1b, W2b, b2b, alpha_b, g1b, be1b, g2b, be2b};
-  const bool ok = (dtype == CFM_BF16) && ffn_chain_supported(M, d, F, dtype, a, b);
-  if (engine == CFM_ENGINE_TC) CFM_CHECK_ARG(ok, "cfm_ffn_chain: chained tcgen05 path does not support M=%d d=%d F=%d", M, d, F);
+  const bool ok = (dtype == CFM_BF16) && ffn_chain_supported(M, d, F, dtype, has_a ? &a : nullptr, b, Wp ? Np : 0);
+  if (engine == CFM_ENGINE_TC) CFM_CHECK_ARG(ok, "cfm_ffn_chain: chained tcgen05 path does not support M=%d d=%d F=%d Np=%d", M, d, F, Np);
   if (ok && (engine == CFM_ENGINE_TC || (engine == CFM_ENGINE_AUTO && !chain_off)))
-    return ffn_chain(y, a, b, X, M, F, Y, y_row_valid, eps, (cudaStream_t)stream);
-  int rc = cfm_ffn(y, d, W1a, b1a, W2a, b2a, X, d, M, d, F, dtype, alpha_a, g1a, be1a, g2a, be2a, Y, d, nullptr, eps, hidden_ws,
-                   engine, stream);
-  if (rc != 0) return rc;
-  return cfm_ffn(Y, d, W1b, b1b, W2b, b2b, X, d, M, d, F, dtype, alpha_b, g1b, be1b, g2b, be2b, Y, d, y_row_valid, eps, hidden_ws,
+    return ffn_chain(y, has_a ? &a : nullptr, b, X, M, F, Y, y_row_valid, eps, Wp, bp, P, Np, (cudaStream_t)stream);
+  int rc = 0;
+  const void* yb = y;
+  if (has_a) {
+    rc = cfm_ffn(y, d, W1a, b1a, W2a, b2a, X, d, M, d, F, dtype, alpha_a, g1a, be1a, g2a, be2a, Y, d, nullptr, eps, hidden_ws,
                  engine, stream);
+    if (rc != 0) return rc;
+    yb = Y;
+  }
+  rc = cfm_ffn(yb, d, W1b, b1b, W2b, b2b, X, d, M, d, F, dtype, alpha_b, g1b, be1b, g2b, be2b, Y, d, y_row_valid, eps, hidden_ws,
+               engine, stream);
+  if (rc != 0 || Wp == nullptr) return rc;
+  return cfm_gemm(Y, d, Wp, bp, P, Np, M, Np, d, dtype, CFM_EPI_BIAS, nullptr, 1.f, nullptr, engine, stream);
 }
 
 extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts,

@@ -185,9 +185,9 @@ struct FfnModule {               // one PositionwiseFeedForwardModule + the Laye
   float alpha;
   const float* g1; const float* be1; const float* g2; const float* be2;
 };
-bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule& a, const FfnModule& b);
-int ffn_chain(const void* y_in, const FfnModule& a, const FfnModule& b, float* X, int M, int F, void* y_out,
-              const uint8_t* y_row_valid, float eps, cudaStream_t st);
+bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule* a, const FfnModule& b, int Np);
+int ffn_chain(const void* y_in, const FfnModule* a, const FfnModule& b, float* X, int M, int F, void* y_out,
+              const uint8_t* y_row_valid, float eps, const void* Wp, const float* bp, void* P, int Np, cudaStream_t st);
 int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st);

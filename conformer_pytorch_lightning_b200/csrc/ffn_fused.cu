@@ -62,6 +62,8 @@ struct FfnParams {
   FfnStage st[2];
   int n_stages;                    // 2: two modules chained on the same tile (X and y of the first stay on chip)
   const uint8_t* y_row_valid;      // row mask of the LAST stage's y
+  const float* bp;                 // projection tail: P = y_last . Wp^T + bp (the QKV projection), NP256 blocks of 256 columns
+  int np_blocks;                   // 0: no projection
   float eps;
   int M, F;
   long long* trace;   // optional per-event clock64 timestamps of CTA 0 (tools/ffn_trace.py); nullptr in production
@@ -94,6 +96,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
                  const __grid_constant__ CUtensorMap tmX,    // X  (M, 256) fp32 store, box 32 x 128
                  const __grid_constant__ CUtensorMap tmR,    // residual load (same tensor as X)
                  const __grid_constant__ CUtensorMap tmY,    // y out (M, 256) bf16 store, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmWp,   // projection weight (Np, 256) bf16, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmP,    // projection output (M, Np) bf16 store, box 64 x 128
                  const FfnParams p) {
   // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
   // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
@@ -116,7 +120,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* tile_done = y_full + 1;           // [1]  final epilogue of the tile finished (256 arrivals)
   uint64_t* res_bar = tile_done + 1;          // [2 groups][4]
   uint64_t* a_ready = res_bar + 8;            // [1]  chain: y of the first module written into sA (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint64_t* y_ready = a_ready + 1;            // [1]  projection tail: y of the last module written into sH (256 arrivals)
+  uint64_t* q_full = y_ready + 1;             // [2]  projection accumulator complete (MMA commit)
+  uint64_t* q_empty = q_full + 2;             // [2]  projection accumulator read out (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
@@ -132,6 +139,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
     prefetch_tmap(&tmX); prefetch_tmap(&tmR); prefetch_tmap(&tmY);
     if (p.n_stages > 1) { prefetch_tmap(&tmW1b); prefetch_tmap(&tmW2b); }
+    if (p.np_blocks > 0) { prefetch_tmap(&tmWp); prefetch_tmap(&tmP); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
@@ -143,7 +151,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     mbar_init(y_full, 1);
     mbar_init(tile_done, 256);
     for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
-    mbar_init(a_ready, 256);
+    mbar_init(a_ready, 256); mbar_init(y_ready, 256);
+    for (int s = 0; s < 2; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -194,6 +203,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         }
       }
       }
+      // projection tail: Wp rows [256 blk, +256) x k [64 kc, +64)
+      for (int pc = 0; pc < 4 * p.np_blocks; ++pc) {
+        mbar_wait(w_empty + stage, phase ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = sW + stage * kPiece;
+          mbar_expect_tx(w_full + stage, kPiece);
+          const int col = (pc & 3) * 64, row = (pc >> 2) * 256;
+          if constexpr (CL == 1) {
+            tma_load_2d(dst, &tmWp, w_full + stage, col, row);
+            tma_load_2d(dst + kAtom, &tmWp, w_full + stage, col, row + 128);
+          } else {
+            tma_load_2d_mc(dst + crank * kAtom, &tmWp, w_full + stage, col, row + crank * 128, kMask);
+          }
+        }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -204,6 +230,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
+      bool job_ready = false;           // the next job's S/H barrier was already seen complete
+      auto next_slot_probe = [&]() {
+        const int ns = (stage + 1 == NST) ? 0 : stage + 1;
+        have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
+      };
+      auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
       for (int sg = 0; sg < p.n_stages; ++sg) {
       // input tile: from TMA (first module) or written by the first module's epilogue, which also left X / alpha in Y
       if (sg == 0) mbar_wait(a_full, it & 1); else mbar_wait(a_ready, it & 1);
@@ -213,12 +245,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       // between two issue blocks is an idle pipe cycle.  The job sequence is therefore written out without any per-job
       // decoding, and the barrier of the NEXT issue block (ring slot or S/H hand-over) is probed non-blockingly
       // before the current block's MMAs are issued.
-      bool job_ready = false;           // the next job's S/H barrier was already seen complete
-      auto next_slot_probe = [&]() {
-        const int ns = (stage + 1 == NST) ? 0 : stage + 1;
-        have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
-      };
-      auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
       // probe used while issuing the last piece of a job: is the barrier of the following job complete?
       auto probe_g1 = [&]() { return mbar_test(s_empty, (n_se & 1) ^ 1); };
       auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + 2 * b, (b ? n_hf1 : n_hf0) & 1); };
@@ -290,6 +316,31 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       }
       do_g2(NC - 2, 2, NC - 1, false);
       do_g2(NC - 1, 0, 0, true);
+      }
+      // projection tail: P_blk = y . Wp_blk^T, accumulators alternate between the S and the Y columns
+      if (p.np_blocks > 0) {
+        mbar_wait(y_ready, it & 1);                       // y of the last module is in sH, the Y columns are dead
+        tc_fence_after();
+        for (int blk = 0; blk < p.np_blocks; ++blk) {
+          const int ab = blk & 1;
+          // accumulator `ab` is used by blocks ab, ab+2, ...: wait until the epilogue has read out block blk-2
+          if (blk >= 2) { mbar_wait(q_empty + ab, (it * ((p.np_blocks + 1 - ab) >> 1) + (blk >> 1) - 1) & 1); tc_fence_after(); }
+          for (int kc = 0; kc < 4; ++kc) {
+            if (!have) mbar_wait(w_full + stage, phase);
+            tc_fence_after();
+            next_slot_probe();
+            if (elect_one()) {
+              const uint64_t da = umma_desc_sw128(h_addr + kc * kAtom);
+              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(ab ? tmem_y : tmem_base, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
+              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+              if (kc == 3) umma_commit(q_full + ab);
+            }
+            __syncwarp();
+            advance();
+          }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -383,10 +434,58 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           resid_stage_params<D, 256>(sparam, threadIdx.x - 128, fs.b2, 0, fs.ln_mode, fs.g1, fs.be1, fs.g2, fs.be2);
           uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
           if (elected && sg == 0) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
+          if (p.np_blocks > 0) ro.y_smem = sH;             // y is only consumed by the projection tail: not stored
           ResidParams rp{nullptr, p.y_row_valid, fs.alpha, p.eps, fs.ln_mode, p.M};
           resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
                                           sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
                                           reinterpret_cast<float2*>(sA + 8192), -1, -1, ro);
+          if (p.np_blocks > 0) {
+            // ---- projection tail (the QKV projection of the attention block that follows): y sits in sH as the A
+            //      operand; each warpgroup turns 128 of a block's 256 accumulator columns into bf16 (+ bias) and
+            //      stores them through two staging tiles in the dead input tile
+            mbar_arrive(y_ready);
+            int sub_cnt = 0;
+            for (int blk = 0; blk < p.np_blocks; ++blk) {
+              const int ab = blk & 1;
+              named_bar_sync(1 + kSiluGroups, 256);          // everybody is done with the previous block's bias
+              sb1[threadIdx.x - 128] = __ldg(p.bp + blk * 256 + (threadIdx.x - 128));
+              named_bar_sync(1 + kSiluGroups, 256);
+              mbar_wait(q_full + ab, (it * ((p.np_blocks + 1 - ab) >> 1) + (blk >> 1)) & 1);
+              tc_fence_after();
+              const uint32_t tacc = (ab ? tmem_y : tmem_base) + lane_base;
+#pragma unroll 1
+              for (int ss = 0; ss < 2; ++ss, ++sub_cnt) {
+                const int sub = grp * 2 + ss;                  // 64-column sub-tile of the block owned by this warpgroup
+                uint8_t* buf = sA + (grp * 2 + (sub_cnt & 1)) * kBufBytes;
+                if (elected) bulk_wait_read<1>();              // the store issued two sub-tiles ago has left this buffer
+                named_bar_sync(bar_id, 128);
+                uint32_t v[64];
+                {
+                  uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+                  uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+                  tmem_ld32(tacc + sub * 64, v0);
+                  tmem_ld32(tacc + sub * 64 + 32, v1);
+                }
+                tmem_ld_wait();
+                const float* bs = sb1 + sub * 64;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float f[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]) + bs[8 * j + e];
+                  *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =
+                      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (elected) { tma_store_2d(&tmP, buf, blk * 256 + sub * 64, m0); bulk_commit(); }
+              }
+              tc_fence_before();
+              mbar_arrive(q_empty + ab);
+            }
+            if (elected) bulk_wait_read<0>();                  // the staging tiles are free before the next tile's input lands
+            named_bar_sync(bar_id, 128);
+          }
           mbar_arrive(tile_done);
           if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
         } else {
@@ -437,7 +536,8 @@ bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, in
 }
 
 static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n, float* X, int ldx, int M, int F,
-                      void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
+                      void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st,
+                      const void* Wp = nullptr, const float* bp = nullptr, void* P = nullptr, int Np = 0) {
   static int cl_env = -1;
   if (cl_env < 0) {
     const char* e = getenv("CFM_B200_FFN_CLUSTER");
@@ -457,8 +557,14 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
   tmY = tmA;
   const int ln_last = mods[n - 1].g1 ? (mods[n - 1].g2 ? 2 : 1) : 0;
-  if (ln_last != 0 && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
+  if (ln_last != 0 && Wp == nullptr && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
+  CUtensorMap tmWp = tmW1[0], tmP = tmA;
+  if (Wp != nullptr) {
+    if ((rc = make_2d_map(&tmWp, false, Wp, Np, D, D)) != 0) return rc;
+    if ((rc = make_2d_map(&tmP, false, P, M, Np, Np)) != 0) return rc;
+  }
   FfnParams p;
+  p.bp = bp; p.np_blocks = Wp ? Np / 256 : 0;
   for (int i = 0; i < 2; ++i) {
     const FfnModule& m = mods[i < n ? i : n - 1];
     p.st[i] = FfnStage{m.b1, m.b2, m.g1, m.be1, m.g2, m.be2, m.alpha, m.g1 ? (m.g2 ? 2 : 1) : 0};
@@ -470,10 +576,10 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
   if (CL == 1)
     CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1[0], tmW2[0], tmW1[1],
-                           tmW2[1], tmX, tmX, tmY, p));
+                           tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   else
     CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],
-                           tmW2[1], tmX, tmX, tmY, p));
+                           tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   CFM_LAUNCHED();
   return 0;
 }
@@ -486,19 +592,28 @@ int ffn_fused(const void* y_in, int ld_in, const void* W1, const float* b1, cons
   return ffn_launch(y_in, ld_in, &m, 1, X, ldx, M, F, y_out, ld_out, y_row_valid, eps, st);
 }
 
-// Two modules on the same tiles, chained inside one kernel: the first one's X and y never leave the SM.
-bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule& a, const FfnModule& b) {
+// Two modules on the same tiles, chained inside one kernel: the first one's X and y never leave the SM.  `a` may be
+// null (single module).  With a projection (Wp != null) the last module's LayerNorm output is consumed on chip by
+// P = y Wp^T + bp and not stored.
+bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule* a, const FfnModule& b, int Np) {
   if (!ffn_fused_supported(d, d, d, M, d, F, dtype, 1)) return false;
-  if (a.g1 == nullptr) return false;                       // the second module's input is the first one's LayerNorm output
-  // X / alpha_next is parked in the accumulator: exact only for power-of-two alpha
-  int ex;
-  return b.alpha > 0.f && frexpf(b.alpha, &ex) == 0.5f;
+  if (a != nullptr) {
+    if (a->g1 == nullptr) return false;                    // the second module's input is the first one's LayerNorm output
+    // X / alpha_next is parked in the accumulator: exact only for power-of-two alpha
+    int ex;
+    if (!(b.alpha > 0.f) || frexpf(b.alpha, &ex) != 0.5f) return false;
+  }
+  if (Np != 0 && (Np % 256 != 0 || b.g1 == nullptr || b.g2 != nullptr)) return false;
+  return true;
 }
 
-int ffn_chain(const void* y_in, const FfnModule& a, const FfnModule& b, float* X, int M, int F, void* y_out,
-              const uint8_t* y_row_valid, float eps, cudaStream_t st) {
-  const FfnModule mods[2] = {a, b};
-  return ffn_launch(y_in, D, mods, 2, X, D, M, F, y_out, D, y_row_valid, eps, st);
+int ffn_chain(const void* y_in, const FfnModule* a, const FfnModule& b, float* X, int M, int F, void* y_out,
+              const uint8_t* y_row_valid, float eps, const void* Wp, const float* bp, void* P, int Np, cudaStream_t st) {
+  FfnModule mods[2];
+  int n = 0;
+  if (a != nullptr) mods[n++] = *a;
+  mods[n++] = b;
+  return ffn_launch(y_in, D, mods, n, X, D, M, F, y_out, D, y_row_valid, eps, st, Wp, bp, P, Np);
 }
 
 }  // namespace cfm

@@ -160,7 +160,8 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     float mean = s1 * inv_n;
     float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + p.eps);
     if (elected) bulk_wait_read<0>();
-    named_bar_sync(bar_id, 128);                 // every staging buffer is free again
+    // every staging buffer is free again (of BOTH groups when y goes to a shared-memory tile that may overlap them)
+    if (NG == 2 && o.y_smem) named_bar_sync(xbar, 256); else named_bar_sync(bar_id, 128);
     int nbuf = 0;
     if (ln == 2) {
       // ---- pass 2 (double LN): X = LN1(v) -> TMEM + fp32 TMA store, statistics of X

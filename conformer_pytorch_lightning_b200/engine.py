@@ -184,13 +184,15 @@ def _mask_u8(mask):
     return mask
 
 
-def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws, ln=None):
+def mhsa_into(x, y, B, T, H, W, attn_mask, pos_embed, cache, want_cache, ws, ln=None, qkv_done=False):
     """x += linear_out(attn(...))  (attention.py:54-100 / 148-179 + encoder_layer.py:60-62).
-    Returns new_cache (B,H,Tk,128) fp32 when want_cache else None."""
+    Returns new_cache (B,H,Tk,128) fp32 when want_cache else None.  qkv_done: the Q/K/V projections of ``y`` were already
+    written to the workspace by the feed-forward call that produced ``y`` (see run_layers)."""
     n, d = y.shape
     dev, dt = y.device, y.dtype
     qkv = ws.get("qkv", (n, 3 * d), dt, dev)
-    ops.gemm(y, W["wqkv"], W["bqkv"], qkv, N.EPI_BIAS)
+    if not qkv_done:
+        ops.gemm(y, W["wqkv"], W["bqkv"], qkv, N.EPI_BIAS)
     q5 = qkv.view(B, T, 3, H, 64)
     q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
     if cache is not None and cache.dim() == 4 and cache.size(0) > 0:
@@ -305,10 +307,15 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
             ops.layernorm(x, Wl["ffm_g"], Wl["ffm_b"], y=y)
         # every residual GEMM carries the LayerNorm that feeds the next module in its epilogue
         if not ffm_done:
-            ffn_into(x, y, Wl["ffm"], 0.5, ws, ln={"y": y, "g1": Wl["mha_g"], "b1": Wl["mha_b"]})
+            # first feed-forward + attention LayerNorm + Q/K/V projections in one library call
+            b = dict(Wl["ffm"], alpha=0.5, g1=Wl["mha_g"], be1=Wl["mha_b"])
+            h = ws.get("ffn_h", (n, b["w1"].shape[0]), y.dtype, dev)
+            qkv = ws.get("qkv", (n, 3 * d), y.dtype, dev)
+            ops.ffn_chain(y, None, b, x, y, proj=(Wl["mha"]["wqkv"], Wl["mha"]["bqkv"], qkv), hidden_ws=h)
         cache = attn_caches[i] if attn_caches is not None else None
         new_caches.append(mhsa_into(x, y, B, T, H, Wl["mha"], attn_mask, pos_embed, cache, want_cache, ws,
-                                    ln={"y": y, "g1": Wl["conv_g"], "b1": Wl["conv_b"], "y_row_valid": row_valid}))
+                                    ln={"y": y, "g1": Wl["conv_g"], "b1": Wl["conv_b"], "y_row_valid": row_valid},
+                                    qkv_done=True))
         # the fused convolution module reads a halo of neighbouring rows of y, so its LayerNorm output goes to y2
         conv_into(x, y, B, T, Wl["conv"], row_valid, layer.conv_module, ws,
                   ln={"y": y2, "g1": Wl["ff_g"], "b1": Wl["ff_b"]})
@@ -322,7 +329,8 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
                 a = dict(Wl["ff"], alpha=0.5, g1=Wl["fin_g"], be1=Wl["fin_b"], g2=Wn["ffm_g"], be2=Wn["ffm_b"])
                 b = dict(Wn["ffm"], alpha=0.5, g1=Wn["mha_g"], be1=Wn["mha_b"])
                 h = ws.get("ffn_h", (n, a["w1"].shape[0]), y.dtype, dev)
-                ops.ffn_chain(y2, a, b, x, y, hidden_ws=h)
+                qkv = ws.get("qkv", (n, 3 * d), y.dtype, dev)
+                ops.ffn_chain(y2, a, b, x, y, proj=(Wn["mha"]["wqkv"], Wn["mha"]["bqkv"], qkv), hidden_ws=h)
             else:
                 ffn_into(x, y2, Wl["ff"], 0.5, ws, ln={"y": y, "g1": Wl["fin_g"], "b1": Wl["fin_b"],
                                                        "g2": Wn["ffm_g"], "b2": Wn["ffm_b"]})

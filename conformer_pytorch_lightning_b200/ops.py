@@ -124,15 +124,19 @@ def conv_module(y_in, w1, b1, dw_w, dw_b, w2, b2, x, B, T, *, row_valid=None, ln
                                     _ptr(glu_ws), _ptr(dw_ws), engine, _stream(x)))
 
 
-def ffn_chain(y_in, a, b, x, y_out, *, y_row_valid=None, hidden_ws=None, engine=N.ENGINE_AUTO):
-    """Two feed-forward modules back to back on the same rows (see cfm_ffn_chain).  a, b: dicts with w1, b1, w2, b2,
-    alpha, g1, be1 and optionally g2, be2; module a's LayerNorm output is module b's input."""
+def ffn_chain(y_in, a, b, x, y_out, *, y_row_valid=None, proj=None, hidden_ws=None, engine=N.ENGINE_AUTO):
+    """Up to two feed-forward modules back to back on the same rows (+ a projection of the final LayerNorm output); see
+    cfm_ffn_chain.  a (or None), b: dicts with w1, b1, w2, b2, alpha, g1, be1 and optionally g2, be2; module a's
+    LayerNorm output is module b's input.  proj = (w (Np,d), bias (Np), out (M,Np)) or None; with a projection on the
+    fused path y_out is NOT written."""
     _req(y_in, "ffn_chain.y_in")
     _req(x, "ffn_chain.x", torch.float32)
     _req(y_out, "ffn_chain.y_out", y_in.dtype)
     M, d = y_in.shape
-    F = a["w1"].shape[0]
+    F = b["w1"].shape[0]
     for m in (a, b):
+        if m is None:
+            continue
         _req(m["w1"], "ffn_chain.w1", y_in.dtype)
         _req(m["w2"], "ffn_chain.w2", y_in.dtype)
         if m["w1"].shape != (F, d) or m["w2"].shape != (d, F):
@@ -141,11 +145,24 @@ def ffn_chain(y_in, a, b, x, y_out, *, y_row_valid=None, hidden_ws=None, engine=
         raise RuntimeError("ffn_chain: shape mismatch")
 
     def mod(m):
+        if m is None:
+            return [None, None, None, None, 0.0, None, None, None, None]
         return [m["w1"].data_ptr(), m["b1"].data_ptr(), m["w2"].data_ptr(), m["b2"].data_ptr(), float(m["alpha"]),
                 _ptr(m.get("g1")), _ptr(m.get("be1")), _ptr(m.get("g2")), _ptr(m.get("be2"))]
+    pw = pb = po = None
+    npj = 0
+    if proj is not None:
+        pw, pb, po = proj
+        _req(pw, "ffn_chain.proj.w", y_in.dtype)
+        _req(pb, "ffn_chain.proj.bias", torch.float32)
+        _req(po, "ffn_chain.proj.out", y_in.dtype)
+        npj = pw.shape[0]
+        if pw.shape != (npj, d) or po.shape != (M, npj) or pb.shape != (npj,):
+            raise RuntimeError("ffn_chain: projection shape mismatch")
     ensure_init(x)
     N.check(N.lib().cfm_ffn_chain(y_in.data_ptr(), M, d, F, _DT[y_in.dtype], *mod(a), *mod(b), x.data_ptr(), y_out.data_ptr(),
-                                  _ptr(y_row_valid), 1e-5, _ptr(hidden_ws), engine, _stream(x)))
+                                  _ptr(y_row_valid), _ptr(pw), _ptr(pb), _ptr(po), npj, 1e-5, _ptr(hidden_ws), engine,
+                                  _stream(x)))
 
 
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):

@@ -110,21 +110,29 @@ int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1, const voi
             void* Y, int ld_out, const uint8_t* y_row_valid, float eps, void* hidden_ws, int engine, void* stream);
 
 /*
- * Two feed-forward modules applied back to back to the same rows, i.e. exactly
- *   cfm_ffn(y, a..., X, g1a/be1a/g2a/be2a -> Y)  followed by  cfm_ffn(Y, b..., X, g1b/be1b/g2b/be2b -> Y, y_row_valid)
- * (the second half-step feed-forward of layer i with norm_final + norm_ff_macaron of layer i+1, then the first
- * feed-forward of layer i+1: encoder_layer.py:68-70 of layer i, :56-59 of layer i+1).  Module a must have a LayerNorm
- * (g1a != NULL) since its output feeds module b.  y, Y: (M,d) act dtype contiguous (Y may alias y), X: (M,d) fp32
- * contiguous, both modules with the same F.  On the tcgen05 engine (bf16, d == 256, F % 256 == 0, alpha_b a power of
- * two) this is ONE kernel: the residual stream and the LayerNorm output between the two modules stay in TMEM / shared
- * memory.  Otherwise the library issues the two cfm_ffn calls (hidden_ws as in cfm_ffn).
+ * Up to two feed-forward modules applied back to back to the same rows, optionally followed by a projection of the
+ * final LayerNorm output, i.e. exactly
+ *   [cfm_ffn(y, a..., X, g1a/be1a/g2a/be2a -> Y)]           (skipped when W1a == NULL)
+ *   cfm_ffn(Y or y, b..., X, g1b/be1b/g2b/be2b -> Y, y_row_valid)
+ *   [cfm_gemm(Y, Wp, bp -> P (M, Np), CFM_EPI_BIAS)]         (skipped when Wp == NULL)
+ * This is the layer boundary of the encoder: the second half-step feed-forward of layer i with norm_final +
+ * norm_ff_macaron of layer i+1 (encoder_layer.py:68-70, :56), the first feed-forward of layer i+1 with its attention
+ * LayerNorm (:57-59) and that attention's Q/K/V projections (attention.py:62-64, Wp = [Wq;Wk;Wv]).
+ * Module a must have a LayerNorm (g1a != NULL) since its output feeds module b.  y, Y: (M,d) act dtype contiguous
+ * (Y may alias y), X: (M,d) fp32 contiguous, both modules with the same F.
+ * On the tcgen05 engine (bf16, d == 256, F % 256 == 0, alpha_b a power of two, Np % 256 == 0 with g2b == NULL) this is
+ * ONE kernel: the residual stream and the LayerNorm output between the two modules stay in TMEM / shared memory, and
+ * with a projection the final LayerNorm output is consumed on chip and Y IS NOT WRITTEN.  Otherwise the library issues
+ * the calls above (hidden_ws as in cfm_ffn).
  */
 int cfm_ffn_chain(const void* y, int M, int d, int F, int dtype,
                   const void* W1a, const float* b1a, const void* W2a, const float* b2a, float alpha_a,
                   const float* g1a, const float* be1a, const float* g2a, const float* be2a,
                   const void* W1b, const float* b1b, const void* W2b, const float* b2b, float alpha_b,
                   const float* g1b, const float* be1b, const float* g2b, const float* be2b,
-                  float* X, void* Y, const uint8_t* y_row_valid, float eps, void* hidden_ws, int engine, void* stream);
+                  float* X, void* Y, const uint8_t* y_row_valid,
+                  const void* Wp, const float* bp, void* P, int Np,
+                  float eps, void* hidden_ws, int engine, void* stream);
 
 /*
  * Scaled-dot-product attention with the reference's mask semantics (attention.py:84-97,

@@ -351,6 +351,51 @@ def test_ffn_fused_tcgen05(M, F, mode):
 
 
 @pytest.mark.parametrize("M,F", [(128, 2048), (333, 2048), (15872, 2048), (200, 256), (20000, 512)])
+@pytest.mark.parametrize("chained", [False, True])
+def test_ffn_chain_projection_tcgen05(M, F, chained):
+    """Feed-forward module(s) + LayerNorm + Q/K/V projection of the LayerNorm output in one kernel vs the separate library
+    calls and vs fp32 torch."""
+    dt, d, Np = torch.bfloat16, 256, 768
+    yin = rnd(M, d, dtype=dt)
+    mods = []
+    for i in range(2):
+        mods.append({"w1": rnd(F, d, dtype=dt, scale=1 / 16, seed=10 * i + 1), "b1": rnd(F, seed=10 * i + 2) * 0.5,
+                     "w2": rnd(d, F, dtype=dt, scale=1 / math.sqrt(F), seed=10 * i + 3), "b2": rnd(d, seed=10 * i + 4) * 0.5,
+                     "alpha": 0.5, "g1": rnd(d, seed=10 * i + 5) * 0.1 + 1, "be1": rnd(d, seed=10 * i + 6) * 0.1})
+    mods[0].update(g2=rnd(d, seed=7) * 0.1 + 1, be2=rnd(d, seed=8) * 0.1)
+    wp = rnd(Np, d, dtype=dt, scale=1 / 16, seed=31)
+    bp = rnd(Np, seed=32) * 0.5
+    x0 = rnd(M, d, seed=9, scale=2.0)
+    Fn = torch.nn.functional
+
+    def ref_mod(y, x, m):
+        h = Fn.silu(y.float() @ m["w1"].float().t() + m["b1"]).to(dt).float()
+        v = x + 0.5 * (h @ m["w2"].float().t() + m["b2"])
+        if m.get("g2") is None:
+            return v, Fn.layer_norm(v, (d,), m["g1"], m["be1"], 1e-5)
+        xn = Fn.layer_norm(v, (d,), m["g1"], m["be1"], 1e-5)
+        return xn, Fn.layer_norm(xn, (d,), m["g2"], m["be2"], 1e-5)
+    x1, y1 = (x0, yin.float())
+    if chained:
+        x1, y1 = ref_mod(yin, x0, mods[0])
+    x_ref, y_ref = ref_mod(y1.to(dt), x1, mods[1])
+    p_ref = y_ref.to(dt).float() @ wp.float().t() + bp
+    res = {}
+    for eng in (N.ENGINE_TC, N.ENGINE_SIMT):
+        x = x0.clone()
+        y = yin.clone()
+        pout = torch.full((M, Np), float("nan"), dtype=dt, device=DEV)
+        hws = torch.empty(M, F, dtype=dt, device=DEV)
+        ops.ffn_chain(y, mods[0] if chained else None, mods[1], x, y, proj=(wp, bp, pout), hidden_ws=hws, engine=eng)
+        assert torch.isfinite(x).all() and torch.isfinite(pout.float()).all()
+        assert rel_err(x, x_ref) < 4e-3, (eng, rel_err(x, x_ref))
+        assert rel_err(pout.float(), p_ref) < 1.5e-2, (eng, rel_err(pout.float(), p_ref))
+        res[eng] = (x, pout.float())
+    assert rel_err(res[N.ENGINE_TC][0], res[N.ENGINE_SIMT][0]) < 4e-3
+    assert rel_err(res[N.ENGINE_TC][1], res[N.ENGINE_SIMT][1]) < 1.5e-2
+
+
+@pytest.mark.parametrize("M,F", [(128, 2048), (333, 2048), (15872, 2048), (200, 256), (20000, 512)])
 @pytest.mark.parametrize("a_mode", [1, 2])
 def test_ffn_chain_tcgen05(M, F, a_mode):
     """Two feed-forward modules chained in one kernel (X and the LayerNorm output in between stay on chip) vs the two
