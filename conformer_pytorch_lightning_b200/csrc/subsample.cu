@@ -268,6 +268,260 @@ subsample_conv2_kernel(const __grid_constant__ CUtensorMap tmP,   // P as (C, F1
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------ conv1 + conv2 in one kernel (C == 256)
+// conv1's 653 MB activation is the front-end's whole problem: writing it is bound by the write side of HBM (210 us)
+// and conv2 then reads it back.  Here it never exists: for every k-step (filter tap (i,j), 64 input channels) of conv2's
+// implicit GEMM, the A tile [128 positions x 64 channels] of relu(conv1) is computed on the spot:
+//   converter warps   im2col of the fp32 features for the tap -> bf16 [128 x 16] (one tcgen05 K step; 4 taps share a tile)
+//   MMA warp          conv1:  acc1 = im2col . W1_kc^T        (M=128, N=64, K=16, one MMA, two TMEM buffers)
+//   converter warps   acc1 -> + b1, ReLU -> bf16 -> the swizzled A slot of the stage ring (where TMA used to put it)
+//   MMA warp          conv2:  acc  += A . W2_(tap,kc)^T       (M=128, N=256, K=64), W2 tiles by TMA as before
+// conv1 is recomputed for each of the 9 taps (0.3 % more tensor work) and runs two k-steps ahead of conv2, across tile
+// boundaries, so the tensor pipe only ever waits for conv2's own operands.  The conv2 accumulator is single-buffered
+// (TMEM: 256 + 2 x 64 columns), its bias + ReLU + 4-D TMA store epilogue has its own warpgroup.
+constexpr int kFusedThreads = 512;           // 4 control warps + 2 converter warpgroups + 1 epilogue warpgroup
+constexpr int kImBytes = 128 * 128;            // im2col tile: 4 K-step slots (taps t, t+1, t+2, t+3 mod 4)
+constexpr int kW1Bytes = 64 * 128;             // conv1 filters: row n = channel n of chunk kc, K-step slot kc
+constexpr int kBSt = 4, kASt = 2;             // W2 tiles need a deep ring (TMA latency), A tiles are produced locally
+constexpr int kFusedSmem = kBSt * kBBytes + kASt * kABytes + kImBytes + kW1Bytes + 2 * kBuf + 2 * BN * 4 + 512;
+static_assert(kFusedSmem <= 232448, "smem budget");
+
+struct FusedParams {
+  const float* x; const float* w1; const float* b1; const float* b2;
+  int B, Tin, idim, T2, F2, TL, tiles_per_utt;
+};
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C) K-major, box (64, 256)
+                       const __grid_constant__ CUtensorMap tmO,   // O as (C, F2, T2, B), box (64, F2, TL, 1)
+                       const FusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;                                   // kBSt x 32 KB
+  uint8_t* sAt = sB + kBSt * kBBytes;                   // kASt x 16 KB
+  uint8_t* sIm = sAt + kASt * kABytes;
+  uint8_t* sW1 = sIm + kImBytes;
+  uint8_t* ring = sW1 + kW1Bytes;                       // 2 output staging tiles
+  float* sb1 = reinterpret_cast<float*>(ring + 2 * kBuf);
+  float* sb2 = sb1 + BN;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(sb2 + BN);   // [kBSt] W2 tile landed
+  uint64_t* b_empty = b_full + kBSt;                    // [kBSt] conv2 MMAs that read the slot retired
+  uint64_t* a_full = b_empty + kBSt;                    // [kASt] A tile written by converter group g & 1 (128 arrivals)
+  uint64_t* a_empty = a_full + kASt;                    // [kASt]
+  uint64_t* im_full = a_empty + kASt;                   // [4] im2col slot written (128 arrivals)
+  uint64_t* im_empty = im_full + 4;                     // [4] conv1 MMAs of the tap retired
+  uint64_t* acc1_full = im_empty + 4;                   // [2]
+  uint64_t* acc1_empty = acc1_full + 2;                 // [2] 128 arrivals
+  uint64_t* tfull = acc1_empty + 2;
+  uint64_t* tempty = tfull + 1;                         // 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.B * p.tiles_per_utt;
+  const int n_my = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  const int n_ks = n_my * 36;                           // k-steps of this CTA, one stream across its tiles
+  const int rows_used = p.TL * p.F2;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmW); prefetch_tmap(&tmO); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kBSt; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < kASt; ++s) { mbar_init(a_full + s, 128); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(im_full + s, 128); mbar_init(im_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc1_full + s, 1); mbar_init(acc1_empty + s, 128); }
+    mbar_init(tfull, 1); mbar_init(tempty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  pdl_launch_dependents();
+  // conv1 filters (C x 9 fp32) -> bf16 B operand, biases -> smem (parameters: not produced by a preceding kernel)
+  for (int co = threadIdx.x; co < BN; co += kFusedThreads) {
+    float wv[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wv[k] = __ldg(p.w1 + co * 9 + k);
+    const int n = co & 63, kc = co >> 6;
+    uint8_t* rowp = sW1 + n * 128;
+    *reinterpret_cast<uint4*>(rowp + ((((2 * kc) ^ n) & 7) << 4)) =
+        make_uint4(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]), pack_bf16x2(wv[4], wv[5]), pack_bf16x2(wv[6], wv[7]));
+    *reinterpret_cast<uint4*>(rowp + ((((2 * kc + 1) ^ n) & 7) << 4)) = make_uint4(pack_bf16x2(wv[8], 0.f), 0u, 0u, 0u);
+    sb1[co] = __ldg(p.b1 + co);
+    sb2[co] = __ldg(p.b2 + co);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base + BN;            // 2 x 64 columns
+
+  if (warp == 0) {
+    // ===================== TMA producer: W2 tiles =====================
+    for (int g = 0; g < n_ks; ++g) {
+      const int ks = g % 36, tap = ks >> 2, kc = ks & 3;
+      const int bs = g % kBSt;
+      mbar_wait(b_empty + bs, ((g / kBSt) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(b_full + bs, kBBytes);
+        tma_load_2d(sB + bs * kBBytes, &tmW, b_full + bs, tap * BN + kc * BK, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc2 = umma_idesc_bf16(128, BN);
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64);
+    const uint64_t dim0 = umma_desc_sw128(smem_u32(sIm)), dw1 = umma_desc_sw128(smem_u32(sW1));
+    auto conv1 = [&](int g) {                           // k-step g of the CTA's stream
+      const int tapg = g >> 2, kc = g & 3;              // global tap counter (slot = tapg & 3)
+      const int ab = g & 1;
+      if (kc == 0) { mbar_wait(im_full + (tapg & 3), (tapg >> 2) & 1); }
+      mbar_wait(acc1_empty + ab, ((g >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        umma_bf16(tmem_acc1 + ab * 64, dim0 + 2 * (tapg & 3), dw1 + 2 * kc, idesc1, 0);
+        umma_commit(acc1_full + ab);
+        if (kc == 3) umma_commit(im_empty + (tapg & 3));
+      }
+      __syncwarp();
+    };
+    if (n_ks > 0) { conv1(0); conv1(1); }
+    for (int g = 0; g < n_ks; ++g) {
+      const int ks = g % 36, tl = g / 36;
+      const int as = g & 1, bs = g % kBSt;
+      if (ks == 0) { mbar_wait(tempty, (tl & 1) ^ 1); }  // the epilogue has drained the previous tile's accumulator
+      mbar_wait(a_full + as, (g >> 1) & 1);
+      mbar_wait(b_full + bs, (g / kBSt) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = umma_desc_sw128(smem_u32(sAt + as * kABytes)), db = umma_desc_sw128(smem_u32(sB + bs * kBBytes));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc2, (ks | k) != 0);
+        umma_commit(a_empty + as);
+        umma_commit(b_empty + bs);
+        if (ks == 35) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (g + 2 < n_ks) conv1(g + 2);
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== converter warps: thread = tile row (position); warpgroup cg takes the k-steps g = cg mod 2
+    //                       (= TMEM buffer acc1[cg]) and builds the im2col tiles of the taps tg = cg mod 2 =====================
+    const int cg = (warp - 4) >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int dt2 = r / p.F2, f2 = r - dt2 * p.F2;
+    // im2col of tap `tapg` (global counter) into K-step slot tapg & 3
+    auto build_im = [&](int tapg) {
+      const int tl = tapg / 9, tap = tapg - tl * 9;
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+      const int b = t / p.tiles_per_utt, t20 = (t % p.tiles_per_utt) * p.TL;
+      const int i = tap / 3, j = tap - i * 3;
+      const int slot = tapg & 3;
+      mbar_wait(im_empty + slot, ((tapg >> 2) & 1) ^ 1);
+      const int t2 = t20 + dt2;
+      float v[9];
+      if (r < rows_used && t2 < p.T2) {
+        const float* xin = p.x + ((size_t)b * p.Tin + 4 * t2 + 2 * i) * p.idim + 4 * f2 + 2 * j;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[a * 3 + c] = __ldg(xin + a * p.idim + c);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = 0.f;
+      }
+      uint8_t* rowp = sIm + r * 128;
+      *reinterpret_cast<uint4*>(rowp + ((((2 * slot) ^ r) & 7) << 4)) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(rowp + ((((2 * slot + 1) ^ r) & 7) << 4)) = make_uint4(pack_bf16x2(v[8], 0.f), 0u, 0u, 0u);
+      fence_proxy_async_smem();
+      mbar_arrive(im_full + slot);
+    };
+    const int n_taps = n_my * 9;
+    for (int tg = cg; tg < 3 && tg < n_taps; tg += 2) build_im(tg);
+    for (int g = cg; g < n_ks; g += 2) {
+      const int kc = g & 3, ab = g & 1;
+      // stay three taps ahead of conv1: at this group's first k-step of tap tg, build tap tg+3 if it is ours
+      if ((kc >> 1) == 0 && (((g >> 2) + 3) & 1) == cg && (g >> 2) + 3 < n_taps) build_im((g >> 2) + 3);
+      mbar_wait(acc1_full + ab, (g >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        tmem_ld32(tmem_acc1 + lane_base + ab * 64, v0);
+        tmem_ld32(tmem_acc1 + lane_base + ab * 64 + 32, v1);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(acc1_empty + ab);
+      const float* bs = sb1 + kc * 64;
+      uint4 pk[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * jj + e]) + bs[8 * jj + e], 0.f);
+        pk[jj] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      }
+      mbar_wait(a_empty + cg, ((g >> 1) & 1) ^ 1);       // conv2 has finished with the A tile that lived here (slot g & 1 = cg)
+      uint8_t* a = sAt + cg * kABytes;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(a + r * 128 + (((jj ^ r) & 7) << 4)) = pk[jj];
+      fence_proxy_async_smem();
+      mbar_arrive(a_full + cg);
+    }
+  } else if (warp >= 12) {
+    // ===================== output epilogue: bias + ReLU + 4-D TMA store, thread = tile row =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 384;
+    const bool elected = (et == 0);
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    int sub_cnt = 0;
+    for (int tl = 0; tl < n_my; ++tl) {
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+      const int b = t / p.tiles_per_utt, t20 = (t % p.tiles_per_utt) * p.TL;
+      mbar_wait(tfull, tl & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub, ++sub_cnt) {
+        uint8_t* buf = ring + (sub_cnt & 1) * kBuf;
+        if (elected) bulk_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint32_t v[64];
+        {
+          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          tmem_ld32(tmem_base + lane_base + sub * 64, v0);
+          tmem_ld32(tmem_base + lane_base + sub * 64 + 32, v1);
+        }
+        tmem_ld_wait();
+        const float* bs = sb2 + sub * 64;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * jj + e]) + bs[8 * jj + e], 0.f);
+          *reinterpret_cast<uint4*>(buf + r * 128 + (((jj ^ r) & 7) << 4)) =
+              make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (elected) {
+          tma_store_4d(&tmO, buf, sub * 64, 0, t20, b);   // box (64, F2, TL, 1): rows past T2 are clipped
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+    if (elected) bulk_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 int make_map_nd(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box) {
   EncodeTiledFn fn = tc::encode_tiled_fn();
@@ -305,6 +559,39 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
   const int T1h = (T1 + 1) / 2, F1h = (F1 + 1) / 2;
   const int TL = 128 / F2;
   cudaStream_t st = (cudaStream_t)stream;
+  // C == 256: conv1 is computed on the fly inside conv2 (CFM_B200_FRONTEND=unfused keeps the two-kernel path)
+  static int fe_unfused = -1;
+  if (fe_unfused < 0) {
+    const char* e = getenv("CFM_B200_FRONTEND");
+    fe_unfused = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
+  }
+  if (!fe_unfused && C == 256 && tc::encode_tiled_fn() != nullptr) {
+    CUtensorMap tmW, tmO;
+    int rc;
+    {
+      const uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C};
+      const uint64_t str[1] = {(uint64_t)9 * C * 2};
+      const uint32_t box[2] = {64, 256};
+      if ((rc = make_map_nd(&tmW, w2, 2, dims, str, box)) != 0) return rc;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)F2, (uint64_t)T2, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)F2 * C * 2, (uint64_t)T2 * F2 * C * 2};
+      const uint32_t box[4] = {64, (uint32_t)F2, (uint32_t)TL, 1};
+      if ((rc = make_map_nd(&tmO, out, 4, dims, str, box)) != 0) return rc;
+    }
+    FusedParams fp{x, w1, b1, b2, B, Tin, idim, T2, F2, TL, (T2 + TL - 1) / TL};
+    static bool fattr = false;
+    if (!fattr) {
+      CFM_CUDA_OK(cudaFuncSetAttribute(subsample_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+      fattr = true;
+    }
+    const int total = B * fp.tiles_per_utt;
+    const int grid = total < num_sms() ? total : num_sms();
+    CFM_CUDA_OK(launch_pdl(subsample_fused_kernel, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
+    CFM_LAUNCHED();
+    return 0;
+  }
   {
     const int n_rows = B * T1;
     const int blocks = std::min((n_rows + kC1Warps - 1) / kC1Warps, num_sms() * 8);
