@@ -330,6 +330,14 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float lt = l + xch_l[(grp ^ 1) * 128 + r];
       l0 = h == 0 ? lt : l0; l1 = h == 1 ? lt : l1; l2 = h == 2 ? lt : l2; l3 = h == 3 ? lt : l3;
     }
+    // The residual rows of the epilogue: each warpgroup's staging ring is its stage's [Q | K | V] area.  Both Q slots are
+    // dead (S_2 / S_3 have retired), so the first 32-column chunk is fetched now; the other three follow once the
+    // projection has finished reading W_o out of the K / V slots.
+    uint8_t* ring = sStage + grp * kStage;
+    if (elected) {
+      mbar_expect_tx(res_bar + grp * 4, QT * 128);
+      resid_tma_load(ring, &tmR, res_bar + grp * 4, grp * 128, i0, b);
+    }
     // ---- context: O_h / l_h -> bf16 A operand (head h = k atom h); this warpgroup takes 32 of each head's 64 columns
     mbar_wait(pv_done, (NH - 1) & 1);
     tc_fence_after();
@@ -358,15 +366,21 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (tid == 0) MTR(26);
-    // every MMA has retired: stage s's K/V slots are warpgroup s's staging ring, stage 1's Q slot holds the parameters
-    float* sparam = reinterpret_cast<float*>(sStage + kStage);
+    // every MMA has retired: the K / V slots (W_o) and the ctx tile (-> parameters, row-sum exchange) are dead
+    float* sparam = reinterpret_cast<float*>(sP);
     resid_stage_params<D, 256>(sparam, tid, p.bo, 0, p.ln_mode, p.g1, p.be1, nullptr, nullptr);
-    uint8_t* ring = sStage + grp * kStage + kQBytes;
-    if (elected) resid_prefetch<D, 4, QT, 2>(ring, res_bar + grp * 4, &tmR, 0, i0, grp, b);
+    if (elected) {
+#pragma unroll
+      for (int c = 1; c < 4; ++c) {
+        mbar_expect_tx(res_bar + grp * 4 + c, QT * 128);
+        resid_tma_load(ring + c * kBufBytes, &tmR, res_bar + grp * 4 + c, (grp * 4 + c) * 32, i0, b);
+      }
+    }
     ResidParams rp{nullptr, p.y_row_valid, 1.0f, p.eps, p.ln_mode, p.B * p.T};
+    ResidOpts ro;
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 3) ro.trace = p.trace + 32;
     resid_ln_epilogue<D, 4, QT, 2>(tmem_base + lane_base, r, i0, 0, elected, 1 + grp, ring, res_bar + grp * 4, ring_phase, sparam,
-                                   &tmX, &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sStage + kStage + 8192), b,
-                                   b * p.T + i0);
+                                   &tmX, &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sP + 8192), b, b * p.T + i0, ro);
     if (tid == 0) MTR(27);
     if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }

@@ -39,6 +39,7 @@ struct ResidOpts {
   float park_scale = 1.f;       // the X row left in the TMEM accumulator columns is multiplied by this (it becomes the
                                 // initial value of the next module's accumulator: X / alpha_next)
   bool no_residual = false;     // the accumulator already contains the residual: v = alpha * (acc + bias)
+  long long* trace = nullptr;   // optional clock64 stamps of (group 0, row 0): tools/mhsa_trace.py
 };
 
 struct ResidParams {
@@ -95,6 +96,8 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
   const bool valid = (p.row_valid == nullptr) || !row_ok || (p.row_valid[row] != 0);
   const float a = valid ? p.alpha : 0.f;
   if (NG == 1) named_bar_sync(bar_id, 128); else named_bar_sync(xbar, 128 * NG);   // sparam visible
+#define RTR(i) do { if (o.trace && grp == 0 && r == 0) o.trace[i] = clock64(); } while (0)
+  RTR(0);
   float s1 = 0.f, s2 = 0.f;
   // ---- pass 1: v = R + alpha*(acc + bias)
 #pragma unroll 1
@@ -108,6 +111,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
       if (elected) bulk_wait_read<R - 1>();
       named_bar_sync(bar_id, 128);
     }
+    RTR(1 + 2 * c);
     uint32_t v[32];
     tmem_ld32(taddr + (ch0 + c) * 32, v);
     tmem_ld_wait();
@@ -130,6 +134,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     }
     if (ln != 0) tmem_st32(taddr + (ch0 + c) * 32, v);   // park the row in our accumulator columns
     fence_proxy_async_smem();
+    RTR(2 + 2 * c);
     named_bar_sync(bar_id, 128);
     if (elected) {
       if (ln != 2 && o.store_x) {
@@ -148,6 +153,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
       }
     }
   }
+  RTR(9);
   if (ln != 0) {
     tmem_st_wait();
     if (NG == 2) {                               // row sums of the other half of the columns
@@ -208,6 +214,7 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     // ---- final pass: y = LN(X) as bf16 (64-column sub-tiles), optional row mask
     const float* g = sparam + (ln == 2 ? 3 * BN : BN);
     const float* be = sparam + (ln == 2 ? 4 * BN : 2 * BN);
+    RTR(10);
     const bool ykeep = (p.y_row_valid == nullptr) || !row_ok || (p.y_row_valid[row] != 0);
     const float unpark = 1.f / o.park_scale;     // exact: park_scale is a power of two (1 / alpha)
     if (!o.store_x) nbuf = 0;                    // nothing of pass 2 went through the ring
@@ -242,11 +249,14 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
       }
     }
   }
+  RTR(11);
   tc_fence_before();
   // the staging ring must be drained before anything overwrites it (next tile's residual prefetch); with two groups
   // nobody may restage sparam / xch for the next tile while the other group still reads them
   if (elected) bulk_wait_read<0>();
   if (NG == 1) named_bar_sync(bar_id, 128); else named_bar_sync(xbar, 128 * NG);
+  RTR(12);
+#undef RTR
 }
 
 }  // namespace tc
