@@ -28,7 +28,7 @@ constexpr int KS = 15, HALO = 7;
 constexpr int ROWS = 128 - (KS - 1);            // 114 output rows per tile
 constexpr int kAtom = 16384, kPiece = 32768, NST = 3;
 constexpr int kTile = 128 * D * 2;             // 64 KB
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;                  // 4 control warps + 2 GLU/depthwise/epilogue warpgroups + 1 depthwise-only warpgroup
 constexpr int kSmemBytes = 2 * kTile + NST * kPiece + 2 * D * 4 + 512;
 static_assert(kSmemBytes <= 232448, "smem budget");
 
@@ -78,7 +78,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
   uint64_t* w_empty = w_full + NST;         // [NST]
   uint64_t* y_full = w_empty + NST;
   uint64_t* s_full = y_full + 1;            // [2] pw1 accumulator (128 value + 128 gate channels) complete
-  uint64_t* c_full = s_full + 2;            // C tile written by the 256 epilogue threads (S drained, G dead)
+  uint64_t* c_full = s_full + 2;            // C tile written by the 384 depthwise threads (S drained, G dead)
   uint64_t* acc_full = c_full + 1;          // pw2 accumulator complete
   uint64_t* tile_done = acc_full + 1;       // 256 arrivals
   uint64_t* res_bar = tile_done + 1;        // [2 groups][4]
@@ -94,7 +94,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
-    mbar_init(y_full, 1); mbar_init(s_full, 1); mbar_init(s_full + 1, 1); mbar_init(c_full, 256); mbar_init(acc_full, 1);
+    mbar_init(y_full, 1); mbar_init(s_full, 1); mbar_init(s_full + 1, 1); mbar_init(c_full, 384); mbar_init(acc_full, 1);
     mbar_init(tile_done, 256);
     for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
     fence_barrier_init();
@@ -177,17 +177,17 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (256 threads) =====================
+    // ===================== epilogue warps (3 warpgroups) =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;                  // tile row for the row-wise phases
     const int grp = (warp - 4) >> 2;
     const int et = threadIdx.x - 128 - grp * 128;
-    const int tid = threadIdx.x - 128;            // 0..255
+    const int tid = threadIdx.x - 128;            // 0..383
     const bool elected = (et == 0);
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     uint32_t ring_phase = 0;
-    // depthwise role: channel pair + half of the output rows
-    const int cp = tid & 127, half = tid >> 7;
+    // depthwise role: channel pair + third of the output rows (warpgroup 2 only takes part in the depthwise phase)
+    const int cp = tid & 127, third = tid >> 7;
     float2 wt[KS];
 #pragma unroll
     for (int j = 0; j < KS; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(p.dw_w + j * D + 2 * cp));
@@ -195,6 +195,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int m0 = t * ROWS;
+      if (grp < 2) {
       sb1[tid] = p.b1[tid];
       sb1[256 + tid] = p.b1[256 + tid];
       named_bar_sync(3, 256);
@@ -228,13 +229,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
       }
       tc_fence_before();
       if (tid == 0) CONV_STAMP(10);
-      named_bar_sync(3, 256);                       // G complete; pw1 has retired, so the y tile and S accumulators are dead
+      }
+      named_bar_sync(5, 384);                       // G complete; pw1 has retired, so the y tile and S accumulators are dead
       if (tid == 0) CONV_STAMP(11);
       // ---- depthwise conv + folded BatchNorm + SiLU -> C (A operand of pw2)
-      constexpr int PASS = 19;                      // 3 passes x 19 outputs = 57 rows per thread
+      constexpr int PASS = 19;                      // 2 passes x 19 outputs = 38 rows per thread
 #pragma unroll 1
-      for (int ps = 0; ps < 3; ++ps) {
-        const int o0 = half * 57 + ps * PASS;
+      for (int ps = 0; ps < 2; ++ps) {
+        const int o0 = third * 38 + ps * PASS;
         const int Ro0 = m0 + o0;                    // global token of the first output of the pass
         // utterance of each output token: taps reaching outside [lo, hi) are zero padding
         const int u0 = Ro0 / p.T, u1 = (Ro0 + PASS - 1) / p.T;
@@ -277,6 +279,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
       fence_proxy_async_smem();
       mbar_arrive(c_full);
       if (tid == 0) CONV_STAMP(12);
+      if (grp == 2) continue;                       // (its next stop is the G-complete barrier of the next tile)
       // ---- pw2 accumulator -> residual stream (+ LayerNorm), interior rows only; each warpgroup takes 128 columns
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
@@ -292,7 +295,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmYin,   // y (M,256) bf16
       if (tid == 0) CONV_STAMP(14);
       if (t + (int)gridDim.x < n_tiles) mbar_wait(tile_done, it & 1);   // sb1 / sY / sG are re-used by the next tile
     }
-    if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
+    if (elected && grp < 2) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
