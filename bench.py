@@ -185,10 +185,23 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on stdout at VERSION/INFO level; stdout must carry exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        # NCCL prints its version banner on stdout at VERSION/INFO level (env var or nccl.conf); stdout must carry
+        # exactly one JSON line, so the level is lowered and, belt and braces, file descriptor 1 points at stderr while
+        # the communicator is created (eager init + one collective)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device("cuda", local)
 
     cfg_name, feats_np, lens_np, T, audio_s = make_inputs(args.workload, seed=1234 + rank)
