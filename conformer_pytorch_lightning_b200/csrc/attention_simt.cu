@@ -8,17 +8,19 @@
 namespace cfm {
 namespace {
 
-constexpr int QR = 32;      // query rows per block (8 per warp)
+// query rows per block = 4 warps x RPW rows (RPW = 8; 2 for streaming chunks, whose 16 rows then spread over 2 x H blocks
+// of 4 busy warps instead of 1 x H blocks with two idle warps)
 constexpr int KT = 64;      // keys per shared-memory tile
 constexpr int DK = 64;
 constexpr int KSTR = DK + 1;  // padded K row stride (bank-conflict free column reads)
 
-template <typename T>
+template <typename T, int RPW>
 __global__ void __launch_bounds__(128)
 attention_simt_kernel(const T* __restrict__ q, int64_t q_bs, int64_t q_ts, const T* __restrict__ k, int64_t k_bs,
                       int64_t k_ts, const T* __restrict__ v, int64_t v_bs, int64_t v_ts, T* __restrict__ out,
                       int H, int Tq, int Tk, const uint8_t* __restrict__ mask, int64_t mask_bs, int64_t mask_rs,
                       const float* __restrict__ key_bias, float scale) {
+  constexpr int QR = 4 * RPW;
   __shared__ float sq[QR][DK];
   __shared__ float sk[KT][KSTR];
   __shared__ float sv[KT][DK];
@@ -32,9 +34,9 @@ attention_simt_kernel(const T* __restrict__ q, int64_t q_bs, int64_t q_ts, const
     sq[r][c] = (i < Tq) ? to_f32(q[b * q_bs + i * q_ts + h * DK + c]) : 0.f;
   }
 
-  float m[8], l[8], o0[8], o1[8];
+  float m[RPW], l[RPW], o0[RPW], o1[RPW];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) { m[r] = -CUDART_INF_F; l[r] = 0.f; o0[r] = 0.f; o1[r] = 0.f; }
+  for (int r = 0; r < RPW; ++r) { m[r] = -CUDART_INF_F; l[r] = 0.f; o0[r] = 0.f; o1[r] = 0.f; }
 
   for (int j0 = 0; j0 < Tk; j0 += KT) {
     __syncthreads();
@@ -50,8 +52,8 @@ attention_simt_kernel(const T* __restrict__ q, int64_t q_bs, int64_t q_ts, const
     const float kb_a = (key_bias && ja < Tk) ? key_bias[((size_t)b * H + h) * Tk + ja] : 0.f;
     const float kb_b = (key_bias && jb < Tk) ? key_bias[((size_t)b * H + h) * Tk + jb] : 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int row = warp * 8 + r;
+    for (int r = 0; r < RPW; ++r) {
+      const int row = warp * RPW + r;
       const int i = i0 + row;
       if (i >= Tq) continue;   // warp-uniform
       float sa = 0.f, sb = 0.f;
@@ -96,8 +98,8 @@ attention_simt_kernel(const T* __restrict__ q, int64_t q_bs, int64_t q_ts, const
   }
 
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int i = i0 + warp * 8 + r;
+  for (int r = 0; r < RPW; ++r) {
+    const int i = i0 + warp * RPW + r;
     if (i >= Tq) continue;
     const float inv = (l[r] > 0.f) ? 1.0f / l[r] : 0.f;   // fully masked row -> 0 (attention.py:92)
     T* orow = out + ((size_t)b * Tq + i) * H * DK + h * DK;
@@ -113,15 +115,17 @@ int attention_simt(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int
                    const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias, float scale,
                    int dtype, cudaStream_t st) {
   CFM_CHECK_ARG(H <= 65535 && B <= 65535, "cfm_attention: B/H too large for the grid");
-  dim3 grid((Tq + QR - 1) / QR, H, B);
-  if (dtype == CFM_F32)
-    attention_simt_kernel<float><<<grid, 128, 0, st>>>((const float*)q, q_bs, q_ts, (const float*)k, k_bs, k_ts,
-                                                       (const float*)v, v_bs, v_ts, (float*)out, H, Tq, Tk, mask,
-                                                       mask_bs, mask_rs, key_bias, scale);
-  else
-    attention_simt_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
-        (const __nv_bfloat16*)q, q_bs, q_ts, (const __nv_bfloat16*)k, k_bs, k_ts, (const __nv_bfloat16*)v, v_bs,
-        v_ts, (__nv_bfloat16*)out, H, Tq, Tk, mask, mask_bs, mask_rs, key_bias, scale);
+  const int rpw = (Tq <= 32) ? 2 : 8;
+  dim3 grid((Tq + 4 * rpw - 1) / (4 * rpw), H, B);
+#define CFM_ATTN_SIMT(TT, R)                                                                                              \
+  attention_simt_kernel<TT, R><<<grid, 128, 0, st>>>((const TT*)q, q_bs, q_ts, (const TT*)k, k_bs, k_ts, (const TT*)v, v_bs, \
+                                                     v_ts, (TT*)out, H, Tq, Tk, mask, mask_bs, mask_rs, key_bias, scale)
+  if (dtype == CFM_F32) {
+    if (rpw == 2) CFM_ATTN_SIMT(float, 2); else CFM_ATTN_SIMT(float, 8);
+  } else {
+    if (rpw == 2) CFM_ATTN_SIMT(__nv_bfloat16, 2); else CFM_ATTN_SIMT(__nv_bfloat16, 8);
+  }
+#undef CFM_ATTN_SIMT
   CFM_LAUNCHED();
   return 0;
 }

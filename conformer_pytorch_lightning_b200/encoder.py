@@ -177,13 +177,66 @@ class ConformerEncoder(nn.Module):
             next_cache_start = attention_key_size
         else:
             next_cache_start = max(attention_key_size - required_cache_size, 0)
-        engine.check_inference_only(self, self._max_dropout())
-        caches = [attn_cache[i:i + 1] for i in range(len(self.encoders))] if num_layers > 0 else None
-        out, new_caches = engine.run_layers(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask,
-                                            pos_embed, None, caches, True, engine.resolve_dtype(self))
-        r_attn_cache = torch.cat([c[:, :, next_cache_start:, :] for c in new_caches], dim=0).to(outputs.dtype)
+        if self.training:
+            engine.check_inference_only(self, self._max_dropout())
+        dtype = engine.resolve_dtype(self)
+        no_mask = inputs_attn_mask is None or inputs_attn_mask.dim() != 3 or inputs_attn_mask.size(2) == 0
+        if (self.use_cuda_graphs and not self.training and outputs.is_cuda and no_mask and len(self.encoders) > 0
+                and not torch.cuda.is_current_stream_capturing()):
+            out, r_attn_cache = self._graph_chunk(outputs, pos_embed, attn_cache, next_cache_start, dtype)
+            r_attn_cache = r_attn_cache.to(outputs.dtype)
+        else:
+            out, r_attn_cache = self._chunk_layers(outputs.float(), pos_embed, attn_cache, next_cache_start, dtype,
+                                                   inputs_attn_mask)
+            r_attn_cache = r_attn_cache.to(outputs.dtype)
         r_cnn_cache = torch.zeros((len(self.encoders), 0, 0, 0), dtype=outputs.dtype, device=outputs.device)
         return out.to(outputs.dtype), r_attn_cache, r_cnn_cache
+
+    def _chunk_layers(self, x, pos_embed, attn_cache, next_cache_start, dtype, attn_mask=None):
+        """Layer loop of one streaming step (encoder.py:109-118): per-layer cache slice in, trimmed caches out."""
+        caches = [attn_cache[i:i + 1] for i in range(len(self.encoders))] if attn_cache.size(0) > 0 else None
+        out, new_caches = engine.run_layers(x, list(self.encoders), self.after_norm, attn_mask, pos_embed, None, caches,
+                                            True, dtype)
+        return out, torch.cat([c[:, :, next_cache_start:, :] for c in new_caches], dim=0)
+
+    def _graph_chunk(self, outputs, pos_embed, attn_cache, next_cache_start, dtype):
+        """Streaming steps are launch-bound (B = 1, 16 rows: ~150 small launches): with a fixed number of left chunks the
+        shapes repeat from chunk to chunk, so the layer loop of a step is captured into a CUDA graph per (chunk, cache
+        size, trim point) exactly like the batched path (first call eager, second captures, later ones replay)."""
+        key = ("chunk", tuple(outputs.shape), tuple(pos_embed.shape), tuple(attn_cache.shape), next_cache_start, dtype,
+               outputs.device, len(self.encoders))
+        plan = self._plans.get(key)
+        if plan is None:
+            self._plans[key] = {"graph": None}
+            return self._chunk_layers(outputs.float(), pos_embed, attn_cache, next_cache_start, dtype)
+        if plan["graph"] is None:
+            x_s = torch.empty(outputs.shape, dtype=torch.float32, device=outputs.device)
+            p_s = torch.empty_like(pos_embed)
+            c_s = torch.empty(attn_cache.shape, dtype=attn_cache.dtype, device=outputs.device)
+            x_s.copy_(outputs); p_s.copy_(pos_embed); c_s.copy_(attn_cache)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._chunk_layers(x_s, p_s, c_s, next_cache_start, dtype)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = _native.launch_count()
+            with torch.cuda.graph(g):
+                out_s, r_s = self._chunk_layers(x_s, p_s, c_s, next_cache_start, dtype)
+            plan.update(graph=g, x=x_s, p=p_s, c=c_s, out=out_s, r=r_s, launches=_native.launch_count() - n0)
+        ver = self._weights_version()
+        if plan.get("ver") != ver:
+            for layer in self.encoders:
+                layer.derived_weights(dtype)
+            plan["ver"] = ver
+        plan["x"].copy_(outputs)
+        plan["p"].copy_(pos_embed)
+        if plan["c"].numel() > 0:
+            plan["c"].copy_(attn_cache)
+        plan["graph"].replay()
+        engine.GRAPH_REPLAYED_LAUNCHES[0] += plan["launches"]
+        return plan["out"].clone(), plan["r"].clone()
 
     def forward_chunk_by_chunk(self, inputs, decoding_chunk_size, num_decoding_left_chunks=-1):
         subsampling_rate, context = 4, 7

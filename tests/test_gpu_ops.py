@@ -48,7 +48,8 @@ def test_layernorm_variants(d, ydt):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,Nn,K", [(1, 256, 256), (77, 256, 2048), (300, 2048, 256), (129, 768, 256), (64, 512, 512)])
+@pytest.mark.parametrize("M,Nn,K", [(1, 256, 256), (77, 256, 2048), (300, 2048, 256), (129, 768, 256), (64, 512, 512),
+                                    (16, 256, 2048), (16, 2048, 256), (16, 768, 256), (7, 255, 264), (13, 512, 1000)])
 def test_gemm_epilogues_simt(dt, M, Nn, K):
     a = rnd(M, K, dtype=dt)
     w = rnd(Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=1)
