@@ -234,3 +234,20 @@ def test_encoder_pipeline_matches_forward(depth):
         n += 1
     assert n == len(want)
     assert max_rel(want[0][0].numpy(), g["out"]) < BF16_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_streaming_graph_replay_equals_eager(dtype):
+    """forward_chunk captures a CUDA graph per (chunk, cache size, trim point); with 2 left chunks the steady-state
+    shape repeats, so a 3-pass run exercises eager, capture and replay.  Replays must equal eager bit for bit."""
+    g = load_golden("m3_chunk_by_chunk")
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    eager = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=dtype)
+    eager.use_cuda_graphs = False
+    feats = torch.from_numpy(g["feats"]).cuda()[:1]
+    with torch.no_grad():
+        want, _ = eager.forward_chunk_by_chunk(feats, 16, 2)
+        for it in range(3):
+            got, _ = enc.forward_chunk_by_chunk(feats, 16, 2)
+            assert torch.equal(got, want), f"pass {it}"
+    assert any(k[0] == "chunk" and p.get("graph") is not None for k, p in enc._plans.items() if isinstance(k, tuple))
