@@ -21,7 +21,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 EXPORTS = [
     "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
-    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain",
+    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax",
 ]
 
 _lib = None
@@ -42,6 +42,9 @@ def _declare(lib):
     lib.cfm_ffn.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i, _p, _f, _p, _i, _p]
     lib.cfm_ffn_chain.argtypes = ([_p, _i, _i, _i, _i] + [_p, _p, _p, _p, _f, _p, _p, _p, _p] * 2 +
                                   [_p, _p, _p, _p, _p, _p, _i, _f, _p, _i, _p])
+    lib.cfm_ctc_ws_bytes.argtypes = [_i, _i, _i]
+    lib.cfm_ctc_ws_bytes.restype = _i64
+    lib.cfm_ctc_argmax.argtypes = [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]
     lib.cfm_mhsa_out.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p, _i64, _i64, _p, _f,
                                  _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p]
     lib.cfm_conv_module.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _i, _p]
@@ -56,7 +59,7 @@ def _declare(lib):
     lib.cfm_subsample_conv.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version", "cfm_subsample_ws_bytes"):
+        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes"):
             fn.restype = _i
 
 

@@ -167,6 +167,8 @@ bool gemm_tc_supported(int lda, int ldc, int M, int N, int K, int dtype, int epi
 int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N,
             int K, int dtype, int epilogue, const float* residual, float alpha,
             const uint8_t* row_valid, cudaStream_t st);
+int gemm_tc_argmax(const void* A, int lda, const void* W, const float* bias, int M, int V, int K, unsigned long long* keys,
+                   cudaStream_t st);
 int gemm_tc_init();
 // RESIDUAL epilogue with fused LayerNorm(s) (ln_mode 1 or 2); needs N == 256 (one tile per row)
 bool gemm_tc_ln_supported(int lda, int ldx, int ldy, int M, int N, int K, int dtype);

@@ -22,6 +22,7 @@
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 #include "resid_epilogue.cuh"
+#include <math_constants.h>
 
 #include <mutex>
 
@@ -103,7 +104,11 @@ struct GemmParams {
   float alpha, eps;
   int M, N, K;                  // N = number of OUTPUT columns (GLU: W has 2N rows)
   int ln_mode;                  // 0 none, 1 y = LN1(X), 2 X = LN1(.), y = LN2(X)
+  unsigned long long* keys;     // ARGMAX epilogue: per-row packed (ordered logit, ~column), combined with atomicMax
+  int n_valid;                  // ARGMAX: columns >= n_valid are padding (W rows zero-filled by TMA)
 };
+constexpr int EPI_ARGMAX = 100; // internal epilogue of cfm_ctc_argmax: no C tile at all
+
 
 
 template <int BN, int EPI>
@@ -235,6 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int GCOLS = OUT_BN / 2;
         for (int ii = et; ii < GCOLS; ii += 128) {
           const int i = grp * GCOLS + ii;
+          if constexpr (EPI == EPI_ARGMAX) sparam[i] = (p.bias && n0 + i < p.n_valid) ? p.bias[n0 + i] : 0.f;
+          else
           sparam[i] = p.bias ? p.bias[n0 + i] : 0.f;
           if constexpr (GLU) sparam[OUT_BN + i] = p.bias ? p.bias[p.N + n0 + i] : 0.f;
         }
@@ -244,6 +251,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------------- bf16 activations: 64-column sub-tiles through a 2-deep staging ring + TMA store
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
+        if constexpr (EPI == EPI_ARGMAX) {
+          // row-wise (max, argmax) of this warpgroup's columns; tiles of the same rows on other CTAs are combined
+          // through a 64-bit atomicMax on (order-preserving logit bits, ~column): ties go to the lowest column
+          named_bar_sync(bar_id, 128);                 // sparam visible
+          float best = -CUDART_INF_F;
+          int best_col = 0;
+#pragma unroll 1
+          for (int ss = 0; ss < OUT_BN / 128; ++ss) {
+            const int sub = grp * (OUT_BN / 128) + ss;
+            uint32_t v[64];
+            {
+              uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+              uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+              tmem_ld32(taddr + sub * 64, v0);
+              tmem_ld32(taddr + sub * 64 + 32, v1);
+            }
+            tmem_ld_wait();
+            const float* bs = sparam + sub * 64;
+            const int c0 = n0 + sub * 64;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+              const float x = __uint_as_float(v[e]) + bs[e];
+              if (c0 + e < p.n_valid && x > best) { best = x; best_col = c0 + e; }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(tempty_bar + acc);
+          const int row = m0 + r;
+          if (row < p.M && best > -CUDART_INF_F) {
+            uint32_t u = __float_as_uint(best);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            atomicMax(p.keys + row, (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - (uint32_t)best_col));
+          }
+          named_bar_sync(bar_id, 128);                 // sparam may be restaged for the next tile
+        } else {
 #pragma unroll 1
         for (int ss = 0; ss < OUT_BN / 128; ++ss, ++sub_cnt) {
           const int sub = grp * (OUT_BN / 128) + ss;   // 64-column sub-tile owned by this warpgroup
@@ -288,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         mbar_arrive(tempty_bar + acc);
+        }
       } else {
         // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
         constexpr int RG = C::kBufs / 2;                  // staging tiles per warpgroup
@@ -404,6 +447,20 @@ int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* 
     case CFM_EPI_BIAS: return launch_tc<128, CFM_EPI_BIAS>(tmA, tmW, tmC, tmR, tmY, p, st);
     default: return launch_tc<128, CFM_EPI_BIAS_SILU>(tmA, tmW, tmC, tmR, tmY, p, st);
   }
+}
+
+// P = A W^T + bias is never written: per-row (max, argmax) over the V = N valid columns into `keys` (zeroed by the caller)
+int gemm_tc_argmax(const void* A, int lda, const void* W, const float* bias, int M, int V, int K, unsigned long long* keys,
+                   cudaStream_t st) {
+  CFM_CHECK_ARG(aligned16(A) && aligned16(W), "cfm_ctc_argmax(tc): x/W must be 16-byte aligned");
+  const int n_pad = (V + 255) / 256 * 256;
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_2d(&tmA, false, A, M, K, lda, BM)) != 0) return rc;
+  if ((rc = make_2d(&tmW, false, W, V, K, K, 256)) != 0) return rc;     // rows >= V of the last block: zero-filled
+  GemmParams p{};
+  p.bias = bias; p.M = M; p.N = n_pad; p.K = K; p.keys = keys; p.n_valid = V;
+  return launch_tc<256, EPI_ARGMAX>(tmA, tmW, tmA, tmA, tmA, p, st);
 }
 
 int gemm_tc(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N, int K, int dtype,

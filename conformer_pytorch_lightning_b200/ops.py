@@ -165,6 +165,26 @@ def ffn_chain(y_in, a, b, x, y_out, *, y_row_valid=None, proj=None, hidden_ws=No
                                   _stream(x)))
 
 
+def ctc_argmax(x, w, bias, *, want_best=False, engine=N.ENGINE_AUTO):
+    """Frame-wise argmax of x w^T + bias over the vocabulary (see cfm_ctc_argmax): x (M,d), w (V,d) same dtype, bias (V)
+    fp32 or None.  Returns ids (M,) int32 [, best (M,) fp32]."""
+    _req(x, "ctc_argmax.x")
+    _req(w, "ctc_argmax.w", x.dtype)
+    M, d = x.shape
+    V = w.shape[0]
+    if w.shape != (V, d):
+        raise RuntimeError("ctc_argmax: shape mismatch")
+    if bias is not None:
+        _req(bias, "ctc_argmax.bias", torch.float32)
+    ensure_init(x)
+    ids = torch.empty(M, dtype=torch.int32, device=x.device)
+    best = torch.empty(M, dtype=torch.float32, device=x.device) if want_best else None
+    ws = torch.empty(max(int(N.lib().cfm_ctc_ws_bytes(M, V, _DT[x.dtype])), 8), dtype=torch.uint8, device=x.device)
+    N.check(N.lib().cfm_ctc_argmax(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), M, V, d, _DT[x.dtype], ids.data_ptr(),
+                                   _ptr(best), ws.data_ptr(), engine, _stream(x)))
+    return (ids, best) if want_best else ids
+
+
 def attention(q, k, v, out, *, mask=None, key_bias=None, scale, engine=N.ENGINE_AUTO):
     """q (B,Tq,H,64), k/v (B,Tk,H,64) views with contiguous (H,64) tail; out (B,Tq,H*64) contiguous.
     mask: uint8/bool (Bm,R,Tk) with Bm in {1,B}, R in {1,Tq}; None = unmasked."""

@@ -209,6 +209,18 @@ int cfm_conv_module(const void* y, const void* W1, const float* b1, const float*
                     void* glu_ws, void* dw_ws, int engine, void* stream);
 
 /*
+ * CTC head, greedy part (scope row f2): ids[m] = argmax_v (x[m,:] . W[v,:] + bias[v]), the first index of the maximum;
+ * best[m] (optional) = that logit.  W: (V,d) act dtype = ctc_lo.weight (decoder.py:14), bias (V) fp32 or NULL,
+ * x: (M,d) act dtype with row stride ldx.  Greedy decoding is this argmax followed by collapsing repeats and dropping
+ * blank 0 on the host.  On the tcgen05 engine (bf16, d % 64 == 0, M >= 64) the (M,V) logits are never written: the
+ * GEMM epilogue reduces each tile to per-row (max, argmax) pairs and combines tiles with a 64-bit atomicMax.  The
+ * CUDA-core engine goes through the logit workspace in chunks of 1024 rows.  ws: cfm_ctc_ws_bytes(M, V, dtype) bytes.
+ */
+int64_t cfm_ctc_ws_bytes(int M, int V, int dtype);
+int cfm_ctc_argmax(const void* x, int ldx, const void* W, const float* bias, int M, int V, int d, int dtype,
+                   int32_t* ids, float* best, void* ws, int engine, void* stream);
+
+/*
  * BatchNorm1d training-mode pieces (convolution.py:44): statistics over all B*T rows, unmasked.
  *   cfm_bn_stats : sum[c] = sum_r x[r,c], sumsq[c] = sum_r (x[r,c])^2   (x fp32 (rows,d); outputs must be zeroed)
  *   cfm_bn_apply_silu : y = silu((x-mean)*rstd*gamma+beta) in act dtype

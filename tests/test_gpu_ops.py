@@ -556,3 +556,48 @@ def test_native_subsampling_frontend(B, Tin, C):
     got = out.float().permute(0, 3, 1, 2)          # (B, C, T2, F2)
     assert torch.isfinite(got).all()
     assert rel_err(got, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("M,V,d", [(15872, 5002, 256), (333, 5002, 256), (64, 300, 256), (1000, 5002, 512), (37, 5002, 256)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_ctc_argmax(M, V, d, dt):
+    """ctc_lo projection + frame argmax without materialising the logits (tcgen05) / through the chunked workspace
+    (CUDA cores) vs torch on the same operands."""
+    x = rnd(M, d, dtype=dt)
+    w = rnd(V, d, dtype=dt, scale=1 / math.sqrt(d), seed=1)
+    b = rnd(V, seed=2) * 0.1
+    logits = x.float() @ w.float().t() + b
+    ref_best, ref_ids = logits.max(dim=1)
+    for eng in ((N.ENGINE_AUTO, N.ENGINE_SIMT) if dt == torch.bfloat16 else (N.ENGINE_SIMT,)):
+        ids, best = ops.ctc_argmax(x, w, b, want_best=True, engine=eng)
+        ids = ids.long()
+        assert ids.min() >= 0 and ids.max() < V
+        picked = logits.gather(1, ids[:, None])[:, 0]
+        # the chosen column must be a maximiser up to accumulation-order / bf16-logit noise
+        on_tc = dt == torch.bfloat16 and eng != N.ENGINE_SIMT and M >= 64      # else: logits rounded to the act dtype
+        tol = 1e-4 if (dt == torch.float32 or on_tc) else 3e-2
+        assert float((ref_best - picked).max()) <= tol * float(ref_best.abs().max() + 1), eng
+        agree = float((ids == ref_ids).float().mean())
+        assert agree > (0.999 if tol == 1e-4 else 0.9), (eng, agree)
+        if on_tc or dt == torch.float32:
+            assert rel_err(best, picked) < 1e-3
+
+
+def test_ctc_greedy_head_matches_oracle_decode():
+    from conformer_pytorch_lightning_b200 import CTCGreedyHead
+    torch.manual_seed(0)
+    head = CTCGreedyHead(256, 5002).to(DEV)
+    hs = rnd(3, 50, 256, seed=7)
+    lens = [50, 31, 7]
+    with torch.no_grad():
+        ids, hyps = head.greedy(hs, lens)
+        logits = hs @ head.ctc_lo.weight.t() + head.ctc_lo.bias
+    want_ids = logits.argmax(-1)
+    assert float((ids == want_ids).float().mean()) > 0.999
+    for b, n in enumerate(lens):
+        seq, prev = [], -1
+        for t in ids[b, :n].tolist():
+            if t != prev and t != 0:
+                seq.append(t)
+            prev = t
+        assert hyps[b] == seq

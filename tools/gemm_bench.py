@@ -154,9 +154,23 @@ def mhsa_bench(B=64, T=248, H=4, d=256):
     print(f"attention + Wo/LN GEMM       : {t:7.1f} us ({fl / t / 1e6:6.1f} TF/s)")
 
 
+def ctc_bench(M=15872, V=5002, d=256):
+    dev = "cuda"
+    x = torch.randn(M, d, device=dev).bfloat16()
+    w = (torch.randn(V, d, device=dev) / 16).bfloat16(); b = torch.randn(V, device=dev) * 0.1
+    fl = 2.0 * M * V * d
+    t = timeit(lambda: ops.ctc_argmax(x, w, b), iters=5, per_graph=4)
+    print(f"ctc_argmax fused (M={M}, V={V}): {t:7.1f} us ({fl / t / 1e6:6.1f} TF/s)")
+    t = timeit(lambda: (torch.nn.functional.linear(x, w) + b).argmax(-1), iters=5, per_graph=4)
+    print(f"torch linear + bias + argmax  : {t:7.1f} us")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         small_kernels()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ctc":
+        ctc_bench()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mhsa":
         mhsa_bench()
