@@ -63,6 +63,15 @@ def test_ctc_greedy_ids_bit_exact_fp32():
     torch.backends.cuda.matmul.allow_tf32 = False
     best = torch.nn.functional.linear(out, w, b).argmax(-1).cpu().numpy().astype(np.int16)
     assert np.array_equal(best, c["best"])
+    # the native CTC head (fp32 path: CUDA-core GEMM through the chunked logit workspace) must give the same frame ids
+    from conformer_pytorch_lightning_b200 import CTCGreedyHead
+    head = CTCGreedyHead(256, 5002).cuda()
+    with torch.no_grad():
+        head.ctc_lo.weight.copy_(w)
+        head.ctc_lo.bias.copy_(b)
+        ids, hyps = head.greedy(out, mask[:, 0, :].sum(-1))
+    assert np.array_equal(ids.cpu().numpy().astype(np.int16), c["best"])
+    assert len(hyps) == out.shape[0]
     # bf16: report the agreement rate (reference's own bf16 agrees with its fp32 on ~94 % of frames, D9)
     _, outb, _ = _run_forward(g, torch.bfloat16)
     bestb = torch.nn.functional.linear(outb, w, b).argmax(-1).cpu().numpy().astype(np.int16)
@@ -70,6 +79,12 @@ def test_ctc_greedy_ids_bit_exact_fp32():
     rate = float((bestb == c["best"])[valid].mean())
     print(f"bf16 CTC frame-id agreement with the fp32 reference: {rate:.4f}")
     assert rate > 0.85
+    head.compute_dtype = torch.bfloat16                   # tcgen05 GEMM with the argmax epilogue
+    with torch.no_grad():
+        idsb = head.frame_ids(outb).cpu().numpy().astype(np.int16)
+    rate_native = float((idsb == c["best"])[valid].mean())
+    print(f"bf16 encoder + native bf16 CTC head agreement with the fp32 reference: {rate_native:.4f}")
+    assert rate_native > 0.85
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
