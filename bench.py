@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="measured path only (for ncu): no e2e / probe / cpu legs")
     args = ap.parse_args()
