@@ -283,8 +283,8 @@ def run_ours(args):
     # compute of the current one on separate streams).  Every step copies its fbank batch host->device and its
     # encoder output device->host inside the timed region; wall clock from the first submit to the last delivery.
     from conformer_pytorch_lightning_b200 import EncoderPipeline
-    pipe = EncoderPipeline(enc, depth=2)
-    outs = [torch.empty((B, T, cfg["encoder_dim"]), dtype=torch.float32).pin_memory() for _ in range(3)]
+    pipe = EncoderPipeline(enc, depth=int(os.environ.get("CFM_B200_PIPE_DEPTH", "2")))
+    outs = [torch.empty((B, T, cfg["encoder_dim"]), dtype=torch.float32).pin_memory() for _ in range(4)]
     lens_host = torch.from_numpy(lens_np)
     e2e_steps = max(8, args.steps)
     for _ in pipe.stream(((feats_host, lens_host) for _ in range(3)), outs):
