@@ -93,12 +93,12 @@ class ConformerEncoder(nn.Module):
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype)
+                engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype, inplace=True)
             cur.wait_stream(side)
             g = torch.cuda.CUDAGraph()
             n0 = _native.launch_count()
             with torch.cuda.graph(g):
-                out_s, _ = engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype)
+                out_s, _ = engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype, inplace=True)
             plan.update(graph=g, x=x_s, am=am_s, pm=pm_s, out=out_s, launches=_native.launch_count() - n0)
         ver = self._weights_version()
         if plan.get("ver") != ver:            # in-place refresh of stale derived weights (bf16 copies, folded BN)

@@ -281,18 +281,22 @@ def _row_valid(pad_mask, B, T):
     return m.view(B * T)
 
 
-def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_caches, want_cache, dtype):
+def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_caches, want_cache, dtype, inplace=False):
     """Layer loop of encoder.py:72-74 / 109-118.
 
-    inputs (B,T,d) fp32 (not modified); layers: list of ConformerEncoderLayer; after_norm: LayerNorm
+    inputs (B,T,d) fp32 (not modified unless ``inplace``: the CUDA-graph plans run on their own static input buffer, which
+    then doubles as the residual stream); layers: list of ConformerEncoderLayer; after_norm: LayerNorm
     module or None; attn_caches: list (one per layer) of (B,H,C,128) tensors or None.
     Returns (out (B,T,d) fp32 fresh tensor, [new caches])."""
     B, T, d = inputs.shape
     n = B * T
     dev = inputs.device
     ws = thread_workspace()
-    x = torch.empty((n, d), dtype=torch.float32, device=dev)
-    x.copy_(inputs.reshape(n, d))
+    if inplace and inputs.dtype == torch.float32 and inputs.is_contiguous():
+        x = inputs.view(n, d)
+    else:
+        x = torch.empty((n, d), dtype=torch.float32, device=dev)
+        x.copy_(inputs.reshape(n, d))
     y = ws.get("ln_y", (n, d), dtype, dev)
     y2 = ws.get("ln_y2", (n, d), dtype, dev)
     row_valid = _row_valid(pad_mask, B, T)
