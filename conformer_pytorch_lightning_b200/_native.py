@@ -19,7 +19,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 # every symbol include/cfm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
+    "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_kernel_launches", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
     "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax",
 ]
@@ -36,6 +36,8 @@ def _declare(lib):
     lib.cfm_last_error.restype = ctypes.c_char_p
     lib.cfm_init.argtypes = [_i]
     lib.cfm_launch_count.restype = _i64
+    lib.cfm_kernel_launches.argtypes = [ctypes.c_char_p]
+    lib.cfm_kernel_launches.restype = _i64
     lib.cfm_layernorm.argtypes = [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _f, _p]
     lib.cfm_gemm.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _p, _i, _p]
     lib.cfm_gemm_ln.argtypes = [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _f, _i, _p]
@@ -59,7 +61,7 @@ def _declare(lib):
     lib.cfm_subsample_conv.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes"):
+        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_kernel_launches", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes"):
             fn.restype = _i
 
 
@@ -94,3 +96,8 @@ def init(device_index):
 
 def launch_count():
     return int(lib().cfm_launch_count())
+
+
+def kernel_launches(name):
+    """Launches of one kernel family ("ffn_fused", "mhsa_fused", ...) issued through the library so far."""
+    return int(lib().cfm_kernel_launches(name.encode()))

@@ -9,6 +9,23 @@ namespace cfm {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
+// per-kernel launch counters: a small append-only table of (literal name, count)
+struct KernelCounter { std::atomic<const char*> name{nullptr}; std::atomic<int64_t> n{0}; };
+static KernelCounter g_kernels[96];
+
+void count_launch(const char* name) {
+  g_launches.fetch_add(1);
+  for (auto& k : g_kernels) {
+    const char* cur = k.name.load(std::memory_order_acquire);
+    if (cur == nullptr) {
+      const char* expected = nullptr;
+      if (k.name.compare_exchange_strong(expected, name, std::memory_order_acq_rel)) cur = name;
+      else cur = expected;
+    }
+    if (cur == name || strcmp(cur, name) == 0) { k.n.fetch_add(1, std::memory_order_relaxed); return; }
+  }
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -21,6 +38,16 @@ void set_error(const char* fmt, ...) {
 extern "C" int cfm_abi_version(void) { return CFM_ABI_VERSION; }
 extern "C" const char* cfm_last_error(void) { return cfm::g_err; }
 extern "C" int64_t cfm_launch_count(void) { return cfm::g_launches.load(); }
+extern "C" int64_t cfm_kernel_launches(const char* name) {
+  if (name == nullptr) return -1;
+  int64_t total = 0;
+  for (auto& k : cfm::g_kernels) {
+    const char* cur = k.name.load(std::memory_order_acquire);
+    if (cur == nullptr) break;
+    if (strcmp(cur, name) == 0) total += k.n.load();
+  }
+  return total;
+}
 
 extern "C" int cfm_init(int device) {
   using namespace cfm;

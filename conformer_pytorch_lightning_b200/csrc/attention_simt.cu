@@ -126,7 +126,7 @@ int attention_simt(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int
     if (rpw == 2) CFM_ATTN_SIMT(__nv_bfloat16, 2); else CFM_ATTN_SIMT(__nv_bfloat16, 8);
   }
 #undef CFM_ATTN_SIMT
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("attention_simt");
   return 0;
 }
 

@@ -357,7 +357,7 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + QT - 1) / QT, H, B);
   CFM_CUDA_OK(launch_pdl(attention_tc_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("attention_tc");
   return 0;
 }
 

@@ -33,10 +33,12 @@ extern std::atomic<int64_t> g_launches;
     }                                                                                \
   } while (0)
 
-// every kernel launch goes through this so that bench.py can report `gpu_launches`
-#define CFM_LAUNCHED()                                  \
+// every kernel launch goes through this so that bench.py can report `gpu_launches`; the per-kernel counters
+// (cfm_kernel_launches("ffn_fused") ...) let the tests assert WHICH engine served a call
+void count_launch(const char* name);
+#define CFM_LAUNCHED_K(name)                            \
   do {                                                  \
-    ::cfm::g_launches.fetch_add(1);                     \
+    ::cfm::count_launch(name);                          \
     CFM_CUDA_OK(cudaPeekAtLastError());                 \
   } while (0)
 

@@ -336,7 +336,7 @@ int conv_fused(const void* y_in, const void* W1, const float* b1, const float* d
   const int n_tiles = (M + ROWS - 1) / ROWS;
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   CFM_CUDA_OK(launch_pdl(conv_fused_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmYin, tmW1, tmW2, tmX, tmX, tmYout, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("conv_fused");
   return 0;
 }
 

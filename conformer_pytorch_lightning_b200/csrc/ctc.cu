@@ -77,7 +77,7 @@ extern "C" int cfm_ctc_argmax(const void* x, int ldx, const void* W, const float
     int rc = gemm_tc_argmax(x, ldx, W, bias, M, V, d, keys, st);
     if (rc != 0) return rc;
     ctc_unpack_kernel<<<(M + 255) / 256, 256, 0, st>>>(keys, ids, best, M);
-    CFM_LAUNCHED();
+    CFM_LAUNCHED_K("ctc_unpack");
     return 0;
   }
   const size_t esz = dtype == CFM_BF16 ? 2 : 4;
@@ -92,7 +92,7 @@ extern "C" int cfm_ctc_argmax(const void* x, int ldx, const void* W, const float
     else
       ctc_argmax_rows_kernel<float><<<(rows + 7) / 8, 256, 0, st>>>((const float*)ws, V, rows, V, ids + m0,
                                                                     best ? best + m0 : nullptr);
-    CFM_LAUNCHED();
+    CFM_LAUNCHED_K("ctc_argmax_rows");
   }
   return 0;
 }

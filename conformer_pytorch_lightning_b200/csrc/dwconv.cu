@@ -134,7 +134,7 @@ int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, 
   if (k == 15) CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 15, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
   else if (k == 31) CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 31, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
   else CFM_CUDA_OK(launch_pdl(dwconv_kernel<T, 0, SILU>, grid, dim3(128), smem, st, 1, xx, w, bias, y, Tlen, d, k));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("dwconv");
   return 0;
 }
 
@@ -236,7 +236,7 @@ extern "C" int cfm_bn_stats(const float* x, int rows, int d, float* sum, float* 
   if (rows <= 0) return 0;
   dim3 grid((d + 63) / 64, max(1, min((rows + 255) / 256, 4 * num_sms())));
   bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, sum, sumsq);
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("bn_stats");
   return 0;
 }
 
@@ -254,7 +254,7 @@ extern "C" int cfm_bn_apply_silu(const float* x, int rows, int d, const float* m
   else
     bn_apply_silu_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n4, d, mean, rstd, gamma, beta,
                                                                                 (__nv_bfloat16*)y);
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("bn_apply_silu");
   return 0;
 }
 
@@ -273,6 +273,6 @@ extern "C" int cfm_relpos_keys(const void* k, int64_t k_bs, int64_t k_ts, const 
   else
     relpos_keys_kernel<__nv_bfloat16><<<blocks, 128, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)k, k_bs, k_ts, (const __nv_bfloat16*)p, p_bs, u, vb, (__nv_bfloat16*)k_out, key_bias, B, H, Tk);
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("relpos_keys");
   return 0;
 }

@@ -580,7 +580,7 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   else
     CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],
                            tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("ffn_fused");
   return 0;
 }
 

@@ -321,7 +321,7 @@ int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, ffn_pair_kernel, tmA, tmW1, tmW2, tmX, tmX, tmY, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("ffn_pair");
   return 0;
 }
 

@@ -210,7 +210,7 @@ int launch(const void* A, int lda, const void* W, const float* bias, void* C, in
       case CFM_EPI_BIAS_GLU: launch_skinny<T, CFM_EPI_BIAS_GLU>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
       default: launch_skinny<T, CFM_EPI_RESIDUAL>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
     }
-    CFM_LAUNCHED();
+    CFM_LAUNCHED_K("gemm_skinny");
     return 0;
   }
   switch (epi) {
@@ -227,7 +227,7 @@ int launch(const void* A, int lda, const void* W, const float* bias, void* C, in
       gemm_simt_kernel<T, CFM_EPI_RESIDUAL><<<grid, 256, 0, st>>>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv);
       break;
   }
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("gemm_simt");
   return 0;
 }
 

@@ -365,7 +365,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();
   CFM_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmA, tmW, tmC, tmR, tmY, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("gemm_tc");
   return 0;
 }
 

@@ -86,7 +86,7 @@ int launch_ln(const float* x, int rows, const float* g1, const float* b1, float*
   else
     CFM_CUDA_OK(launch_pdl(layernorm_kernel<NV, __nv_bfloat16>, dim3(blocks), dim3(256), 0, st, 1, x, rows, g1, b1, x_out,
                            g2, b2, (__nv_bfloat16*)y, rv, eps));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("layernorm");
   return 0;
 }
 

@@ -455,7 +455,7 @@ int mhsa_fused(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t
   if (const char* e = getenv("CFM_B200_MHSA_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   dim3 grid((T + QT - 1) / QT, B);
   CFM_CUDA_OK(launch_pdl(mhsa_fused_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, tmWo, tmX, tmX, tmY, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("mhsa_fused");
   return 0;
 }
 

@@ -589,7 +589,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
     const int total = B * fp.tiles_per_utt;
     const int grid = total < num_sms() ? total : num_sms();
     CFM_CUDA_OK(launch_pdl(subsample_fused_kernel, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
-    CFM_LAUNCHED();
+    CFM_LAUNCHED_K("subsample_fused");
     return 0;
   }
   {
@@ -600,7 +600,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
     CFM_CHECK_ARG(sm <= 48 * 1024, "cfm_subsample_conv: idim=%d too large", idim);
     CFM_CUDA_OK(launch_pdl(subsample_conv1_kernel, grid, dim3(kC1Warps * 32), sm, st, 1, x, w1, b1, (__nv_bfloat16*)ws, B, Tin,
                            idim, C, T1, F1, T1h, F1h));
-    CFM_LAUNCHED();
+    CFM_LAUNCHED_K("subsample_conv1");
   }
   CUtensorMap tmP, tmW, tmO;
   int rc;
@@ -631,6 +631,6 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
   const int total = B * p.tiles_per_utt * p.n_blocks;
   const int grid = total < num_sms() ? total : num_sms();
   CFM_CUDA_OK(launch_pdl(subsample_conv2_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmP, tmW, tmO, p));
-  CFM_LAUNCHED();
+  CFM_LAUNCHED_K("subsample_conv2");
   return 0;
 }

@@ -53,6 +53,9 @@ const char* cfm_last_error(void);
 int         cfm_init(int device);
 /* number of kernel launches issued through this library by the calling process (for bench `gpu_launches`) */
 int64_t     cfm_launch_count(void);
+/* launches of one kernel family by name ("ffn_fused", "mhsa_fused", "conv_fused", "gemm_tc", "attention_tc", ...):
+ * lets a caller (and the parity tests) verify which engine served its calls; 0 for unknown names */
+int64_t     cfm_kernel_launches(const char* name);
 
 /*
  * LayerNorm (+ optional second LayerNorm, + optional row mask).  Replaces nn.LayerNorm calls

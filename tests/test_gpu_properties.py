@@ -1,6 +1,6 @@
-"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (no oracle needed, the oracle cannot
-finish these sizes in seconds): utterance independence, batch-permutation equivariance, chunk-mask causality,
-padding invariance, determinism.  pytest -m gpu."""
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes: utterance independence, batch-permutation
+equivariance, chunk-mask causality, padding invariance, determinism.  (Oracle parity at the same full sizes is in
+tests/test_gpu_fullsize_parity.py.)  pytest -m gpu."""
 import numpy as np
 import pytest
 import torch

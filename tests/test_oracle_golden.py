@@ -136,3 +136,39 @@ def test_torch_cpu_port_matches_reference(name):
     t = torch.from_numpy
     out = OT.encoder_layers(t(g["embed_out"]), t(g["attn_mask"]), t(g["pos_embed"]), t(g["pad_mask"]), sd, g["cfg"])
     assert max_rel(out.numpy(), g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["m12_pad", "m3_static16", "l2_pad", "m12_c1_wav"])
+def test_torch_cpu_port_full_forward_matches_reference(name):
+    """The port's full forward (front-end + masks + layers), which is the checker of the full-size GPU parity tests
+    (tests/test_gpu_fullsize_parity.py), reproduces the reference's outputs -- also when run in utterance groups."""
+    import torch
+    from oracle import conformer_oracle_torch as OT
+    g = load_golden(name)
+    sd = OT.to_torch_sd(O.make_state_dict(g["cfg"], g["weight_seed"]))
+    out, pad, attn, x, pos = OT.encoder_forward(torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"]), sd, g["cfg"],
+                                                batch_chunk=2)
+    assert np.array_equal(pad.numpy(), g["out_mask"]) and np.array_equal(attn.numpy(), g["attn_mask"])
+    assert max_rel(x.numpy(), g["embed_out"]) < TOL and max_rel(pos.numpy(), g["pos_embed"]) < 1e-6
+    assert max_rel(out.numpy(), g["out"]) < TOL
+
+
+def test_torch_cpu_port_training_forward():
+    """Training-mode port (BatchNorm batch statistics + running-stat updates) against the reference's golden."""
+    import torch
+    from oracle import conformer_oracle_torch as OT
+    g = load_golden("m3_train_fwd")
+    cfg = g["cfg"]
+    sd = OT.to_torch_sd(O.make_state_dict(cfg, g["weight_seed"]))
+    x, pos, pad, attn = OT.encoder_embed(torch.from_numpy(g["feats"]), torch.from_numpy(g["lens"]), sd, cfg)
+    st = [{"running_mean": sd[f"encoders.{i}.conv_module.norm.running_mean"].clone(),
+           "running_var": sd[f"encoders.{i}.conv_module.norm.running_var"].clone(), "num_batches_tracked": 3}
+          for i in range(cfg["encoder_num_layers"])]
+    with torch.no_grad():
+        out = OT.encoder_layers_train(x, attn, pos, pad, sd, cfg, bn_states=st)
+    assert max_rel(out.numpy(), g["out"]) < TOL
+    for i, s in enumerate(st):
+        key = f"encoders__{i}__conv_module__norm__"
+        assert max_rel(s["running_mean"].numpy(), g[key + "running_mean"]) < 1e-5
+        assert max_rel(s["running_var"].numpy(), g[key + "running_var"]) < 1e-5
+        assert s["num_batches_tracked"] == 4
