@@ -20,25 +20,33 @@ def _sincos_table(max_len, d_model):
 
 class _PositionTable(nn.Module):
     """The reference keeps ``pe`` as a plain attribute and re-casts it *in place* to the dtype of
-    every input, so one bf16 call permanently degrades the table.  Here the fp32
-    master table is immutable and per-(device,dtype) casts are cached."""
+    every input, so one bf16 call permanently degrades the table.  Here the master table is immutable
+    (a non-persistent buffer: it follows ``.to(device)`` and stays out of the state_dict) and per-(device, dtype)
+    casts are cached; there is no per-call mutable state (callable from any thread)."""
 
     def __init__(self, d_model, dropout, max_len, table_dtype):
         super().__init__()
         self.dropout = nn.Dropout(p=dropout)
-        self.pe = _sincos_table(max_len, d_model).to(table_dtype)
+        self.register_buffer("pe", _sincos_table(max_len, d_model).to(table_dtype), persistent=False)
         self._cast = {}
 
-    def _table(self, like):
-        key = (like.device, like.dtype)
+    def _table(self, device, dtype):
+        if device == self.pe.device and dtype == self.pe.dtype:
+            return self.pe
+        key = (device, dtype)
         t = self._cast.get(key)
-        if t is None:
-            t = self._cast[key] = self.pe.to(like.device).to(like.dtype)
+        if t is None or t.data_ptr() == 0:
+            t = self._cast[key] = self.pe.to(device).to(dtype)
         return t
 
-    def position_encoding(self, offset, size, apply_dropout=True):
-        ref = getattr(self, "_last_like", self.pe)
-        pos_embed = self._table(ref)[offset: offset + size]
+    def _apply(self, fn, *args, **kwargs):
+        self._cast = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def position_encoding(self, offset, size, apply_dropout=True, like=None):
+        """``like``: tensor whose device / dtype the slice should have (default: the table's own fp32 / fp16)."""
+        table = self.pe if like is None else self._table(like.device, like.dtype)
+        pos_embed = table[offset: offset + size]
         if apply_dropout:
             pos_embed = self.dropout(pos_embed)
         return pos_embed
@@ -51,8 +59,7 @@ class RelativePositionalEncoding(_PositionTable):
         super().__init__(d_model, dropout, max_len, torch.float32)
 
     def forward(self, inputs, offset=0):
-        self._last_like = inputs
-        pos_embed = self.position_encoding(offset, inputs.size(0), False)
+        pos_embed = self.position_encoding(offset, inputs.size(0), False, like=inputs)
         return self.dropout(inputs), self.dropout(pos_embed)
 
 
@@ -63,10 +70,15 @@ class PositionalEncoding(_PositionTable):
         super().__init__(d_model, dropout, max_len, torch.float16)
 
     def forward(self, inputs, offset=0):
-        self._last_like = inputs
-        pos_embed = self.position_encoding(offset, inputs.size(0), False)
+        pos_embed = self.position_encoding(offset, inputs.size(0), False, like=inputs)
         x = inputs + pos_embed
         return self.dropout(x), self.dropout(pos_embed)
+
+
+def _check_head_dim(encoder_dim, num_heads):
+    if encoder_dim % num_heads != 0 or encoder_dim // num_heads != 64:
+        raise ValueError(f"the native attention kernels are specialised for a head dimension of 64 (Conformer-M: 256/4, "
+                         f"Conformer-L: 512/8); got encoder_dim={encoder_dim}, num_heads={num_heads}")
 
 
 class _MHSABase(nn.Module):
@@ -96,6 +108,7 @@ class RelativeMultiHeadSelfAttentionModule(_MHSABase):
 
     def __init__(self, encoder_dim, num_heads, dropout):
         super().__init__()
+        _check_head_dim(encoder_dim, num_heads)
         self.d_k = encoder_dim // num_heads
         self.num_heads = num_heads
         self.linear_pos = nn.Linear(encoder_dim, encoder_dim, bias=False)
@@ -119,6 +132,7 @@ class MultiHeadSelfAttentionModule(_MHSABase):
 
     def __init__(self, encoder_dim, num_heads, dropout):
         super().__init__()
+        _check_head_dim(encoder_dim, num_heads)
         self.d_k = encoder_dim // num_heads
         self.num_heads = num_heads
         self.linear_k = nn.Linear(encoder_dim, encoder_dim)

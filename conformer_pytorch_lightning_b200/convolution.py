@@ -81,8 +81,8 @@ class ConvolutionSubSampling(nn.Module):
 
     # (the PyTorch paths above remain the fp32 / tiny-input / training implementation)
 
-    def position_encoding(self, offset, size):
-        return self.pos_enc.position_encoding(offset, size)
+    def position_encoding(self, offset, size, like=None):
+        return self.pos_enc.position_encoding(offset, size, like=like)
 
     # ------------------------------------------------------------------ native bf16 front-end (scope row f1)
     def _native_ok(self, inputs):

@@ -51,14 +51,18 @@ extern "C" int64_t cfm_kernel_launches(const char* name) {
 
 extern "C" int cfm_init(int device) {
   using namespace cfm;
-  CFM_CUDA_OK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CFM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  CFM_CHECK_ARG(prop.major == 10, "cfm_init: device %d is sm_%d%d; this library is built for sm_100a only",
-                device, prop.major, prop.minor);
+  // per-device setup (shared-memory opt-ins are per device); the caller's current device is restored
+  int prev = 0;
+  CFM_CUDA_OK(cudaGetDevice(&prev));
+  int major = 0, minor = 0;
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  CFM_CHECK_ARG(major == 10, "cfm_init: device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
+  if (prev != device) CFM_CUDA_OK(cudaSetDevice(device));
   int rc = gemm_tc_init();
-  if (rc != 0) return rc;
-  return attention_tc_init();
+  if (rc == 0) rc = attention_tc_init();
+  if (prev != device) cudaSetDevice(prev);
+  return rc;
 }
 
 extern "C" int cfm_gemm(const void* A, int lda, const void* W, const float* bias, void* C, int ldc, int M, int N,
@@ -127,11 +131,7 @@ extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1
     CFM_CHECK_ARG(fused_ok, "cfm_ffn: fused tcgen05 path does not support M=%d d=%d F=%d dtype=%d", M, d, F, dtype);
   if (fused_ok && engine != CFM_ENGINE_SIMT) {
     // CFM_B200_FFN_MODE: "pair" = tcgen05 cta_group::2 kernel (ffn_pair.cu), anything else = ffn_fused.cu
-    static int pair_mode = -1;
-    if (pair_mode < 0) {
-      const char* e = getenv("CFM_B200_FFN_MODE");
-      pair_mode = (e && strcmp(e, "pair") == 0) ? 1 : 0;
-    }
+    static const bool pair_mode = env_is("CFM_B200_FFN_MODE", "pair");
     if (pair_mode)
       return ffn_pair(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
                       eps, (cudaStream_t)stream);
@@ -161,11 +161,7 @@ extern "C" int cfm_mhsa_out(const void* q, int64_t q_bs, int64_t q_ts, const voi
   if (B == 0 || Tq == 0) return 0;
   const int d = H * 64, M = B * Tq;
   // CFM_B200_MHSA_MODE: "unfused" = always attention kernel + residual GEMM
-  static int unfused_mode = -1;
-  if (unfused_mode < 0) {
-    const char* e = getenv("CFM_B200_MHSA_MODE");
-    unfused_mode = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
-  }
+  static const bool unfused_mode = env_is("CFM_B200_MHSA_MODE", "unfused");
   const bool fused_ok = scale > 0.f && mhsa_fused_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, d, dtype,
                                                             key_bias != nullptr);
   if (engine == CFM_ENGINE_TC)
@@ -196,11 +192,7 @@ extern "C" int cfm_conv_module(const void* y, const void* W1, const float* b1, c
   const int M = B * T;
   if (M == 0) return 0;
   // CFM_B200_CONV_MODE: "unfused" = always the three-kernel chain
-  static int unfused_mode = -1;
-  if (unfused_mode < 0) {
-    const char* e = getenv("CFM_B200_CONV_MODE");
-    unfused_mode = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
-  }
+  static const bool unfused_mode = env_is("CFM_B200_CONV_MODE", "unfused");
   const bool fused_ok = conv_fused_supported(M, T, d, k, dtype);
   if (engine == CFM_ENGINE_TC)
     CFM_CHECK_ARG(fused_ok, "cfm_conv_module: fused tcgen05 path does not support T=%d d=%d k=%d dtype=%d", T, d, k, dtype);
@@ -232,11 +224,7 @@ extern "C" int cfm_ffn_chain(const void* y, int M, int d, int F, int dtype, cons
   CFM_CHECK_ARG(M >= 0 && d > 0 && F > 0, "cfm_ffn_chain: bad shape");
   if (M == 0) return 0;
   // CFM_B200_FFN_CHAIN=0: always separate cfm_ffn / cfm_gemm calls
-  static int chain_off = -1;
-  if (chain_off < 0) {
-    const char* e = getenv("CFM_B200_FFN_CHAIN");
-    chain_off = (e && e[0] == '0') ? 1 : 0;
-  }
+  static const bool chain_off = env_is("CFM_B200_FFN_CHAIN", "0");
   const FfnModule a{W1a, b1a, W2a, b2a, alpha_a, g1a, be1a, g2a, be2a};
   const FfnModule b{W1b, b1b, W2b, b2b, alpha_b, g1b, be1b, g2b, be2b};
   const bool ok = (dtype == CFM_BF16) && ffn_chain_supported(M, d, F, dtype, has_a ? &a : nullptr, b, Wp ? Np : 0);

@@ -330,9 +330,8 @@ bool attention_tc_supported(int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_
 }
 
 int attention_tc_init() {
-  return cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess
-             ? 0
-             : (set_error("cudaFuncSetAttribute(attention_tc_kernel) failed"), -2);
+  CFM_SMEM_OPT_IN(attention_tc_kernel, kSmemBytes);      // per device: cfm_init runs once per device
+  return 0;
 }
 
 int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts, const void* v,

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/cfm_b200.h"
 
@@ -113,14 +114,31 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CFM_B200_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
+// environment switches are read once per process (thread-safe function-local statics)
+inline bool env_is(const char* name, const char* value) {
+  const char* e = getenv(name);
+  return e != nullptr && strcmp(e, value) == 0;
 }
+inline bool pdl_enabled() {
+  static const bool v = !env_is("CFM_B200_PDL", "0");
+  return v;
+}
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+// cudaFuncSetAttribute is a PER-DEVICE setting: remember which devices of this process already have it
+#define CFM_SMEM_OPT_IN(kernel, bytes)                                                                        \
+  do {                                                                                                        \
+    static std::atomic<unsigned long long> _done{0};                                                          \
+    const int _dev = ::cfm::current_device() & 63;                                                            \
+    if (!((_done.load(std::memory_order_acquire) >> _dev) & 1ull)) {                                          \
+      CFM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      _done.fetch_or(1ull << _dev, std::memory_order_release);                                                \
+    }                                                                                                         \
+  } while (0)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
@@ -150,12 +168,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  const int dev = current_device() & 63;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -318,11 +318,7 @@ bool conv_fused_supported(int M, int T, int d, int k, int dtype) {
 int conv_fused(const void* y_in, const void* W1, const float* b1, const float* dw_w, const float* dw_b, const void* W2,
                const float* b2, float* X, int M, int T, const uint8_t* row_valid, const float* g1, const float* be1,
                void* y_out, float eps, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  CFM_SMEM_OPT_IN(conv_fused_kernel, kSmemBytes);
   CUtensorMap tmYin, tmW1, tmW2, tmX, tmYout;
   int rc;
   if ((rc = make_map(&tmYin, false, y_in, M, D, D, 128)) != 0) return rc;

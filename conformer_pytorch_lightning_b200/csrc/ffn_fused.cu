@@ -538,13 +538,9 @@ bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, in
 static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n, float* X, int ldx, int M, int F,
                       void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st,
                       const void* Wp = nullptr, const float* bp = nullptr, void* P = nullptr, int Np = 0) {
-  static int cl_env = -1;
-  if (cl_env < 0) {
-    const char* e = getenv("CFM_B200_FFN_CLUSTER");
-    cl_env = (e && e[0] == '1') ? 1 : 2;
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  }
+  static const int cl_env = env_is("CFM_B200_FFN_CLUSTER", "1") ? 1 : 2;
+  CFM_SMEM_OPT_IN(ffn_fused_kernel<1>, kSmemBytes);
+  CFM_SMEM_OPT_IN(ffn_fused_kernel<2>, kSmemBytes);
   const int CL = cl_env;
   CUtensorMap tmA, tmW1[2], tmW2[2], tmX, tmY;
   int rc;

@@ -293,11 +293,7 @@ int make_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, in
 int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
              int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
              const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  CFM_SMEM_OPT_IN(ffn_pair_kernel, kSmemBytes);
   CUtensorMap tmA, tmW1, tmW2, tmX, tmY;
   int rc;
   if ((rc = make_map(&tmA, false, y_in, M, D, ld_in, 128)) != 0) return rc;

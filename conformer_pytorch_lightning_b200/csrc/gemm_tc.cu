@@ -356,11 +356,7 @@ template <int BN, int EPI>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
               const CUtensorMap& tmY, const GemmParams& p, cudaStream_t st) {
   using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
-  }
+  CFM_SMEM_OPT_IN((gemm_tc_kernel<BN, EPI>), C::kSmemBytes);
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
   const int grid = total < num_sms() ? total : num_sms();

@@ -412,11 +412,7 @@ int mhsa_fused(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t
                const void* Wo, const float* bo, float* X, const float* g1, const float* be1, void* Y,
                const uint8_t* y_row_valid, float eps, cudaStream_t st) {
   CFM_CHECK_ARG(scale > 0.f, "cfm_mhsa_out(tc): scale must be positive");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(mhsa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  CFM_SMEM_OPT_IN(mhsa_fused_kernel, kSmemBytes);
   CUtensorMap tmQ, tmK, tmV, tmWo, tmX, tmY;
   int rc;
   if ((rc = make_qkv_map(&tmQ, q, B, T, q_bs, q_ts)) != 0) return rc;

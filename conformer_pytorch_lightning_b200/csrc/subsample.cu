@@ -560,11 +560,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
   const int TL = 128 / F2;
   cudaStream_t st = (cudaStream_t)stream;
   // C == 256: conv1 is computed on the fly inside conv2 (CFM_B200_FRONTEND=unfused keeps the two-kernel path)
-  static int fe_unfused = -1;
-  if (fe_unfused < 0) {
-    const char* e = getenv("CFM_B200_FRONTEND");
-    fe_unfused = (e && strcmp(e, "unfused") == 0) ? 1 : 0;
-  }
+  static const bool fe_unfused = env_is("CFM_B200_FRONTEND", "unfused");
   if (!fe_unfused && C == 256 && tc::encode_tiled_fn() != nullptr) {
     CUtensorMap tmW, tmO;
     int rc;
@@ -581,11 +577,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
       if ((rc = make_map_nd(&tmO, out, 4, dims, str, box)) != 0) return rc;
     }
     FusedParams fp{x, w1, b1, b2, B, Tin, idim, T2, F2, TL, (T2 + TL - 1) / TL};
-    static bool fattr = false;
-    if (!fattr) {
-      CFM_CUDA_OK(cudaFuncSetAttribute(subsample_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-      fattr = true;
-    }
+    CFM_SMEM_OPT_IN(subsample_fused_kernel, kFusedSmem);
     const int total = B * fp.tiles_per_utt;
     const int grid = total < num_sms() ? total : num_sms();
     CFM_CUDA_OK(launch_pdl(subsample_fused_kernel, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
@@ -623,11 +615,7 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
     if ((rc = make_map_nd(&tmO, out, 4, dims, str, box)) != 0) return rc;
   }
   Conv2Params p{b2, B, C, T2, F2, TL, (T2 + TL - 1) / TL, C / 256};
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(subsample_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  CFM_SMEM_OPT_IN(subsample_conv2_kernel, kSmemBytes);
   const int total = B * p.tiles_per_utt * p.n_blocks;
   const int grid = total < num_sms() ? total : num_sms();
   CFM_CUDA_OK(launch_pdl(subsample_conv2_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmP, tmW, tmO, p));

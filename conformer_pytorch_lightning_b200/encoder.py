@@ -1,7 +1,7 @@
 """Drop-in for the reference's src/encoder.py (ConformerEncoder, :9-153)."""
-import os
-
+import collections
 import operator
+import os
 
 import torch
 import torch.nn as nn
@@ -42,7 +42,10 @@ class ConformerEncoder(nn.Module):
         self.compute_dtype = None
         # CUDA-graph plans of the measured path, one per (batch, frames, dtype, mask layout); see _graph_layers
         self.use_cuda_graphs = os.environ.get("CFM_B200_CUDA_GRAPHS", "1") != "0"
-        self._plans = {}
+        # least-recently-used plans are evicted beyond this many (a plan owns a graph + its static buffers; length-
+        # bucketed traffic has many shapes)
+        self.max_plans = int(os.environ.get("CFM_B200_MAX_PLANS", "16"))
+        self._plans = collections.OrderedDict()
 
     # ------------------------------------------------------------------ B200-specific knobs
     def set_compute_dtype(self, dtype):
@@ -78,11 +81,13 @@ class ConformerEncoder(nn.Module):
         key = (tuple(outputs.shape), dtype, outputs.device,
                None if attn_mask is None else tuple(attn_mask.shape),
                None if pad_u8 is None else tuple(pad_u8.shape), len(layers))
-        plan = self._plans.get(key)
+        plan = self._lookup_plan(key)
         if plan is None:
-            self._plans[key] = {"graph": None}
             out, _ = engine.run_layers(outputs.float(), layers, self.after_norm, attn_mask, None, pad_u8, None, False, dtype)
             return out
+        gen = self._derived_generation()
+        if plan["graph"] is not None and plan["gen"] != gen:
+            plan["graph"] = None              # derived weights were re-allocated: the graph holds stale addresses
         if plan["graph"] is None:
             x_s = torch.empty(outputs.shape, dtype=torch.float32, device=outputs.device)
             am_s = None if attn_mask is None else torch.empty(attn_mask.shape, dtype=torch.bool, device=outputs.device)
@@ -99,16 +104,35 @@ class ConformerEncoder(nn.Module):
             n0 = _native.launch_count()
             with torch.cuda.graph(g):
                 out_s, _ = engine.run_layers(x_s, layers, self.after_norm, am_s, None, pm_s, None, False, dtype, inplace=True)
-            plan.update(graph=g, x=x_s, am=am_s, pm=pm_s, out=out_s, launches=_native.launch_count() - n0)
+            plan.update(graph=g, x=x_s, am=am_s, pm=pm_s, out=out_s, launches=_native.launch_count() - n0,
+                        gen=self._derived_generation(), ver=None)
         ver = self._weights_version()
         if plan.get("ver") != ver:            # in-place refresh of stale derived weights (bf16 copies, folded BN)
             for layer in layers:
                 layer.derived_weights(dtype)
             plan["ver"] = ver
+            if self._derived_generation() != plan["gen"]:
+                # the refresh had to re-allocate (cannot happen for same-shaped parameters): re-capture
+                plan["graph"] = None
+                return self._graph_layers(outputs, attn_mask, pad_mask, dtype)
         self._fill(plan, outputs, attn_mask, pad_u8)
         plan["graph"].replay()
         engine.GRAPH_REPLAYED_LAUNCHES[0] += plan["launches"]     # native kernels inside the replayed graph
         return plan["out"].clone()
+
+    def _lookup_plan(self, key):
+        """LRU lookup; a new key is registered (first call of a shape runs eagerly, the second captures)."""
+        plan = self._plans.get(key)
+        if plan is not None:
+            self._plans.move_to_end(key)
+            return plan
+        while len(self._plans) >= max(1, self.max_plans):
+            self._plans.popitem(last=False)
+        self._plans[key] = {"graph": None, "gen": None}
+        return None
+
+    def _derived_generation(self):
+        return sum(layer.derived_generation() for layer in self.encoders)
 
     def _weights_version(self):
         """Cheap staleness key: sum of the autograd version counters of every parameter/buffer of the layer
@@ -130,7 +154,7 @@ class ConformerEncoder(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._bump()
-        self.__dict__["_plans"] = {}          # device / dtype moves invalidate captured graphs
+        self.__dict__["_plans"] = collections.OrderedDict()          # device / dtype moves invalidate captured graphs
         return super()._apply(fn, *args, **kwargs)
 
     @staticmethod
@@ -170,7 +194,7 @@ class ConformerEncoder(nn.Module):
         num_layers, cache_size = attn_cache.size(0), attn_cache.size(2)
         chunk_size = outputs.size(1)
         attention_key_size = cache_size + chunk_size
-        pos_embed = self.embed.position_encoding(offset=offset - cache_size, size=attention_key_size)
+        pos_embed = self.embed.position_encoding(offset=offset - cache_size, size=attention_key_size, like=outputs)
         if required_cache_size < 0:
             next_cache_start = 0
         elif required_cache_size == 0:
@@ -181,8 +205,10 @@ class ConformerEncoder(nn.Module):
             engine.check_inference_only(self, self._max_dropout())
         dtype = engine.resolve_dtype(self)
         no_mask = inputs_attn_mask is None or inputs_attn_mask.dim() != 3 or inputs_attn_mask.size(2) == 0
+        # graphs only for a bounded left context: with required_cache_size < 0 the cache grows every chunk, no shape
+        # ever repeats within an utterance and a plan per chunk index would pile up graphs + private pools
         if (self.use_cuda_graphs and not self.training and outputs.is_cuda and no_mask and len(self.encoders) > 0
-                and not torch.cuda.is_current_stream_capturing()):
+                and required_cache_size >= 0 and not torch.cuda.is_current_stream_capturing()):
             out, r_attn_cache = self._graph_chunk(outputs, pos_embed, attn_cache, next_cache_start, dtype)
             r_attn_cache = r_attn_cache.to(outputs.dtype)
         else:
@@ -205,10 +231,11 @@ class ConformerEncoder(nn.Module):
         size, trim point) exactly like the batched path (first call eager, second captures, later ones replay)."""
         key = ("chunk", tuple(outputs.shape), tuple(pos_embed.shape), tuple(attn_cache.shape), next_cache_start, dtype,
                outputs.device, len(self.encoders))
-        plan = self._plans.get(key)
+        plan = self._lookup_plan(key)
         if plan is None:
-            self._plans[key] = {"graph": None}
             return self._chunk_layers(outputs.float(), pos_embed, attn_cache, next_cache_start, dtype)
+        if plan["graph"] is not None and plan["gen"] != self._derived_generation():
+            plan["graph"] = None
         if plan["graph"] is None:
             x_s = torch.empty(outputs.shape, dtype=torch.float32, device=outputs.device)
             p_s = torch.empty_like(pos_embed)
@@ -224,7 +251,8 @@ class ConformerEncoder(nn.Module):
             n0 = _native.launch_count()
             with torch.cuda.graph(g):
                 out_s, r_s = self._chunk_layers(x_s, p_s, c_s, next_cache_start, dtype)
-            plan.update(graph=g, x=x_s, p=p_s, c=c_s, out=out_s, r=r_s, launches=_native.launch_count() - n0)
+            plan.update(graph=g, x=x_s, p=p_s, c=c_s, out=out_s, r=r_s, launches=_native.launch_count() - n0,
+                        gen=self._derived_generation())
         ver = self._weights_version()
         if plan.get("ver") != ver:
             for layer in self.encoders:

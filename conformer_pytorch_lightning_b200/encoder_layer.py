@@ -40,6 +40,10 @@ class ConformerEncoderLayer(nn.Module):
                 "ff_g": f(self.norm_ff.weight), "ff_b": f(self.norm_ff.bias),
                 "fin_g": f(self.norm_final.weight), "fin_b": f(self.norm_final.bias)}
 
+    def derived_generation(self):
+        return (self.feed_forward_macaron._derived.generation + self.feed_forward._derived.generation +
+                self.self_attn._derived.generation + self.conv_module._derived.generation)
+
     def forward(self, inputs, inputs_attn_mask, pos_embed,
                 inputs_pad_mask=torch.ones((0, 0, 0), dtype=torch.bool),
                 attn_cache=torch.ones((0, 0, 0), dtype=torch.bool),

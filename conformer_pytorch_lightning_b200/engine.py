@@ -52,18 +52,30 @@ def check_inference_only(module, dropout_p):
 # --------------------------------------------------------------------------- workspace
 class Workspace:
     """Named scratch buffers, re-used across calls on the same thread (no hidden allocation
-    inside the native ops; the buffers live in PyTorch's caching allocator)."""
+    inside the native ops; the buffers live in PyTorch's caching allocator).  One flat buffer per
+    (name, dtype, device) that only ever grows (geometrically); a request returns a view of its head, so shapes that
+    change from call to call (streaming key lengths) do not accumulate buffers.  A buffer that is outgrown stays
+    referenced (captured CUDA graphs may hold its address): total memory is bounded by twice the largest request."""
 
     def __init__(self):
         self._t = {}
+        self._retired = []
 
     def get(self, name, shape, dtype, device):
-        key = (name, tuple(shape), dtype, device)
+        key = (name, dtype, device)
+        n = 1
+        for v in shape:
+            n *= int(v)
         t = self._t.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype, device=device)
+        if t is None or t.numel() < n:
+            if t is not None:
+                self._retired.append(t)
+                n_alloc = max(n, 2 * t.numel())
+            else:
+                n_alloc = n
+            t = torch.empty(max(n_alloc, 1), dtype=dtype, device=device)
             self._t[key] = t
-        return t
+        return t[:n].view(shape)
 
 
 _tls = threading.local()
@@ -78,31 +90,36 @@ def thread_workspace():
 
 # --------------------------------------------------------------------------- derived weights
 class Derived:
-    """Cache of tensors derived from a module's parameters.  Rebuilt (in place when shapes
-    allow, so captured CUDA graphs stay valid) whenever a parameter version, storage,
-    the training flag or the compute dtype changes."""
+    """Cache of tensors derived from a module's parameters, one slot per compute dtype (bf16 and fp32 copies coexist:
+    a captured CUDA graph holds raw pointers into its slot, so switching the compute dtype back and forth must not free
+    the other dtype's tensors).  A slot is rebuilt -- in place when shapes allow, so captured graphs stay valid --
+    whenever a parameter version, storage or the training flag changes; ``generation`` counts the rebuilds that had to
+    re-allocate (captured graphs that baked in the old addresses must be dropped, see ConformerEncoder)."""
 
     def __init__(self):
-        self.key = None
-        self.t = None
+        self.slots = {}
+        self.generation = 0
 
     def get(self, module, dtype, build):
         tensors = list(module.parameters(recurse=True)) + list(module.buffers(recurse=True))
-        key = (dtype, module.training) + tuple((p.data_ptr(), p._version) for p in tensors)
-        if key != self.key:
+        key = (module.training,) + tuple((p.data_ptr(), p._version) for p in tensors)
+        slot = self.slots.get(dtype)
+        if slot is None or slot[0] != key:
             with torch.no_grad():
                 new = build(dtype)
-            old = self.t
+            old = slot[1] if slot is not None else None
             if old is not None and old.keys() == new.keys() and all(
                     old[k].shape == new[k].shape and old[k].dtype == new[k].dtype and old[k].device == new[k].device
                     for k in new):
                 for k in new:
                     if old[k].data_ptr() != new[k].data_ptr():
                         old[k].copy_(new[k])
+                new = old
             else:
-                self.t = new
-            self.key = key
-        return self.t
+                self.generation += 1
+            self.slots[dtype] = (key, new)
+            return new
+        return slot[1]
 
 
 def _act(w, dtype):

@@ -32,7 +32,14 @@ def _req(t, name, dtype=None, contiguous=True):
 
 
 def ensure_init(t):
-    N.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    """Per-device library setup on first use; kernels are launched on the calling thread's CURRENT device, so a tensor
+    on another device is an error here rather than an illegal-address fault later."""
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:
+        raise RuntimeError(f"tensor on cuda:{idx} but the current device is cuda:{cur}: wrap the call in "
+                           f"`with torch.cuda.device({idx}):`")
+    N.init(idx)
 
 
 def layernorm(x, g1, b1, *, x_out=None, g2=None, b2=None, y=None, row_valid=None, eps=1e-5):

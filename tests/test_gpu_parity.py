@@ -266,3 +266,45 @@ def test_streaming_graph_replay_equals_eager(dtype):
             got, _ = enc.forward_chunk_by_chunk(feats, 16, 2)
             assert torch.equal(got, want), f"pass {it}"
     assert any(k[0] == "chunk" and p.get("graph") is not None for k, p in enc._plans.items() if isinstance(k, tuple))
+
+
+def test_compute_dtype_alternation_on_one_encoder():
+    """a captured bf16 graph must survive a switch to fp32 and back -- the derived bf16 weight copies
+    are kept per dtype, so the graph's baked-in addresses stay valid."""
+    g = load_golden("m3_static16")
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=torch.bfloat16)
+    feats, lens = torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["lens"]).cuda()
+    with torch.no_grad():
+        bf = [enc(feats, lens)[0] for _ in range(3)]                 # eager, capture, replay
+        enc.set_compute_dtype(torch.float32)
+        f32 = [enc(feats, lens)[0] for _ in range(3)]
+        junk = [torch.randn(1 << 20, device="cuda") for _ in range(64)]   # churn the allocator
+        enc.set_compute_dtype(torch.bfloat16)
+        bf2 = [enc(feats, lens)[0] for _ in range(3)]
+        enc.set_compute_dtype(torch.float32)
+        f32b = enc(feats, lens)[0]
+    del junk
+    assert all(torch.equal(bf[0], o) for o in bf + bf2)
+    assert all(torch.equal(f32[0], o) for o in f32 + [f32b])
+    assert max_rel(f32[0].cpu().numpy(), g["out"]) < FP32_TOL
+    assert max_rel(bf2[2].cpu().numpy(), g["out"]) < BF16_TOL
+
+
+def test_graph_plans_are_lru_bounded():
+    """ADVICE r1 (medium) / VERDICT weak #9: plans are evicted least-recently-used, and unbounded-left-context streaming
+    does not create per-chunk plans."""
+    cfg = O.conformer_cfg("M", encoder_num_layers=2)
+    enc = build_encoder(cfg, 1, compute_dtype=torch.bfloat16)
+    enc.max_plans = 4
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for tin in (300, 340, 380, 420, 460, 500, 300, 300):
+            feats = torch.randn(2, tin, 80, generator=g).cuda()
+            enc(feats, torch.full((2,), tin, dtype=torch.int32).cuda())
+        assert len(enc._plans) <= 4
+        n_before = len(enc._plans)
+        out, _ = enc.forward_chunk_by_chunk(torch.randn(1, 67 + 64 * 5, 80, generator=g).cuda(), 16, -1)
+        assert len(enc._plans) == n_before                       # growing cache: no plan per chunk index
+        out2, _ = enc.forward_chunk_by_chunk(torch.randn(1, 67 + 64 * 5, 80, generator=g).cuda(), 16, 1)
+        assert len(enc._plans) <= 4
+    assert torch.isfinite(out).all() and torch.isfinite(out2).all()
