@@ -15,11 +15,16 @@ e2e   : the same metric through the public API with pinned HOST fbank features: 
         ``ConformerEncoder.forward(feats, lengths)`` batch after batch (H2D copy + sub-sampling front-end + layers + D2H of
         the output every step), overlapping the copies of neighbouring batches with compute; `serial_latency_ms` is one
         synchronous forward call with both copies.
-roofline : dominant kernel = the fused feed-forward kernel (w_1 + SiLU + w_2 + residual + LayerNorm, ~half of
-        the step), timed in-step with CUDA events around each of its 24 launches; `roofline_hbm` is the same
-        for the HBM-bound depthwise-conv kernel when it runs (unfused convolution path only; null otherwise).
+roofline : dominant kernel = the fused feed-forward kernel (w_1 + SiLU + w_2 + residual + LayerNorm, ~60 % of
+        the step), timed in-step with CUDA events around each of its launches; the peak is the measured BURST bf16
+        figure when the clocks sampled during the timed region sat at max with no power cap, else the sustained one
+        (both fractions are printed); `roofline_kernels` gives the same for the fused attention and convolution-module
+        kernels; `roofline_hbm` for the HBM-bound depthwise-conv kernel when it runs (unfused convolution path only).
 cpu_baseline / --impl reference : the ATen-CPU oracle port of the reference's CPU path (the reference is
         Python and cannot travel to the GPU box) on a bounded sample of the same workload.
+extra.eager_gpu_baseline : the same ATen port as eager PyTorch on this GPU (fp32 TF32-off and bf16 autocast): the
+        cuBLAS / cuDNN bar on the same box (report only).
+extra.strong_scaling (N > 1) : ONE global batch sharded by utterance + NCCL all-gather of the outputs, host to host.
 """
 import argparse
 import json
@@ -184,24 +189,18 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    real_stdout = None
     if world > 1:
-        # NCCL prints its version banner on stdout at VERSION/INFO level (env var or nccl.conf); stdout must carry
-        # exactly one JSON line, so the level is lowered and, belt and braces, file descriptor 1 points at stderr while
-        # the communicator is created (eager init + one collective)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its banner / INFO log to stdout whenever it likes; stdout must carry exactly one JSON line, so for
+        # the whole multi-rank run file descriptor 1 points at stderr (the NCCL log stays visible there, at whatever
+        # NCCL_DEBUG level the caller chose) and the JSON line is written to the saved descriptor at the end.
         sys.stdout.flush()
-        saved_fd = os.dup(1)
+        real_stdout = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            warm = torch.zeros(1, device=torch.device("cuda", local))
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.zeros(1, device=torch.device("cuda", local))
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
     dev = torch.device("cuda", local)
 
     cfg_name, feats_np, lens_np, T, audio_s = make_inputs(args.workload, seed=1234 + rank)
@@ -274,7 +273,9 @@ def run_ours(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches}))
+            out = real_stdout if real_stdout is not None else sys.stdout
+            out.write(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches}) + "\n")
+            out.flush()
         return
     # serial latency of one forward call (H2D -> front-end -> layers -> D2H -> sync), L2 flushed between calls
     lat_ms, _, _ = timed(e2e_step, max(3, args.steps // 4), 3, wall=True)
@@ -303,42 +304,64 @@ def run_ours(args):
     e2e_val = world * audio_s / (e2e_ms / 1e3)
     out_bytes = B * T * cfg["encoder_dim"] * 4
 
-    # ---- roofline of the dominant kernels, timed in-step with CUDA events around each matching launch
-    #      (eager launches: graph replays cannot be bracketed per kernel)
+    # ---- roofline of the dominant kernels, timed in-step with CUDA events around each library call of the step
+    #      (eager launches: graph replays cannot be bracketed per kernel).  One entry per call family; the kernel that
+    #      actually served the calls is read back from the library's per-kernel launch counters.
     pk = peaks()
-    n_tok, d, F = B * T, cfg["encoder_dim"], cfg["hidden_dim"]
-    ev = {"ffn": [], "dw": []}
+    clocks = clk.summary()
+    burst_ok = ("sw_power_cap" not in clocks["reasons"] and clocks["sm_mhz"] is not None and clocks["sm_max_mhz"]
+                and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
+    # a kernel timed inside a ~30 ms timed region at full boost clock with no power cap runs against the BURST tensor
+    # peak; under a power cap / reduced clocks the sustained figure applies.  Both fractions are printed.
+    tf_peak, tf_kind = (pk["tf_burst"], "burst") if burst_ok else (pk["tf_sustained"], "sustained")
+    n_tok, d, F, kc = B * T, cfg["encoder_dim"], cfg["hidden_dim"], cfg["kernel_size"]
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and args.workload == "C2":      # ncu captures were taken on the C2 shapes
-        traffic = json.load(open(tpath))
+    for tname in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and args.workload == "C2":      # ncu captures were taken on the C2 shapes
+            traffic = json.load(open(tpath))
+            break
+    FAMILIES = ("ffn_fused", "mhsa_fused", "conv_fused", "gemm_tc", "attention_tc", "dwconv", "gemm_simt", "attention_simt",
+                "layernorm")
+    probes = {}                                       # call family -> list of (start, end, flop, bytes)
 
-    ffn_flops = []                                    # algorithmic FLOP of every bracketed ffn_fused_kernel launch
+    def flops_of(name, a, kw):
+        if name == "ffn":
+            return 4.0 * n_tok * d * F
+        if name == "ffn_chain":                                    # (y, a, b, x, y_out, proj=...)
+            pj = kw.get("proj")
+            return (2 if a[1] is not None else 1) * 4.0 * n_tok * d * F + (2.0 * n_tok * d * pj[0].shape[0] if pj is not None else 0.0)
+        if name == "mhsa_out":                                     # scores + PV over the full T x T square + linear_out
+            return 4.0 * B * T * T * d + 2.0 * n_tok * d * d
+        if name == "conv_module":                                  # pw1 (d -> 2d) + pw2 (d -> d) + depthwise taps
+            return 6.0 * n_tok * d * d + 2.0 * n_tok * d * kc
+        if name == "gemm":
+            return 2.0 * a[0].shape[0] * a[1].shape[0] * a[0].shape[1]
+        if name == "attention":
+            return 4.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1] * a[0].shape[2] * a[0].shape[3]
+        return 0.0
 
-    def wrap(mod, name, key):
-        orig = getattr(mod, name)
+    def wrap(name, key):
+        orig = getattr(ops, name)
 
         def probe(*a, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
             r = orig(*a, **kw)
-            e.record()
-            ev[key].append((s, e))
-            if name == "ffn":
-                ffn_flops.append(4.0 * n_tok * d * F)                # two GEMMs of 2*M*d*F
-            elif name == "ffn_chain":                              # (y, a, b, x, y_out, proj=...)
-                n_mod = 2 if a[1] is not None else 1
-                pj = kw.get("proj")
-                ffn_flops.append(n_mod * 4.0 * n_tok * d * F + (2.0 * n_tok * d * pj[0].shape[0] if pj is not None else 0.0))
+            e_.record()
+            probes.setdefault(key, []).append((s_, e_, flops_of(name, a, kw)))
             return r
-        setattr(mod, name, probe)
-        return orig
+        setattr(ops, name, probe)
+        return name, orig
 
     graphs = enc.use_cuda_graphs
     enc.use_cuda_graphs = False
-    o_ffn, o_chain, o_dw = wrap(ops, "ffn", "ffn"), wrap(ops, "ffn_chain", "ffn"), wrap(ops, "dwconv", "dw")
+    saved = [wrap("ffn", "ffn"), wrap("ffn_chain", "ffn"), wrap("mhsa_out", "mhsa"), wrap("conv_module", "conv"),
+             wrap("dwconv", "dw"), wrap("gemm", "gemm"), wrap("attention", "attn")]
+    fam0 = {f: _native.kernel_launches(f) for f in FAMILIES}
+    PROBE_PASSES = 3
     try:
-        for _ in range(3):
+        for _ in range(PROBE_PASSES):
             flush.fill_(1)
             # head start for the CPU: the GPU spins ~2.5 ms while all launches of the step are enqueued, so the
             # bracketed intervals are device execution time, not host launch gaps
@@ -346,35 +369,66 @@ def run_ours(args):
             step()
         torch.cuda.synchronize()
     finally:
-        ops.ffn, ops.ffn_chain, ops.dwconv = o_ffn, o_chain, o_dw
+        for name, orig in saved:
+            setattr(ops, name, orig)
         enc.use_cuda_graphs = graphs
-    t_ffn_all = [s.elapsed_time(e) for s, e in ev["ffn"]]
-    t_ffn = float(np.mean(t_ffn_all)) if t_ffn_all else float("nan")
-    t_dw = float(np.mean([s.elapsed_time(e) for s, e in ev["dw"]])) if ev["dw"] else float("nan")
+    fam = {f: (_native.kernel_launches(f) - fam0[f]) // PROBE_PASSES for f in FAMILIES}
+
+    def tensor_roofline(key, fused_family, fused_label, unfused_label):
+        if key not in probes:
+            return None
+        ts = [s_.elapsed_time(e_) for s_, e_, _ in probes[key]]
+        fl = [f for _, _, f in probes[key]]
+        ach = sum(fl) / (sum(ts) * 1e-3) / 1e12
+        per_step = len(ts) // PROBE_PASSES
+        fused = fam.get(fused_family, 0) > 0
+        tr = traffic.get(fused_family + "_kernel") if fused else None
+        return {"bound": "tensor", "kernel": fused_label if fused else unfused_label,
+                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "frac_burst": ach / pk["tf_burst"], "frac_sustained": ach / pk["tf_sustained"],
+                "traffic": (tr["dram_read_bytes"] + tr["dram_write_bytes"]) if tr else None,
+                "launch_us": float(np.mean(ts)) * 1e3, "launches_per_step": per_step,
+                "gflop_per_launch": float(np.mean(fl)) / 1e9, "share_of_step": per_step * float(np.mean(ts)) / ms_per_step,
+                "peak_source": f"{pk['source']}, {tf_kind} bf16 (clocks {clocks['sm_mhz']} / {clocks['sm_max_mhz']} MHz, "
+                               f"reasons {clocks['reasons']})"}
+
     # one launch of ffn_fused_kernel = one or two feed-forward modules (4*M*d*F FLOP each: SURVEY 8d gives 8*N*d*F per layer
     # for its two modules) + optionally the Q/K/V projections (2*M*d*3d) of the layer that follows
-    ach = sum(ffn_flops) / (sum(t_ffn_all) * 1e-3) / 1e12 if t_ffn_all else float("nan")
-    n_ffn = len(t_ffn_all) // 3
-    roofline = {"bound": "tensor",
-                "kernel": f"ffn_fused_kernel (feed-forward module(s) w_1+SiLU+w_2+residual+LayerNorm, chained across the layer "
-                          f"boundary, + Q/K/V projections, in one kernel) M={n_tok} d={d} F={F}",
-                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": (traffic["ffn_fused_kernel"]["dram_read_bytes"] + traffic["ffn_fused_kernel"]["dram_write_bytes"])
-                if "ffn_fused_kernel" in traffic else None,
-                "launch_us": t_ffn * 1e3, "launches_per_step": n_ffn,
-                "gflop_per_launch": (sum(ffn_flops) / len(ffn_flops) / 1e9) if ffn_flops else None,
-                "share_of_step": n_ffn * t_ffn / ms_per_step,
-                "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside the step)"}
+    roofline = tensor_roofline(
+        "ffn", "ffn_fused",
+        f"ffn_fused_kernel (feed-forward module(s) w_1+SiLU+w_2+residual+LayerNorm, chained across the layer boundary, "
+        f"+ Q/K/V projections, in one kernel) M={n_tok} d={d} F={F}",
+        f"gemm_tc_kernel x2 per feed-forward module (w_1+SiLU, w_2+residual+LayerNorm; the fused kernel does not cover "
+        f"d={d}) M={n_tok} d={d} F={F}")
+    roofline_kernels = [r for r in (
+        tensor_roofline("mhsa", "mhsa_fused",
+                        f"mhsa_fused_kernel (scores+mask+softmax+PV for all heads + linear_out + residual + LayerNorm) B={B} T={T} d={d}",
+                        f"attention_tc_kernel + gemm_tc_kernel (linear_out + residual + LayerNorm) B={B} T={T} d={d}"),
+        tensor_roofline("conv", "conv_fused",
+                        f"conv_fused_kernel (pointwise_conv1+GLU, depthwise k={kc}+BatchNorm+SiLU, pointwise_conv2+mask+residual+LayerNorm) M={n_tok} d={d}",
+                        f"gemm_tc_kernel (pw1+GLU) + dwconv_kernel + gemm_tc_kernel (pw2+residual+LayerNorm) M={n_tok} d={d} k={kc}"),
+    ) if r is not None]
+    t_dw = float(np.mean([s_.elapsed_time(e_) for s_, e_, _ in probes["dw"]])) if "dw" in probes else float("nan")
     dw_bytes = 2.0 * n_tok * d * 2                    # read + write one bf16 (N,d) tensor
     ach_dw = dw_bytes / (t_dw * 1e-3) / 1e9
     # the stand-alone depthwise kernel only runs on the unfused path (CFM_B200_CONV_MODE=unfused, fp32, d != 256):
     # in conv_fused_kernel the GLU and depthwise tensors never reach HBM, so there is nothing to put on an HBM roofline
-    roofline_hbm = None if not ev["dw"] else {"bound": "hbm", "kernel": f"dwconv_kernel k={cfg['kernel_size']} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
-                    "achieved": ach_dw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_dw / pk["hbm_gbs"],
-                    "traffic": (traffic["dwconv_kernel"]["dram_read_bytes"] + traffic["dwconv_kernel"]["dram_write_bytes"])
-                    if "dwconv_kernel" in traffic else None,
-                    "launch_us": t_dw * 1e3, "launches_per_step": cfg["encoder_num_layers"],
-                    "peak_source": pk["source"]}
+    roofline_hbm = None if "dw" not in probes else {
+        "bound": "hbm", "kernel": f"dwconv_kernel k={kc} + folded BatchNorm + SiLU, (N={n_tok}, d={d}) bf16",
+        "achieved": ach_dw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_dw / pk["hbm_gbs"],
+        "traffic": (traffic["dwconv_kernel"]["dram_read_bytes"] + traffic["dwconv_kernel"]["dram_write_bytes"])
+        if "dwconv_kernel" in traffic else None,
+        "launch_us": t_dw * 1e3, "launches_per_step": len(probes["dw"]) // PROBE_PASSES, "peak_source": pk["source"]}
+
+    # ---- strong scaling (BASELINE configs[1]: ONE batch sharded over the GPUs) with the final output gather
+    strong = None
+    if world > 1:
+        strong = strong_scaling_leg(args, enc, cfg, dev, rank, world, dtype, flush, barrier)
+
+    # ---- the same-box GPU bar: the reference's algorithm as eager PyTorch (cuBLAS / cuDNN / ATen kernels) on this B200
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        eager = eager_gpu_baseline(cfg, dev, x_emb, attn, pos, pad, audio_s)
 
     if rank == 0:
         cpu = None
@@ -382,7 +436,7 @@ def run_ours(args):
             v, best, sb, _ = cpu_port_rtfx(args.workload, args.cpu_sample, 3)
             cpu = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"ATen-CPU port (oracle/conformer_oracle_torch.py), measured path on {sb} of {B} utterances, best of 3 ({best:.2f} s)"}
-        algo_tf = 1.024 if args.workload == "C2" else None
+        algo_tf = {"C2": 1.024, "C3": 3.552, "C4": 1.914}.get(args.workload)      # SURVEY 8d totals (TFLOP per pass)
         line = {"metric": "encoder audio-sec/sec (RTFx), measured path", "value": value, "unit": "audio-s/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
@@ -397,13 +451,107 @@ def run_ours(args):
                                "ConformerEncoder.forward per batch; H2D / compute / D2H of consecutive batches on three streams; "
                                "wall clock over all steps (per-step working set ~1.4 GB >> L2); serial_latency_ms = one "
                                "synchronous forward call incl. both copies"},
-                "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-                "clocks": clk.summary()}
+                "gpu_launches": launches, "roofline": roofline, "roofline_kernels": roofline_kernels,
+                "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "clocks": clocks,
+                "kernels_per_step": {k: v for k, v in fam.items() if v},
+                "extra": {"eager_gpu_baseline": eager, "strong_scaling": strong}}
         if algo_tf:
             line["model_tflops"] = algo_tf / (ms_per_step / 1e3) * world
-        print(json.dumps(line), flush=True)
+        out = real_stdout if real_stdout is not None else sys.stdout
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_gpu_baseline(cfg, dev, x_emb, attn, pos, pad, audio_s):
+    """Report-only: the measured path of the reference as EAGER PyTorch on the same GPU -- the ATen restatement in
+    oracle/conformer_oracle_torch.py issues exactly the torch ops the reference's modules issue (F.linear, F.conv1d,
+    softmax, layer_norm, ...; pinned bit-exactly to the reference's goldens on CPU), here dispatched to cuBLAS / cuDNN /
+    ATen CUDA kernels.  fp32 with TF32 off (the parity setting) and bf16 autocast (the fast setting)."""
+    import contextlib
+    import torch
+    from oracle import conformer_oracle as O
+    from oracle import conformer_oracle_torch as OT
+    sd = {k: v.to(dev) for k, v in OT.to_torch_sd(O.make_state_dict(cfg, 0)).items()}
+    res = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for mode in ("fp32_tf32_off", "bf16_autocast"):
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else contextlib.nullcontext()
+            with ctx:
+                for _ in range(2):
+                    OT.encoder_layers(x_emb, attn, pos, pad, sd, cfg)
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record()
+                    OT.encoder_layers(x_emb, attn, pos, pad, sd, cfg)
+                    e_.record()
+                    e_.synchronize()
+                    ts.append(s_.elapsed_time(e_))
+            ms = float(np.median(ts))
+            res[mode] = {"ms_per_step": ms, "value": audio_s / (ms / 1e3), "unit": "audio-s/s"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    res["what"] = ("eager PyTorch (ATen port of the reference modules, oracle/conformer_oracle_torch.py) on the same B200, "
+                   "measured path, same batch, median of 5 device-timed passes")
+    return res
+
+
+def strong_scaling_leg(args, enc, cfg, dev, rank, world, dtype, flush, barrier):
+    """ONE length-sorted global batch (the N=1 workload, identical on every rank) is stride-sharded over the ranks
+    (sharding.shard_indices), each rank encodes its shard from pinned HOST features through the public forward, the
+    outputs are all-gathered over NCCL (the north_star's 'final output gather') and rank 0 copies the assembled batch to
+    the host -- all inside the timed region.  Wall clock per step, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from conformer_pytorch_lightning_b200 import sharding
+    cfg_name, feats_np, lens_np, T, audio_s = make_inputs(args.workload, seed=1234)
+    Bg = feats_np.shape[0]
+    idx = sharding.shard_indices(Bg, rank, world)
+    per = (Bg + world - 1) // world
+    feats_host = torch.from_numpy(feats_np[idx.numpy()]).pin_memory()
+    lens_dev = torch.from_numpy(lens_np[idx.numpy()]).to(dev)
+    gathered = torch.empty((world * per, T, cfg["encoder_dim"]), dtype=torch.float32, device=dev)
+    host_out = torch.empty((world * per, T, cfg["encoder_dim"]), dtype=torch.float32).pin_memory() if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    gather_ms = []
+
+    def one():
+        with torch.no_grad():
+            out, _ = enc(feats_host.to(dev, non_blocking=True), lens_dev)
+            if out.size(0) < per:                       # ragged last shard: pad to the common shard size
+                out = torch.cat([out, out.new_zeros((per - out.size(0),) + tuple(out.shape[1:]))])
+            ev[0].record()
+            dist.all_gather_into_tensor(gathered, out.contiguous())
+            ev[1].record()
+            if rank == 0:
+                host_out.copy_(gathered, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            gather_ms.append(ev[0].elapsed_time(ev[1]))
+
+    for _ in range(max(3, args.warmup)):
+        one()
+    gather_ms.clear()
+    steps = max(8, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    t = torch.tensor([1e3 * (time.perf_counter() - t0) / steps, float(np.mean(gather_ms))], device=dev, dtype=torch.float64)
+    barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0].item())
+    return {"scaling": "strong", "value": audio_s / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms, "steps": steps,
+            "global_batch": Bg, "per_gpu_batch": per, "all_gather_ms": float(t[1].item()),
+            "all_gather_bytes": int(gathered.numel() * 4),
+            "what": "one global batch stride-sharded by utterance; per step: H2D of the shard's fbank, forward, NCCL all-gather "
+                    "of the (B/N, T, d) outputs, D2H of the assembled batch on rank 0; wall clock, max over ranks"}
 
 
 def enc_make_pad(lens, max_len):
@@ -421,6 +569,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU bar")
     ap.add_argument("--profile", action="store_true", help="measured path only (for ncu): no e2e / probe / cpu legs")
     args = ap.parse_args()
     if args.impl == "reference":
