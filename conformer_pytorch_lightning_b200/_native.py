@@ -21,7 +21,10 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 EXPORTS = [
     "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_kernel_launches", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
-    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax",
+    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax", "cfm_gemm_ex",
+    "cfm_ln_fwd_train", "cfm_ln_bwd", "cfm_silu_dropout_fwd", "cfm_silu_dropout_bwd", "cfm_resid_dropout_add",
+    "cfm_scale_dropout_bwd", "cfm_glu_fwd", "cfm_glu_bwd", "cfm_bn_silu_bwd", "cfm_dwconv_wgrad", "cfm_softmax_fwd",
+    "cfm_softmax_bwd", "cfm_colsum", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
 ]
 
 _lib = None
@@ -59,9 +62,30 @@ def _declare(lib):
     lib.cfm_subsample_ws_bytes.argtypes = [_i, _i, _i, _i]
     lib.cfm_subsample_ws_bytes.restype = _i64
     lib.cfm_subsample_conv.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]
+    lib.cfm_gemm_ex.argtypes = [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _i,
+                                _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]
+    _u64 = ctypes.c_uint64
+    lib.cfm_ln_fwd_train.argtypes = [_p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _f, _p]
+    lib.cfm_ln_bwd.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]
+    lib.cfm_silu_dropout_fwd.argtypes = [_p, _p, _i, _i, _i, _f, _u64, _i, _p]
+    lib.cfm_silu_dropout_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _f, _u64, _i, _p]
+    lib.cfm_resid_dropout_add.argtypes = [_p, _p, _i, _i, _i, _f, _p, _f, _u64, _i, _p]
+    lib.cfm_scale_dropout_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _u64, _i, _p]
+    lib.cfm_glu_fwd.argtypes = [_p, _p, _i, _i, _i, _p]
+    lib.cfm_glu_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]
+    lib.cfm_bn_silu_bwd.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]
+    lib.cfm_dwconv_wgrad.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]
+    lib.cfm_softmax_fwd.argtypes = [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]
+    lib.cfm_softmax_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]
+    lib.cfm_colsum.argtypes = [_p, _i64, _p, _i, _i, _i, _p]
+    lib.cfm_ctc_loss_ws_bytes.argtypes = [_i, _i, _i]
+    lib.cfm_ctc_loss_ws_bytes.restype = _i64
+    lib.cfm_ctc_loss_fwd.argtypes = [_p, _i64, _i, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]
+    lib.cfm_ctc_loss_bwd.argtypes = [_p, _i64, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_kernel_launches", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes"):
+        if name not in ("cfm_last_error", "cfm_launch_count", "cfm_kernel_launches", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes",
+                        "cfm_ctc_loss_ws_bytes"):
             fn.restype = _i
 
 

@@ -268,3 +268,27 @@ extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const vo
   return attention_simt(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
                         key_bias, scale, dtype, st);
 }
+
+extern "C" int cfm_gemm_ex(const void* A, int a_mn_major, int64_t lda, int64_t a_hs, int64_t a_bs, const void* B,
+                           int b_mn_major, int64_t ldb, int64_t b_hs, int64_t b_bs, void* C, int c_dtype, int64_t ldc,
+                           int64_t c_hs, int64_t c_bs, int accumulate, int M, int N, int K, int nH, int nB, int in_dtype,
+                           float alpha, int splits, int engine, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(A && B && C, "cfm_gemm_ex: null A/B/C");
+  CFM_CHECK_ARG(in_dtype == CFM_F32 || in_dtype == CFM_BF16, "cfm_gemm_ex: bad input dtype %d", in_dtype);
+  CFM_CHECK_ARG(c_dtype == CFM_F32 || c_dtype == CFM_BF16, "cfm_gemm_ex: bad output dtype %d", c_dtype);
+  CFM_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && nH >= 1 && nB >= 1, "cfm_gemm_ex: bad shape");
+  CFM_CHECK_ARG(lda > 0 && ldb > 0 && ldc >= N, "cfm_gemm_ex: bad leading dimensions");
+  if (M == 0 || N == 0) return 0;
+  CFM_CHECK_ARG(K > 0, "cfm_gemm_ex: K must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = gemm_gen_tc_supported(A, lda, a_hs, a_bs, B, ldb, b_hs, b_bs, C, c_dtype, ldc, c_hs, c_bs, M, N, K, in_dtype);
+  if (engine == CFM_ENGINE_TC)
+    CFM_CHECK_ARG(tc_ok, "cfm_gemm_ex: tcgen05 engine does not support M=%d N=%d K=%d (dtype %d, strides/alignment)", M, N, K,
+                  in_dtype);
+  if (tc_ok && engine != CFM_ENGINE_SIMT)
+    return gemm_gen(A, a_mn_major, lda, a_hs, a_bs, B, b_mn_major, ldb, b_hs, b_bs, C, c_dtype, ldc, c_hs, c_bs, accumulate, M, N,
+                    K, nH, nB, alpha, splits, st);
+  return gemm_gen_simt(A, a_mn_major, lda, a_hs, a_bs, B, b_mn_major, ldb, b_hs, b_bs, C, c_dtype, ldc, c_hs, c_bs, accumulate,
+                       M, N, K, nH, nB, in_dtype, alpha, st);
+}

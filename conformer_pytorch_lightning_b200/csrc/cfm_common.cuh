@@ -237,4 +237,16 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
                  float scale, int dtype, cudaStream_t st);
 int attention_tc_init();
 
+// general GEMM of the training path (gemm_gen.cu): C (+)= alpha * opA(A) opB(B)^T, transposed operands, (head, batch) dims
+bool gemm_gen_tc_supported(const void* A, long long lda, long long a_hs, long long a_bs, const void* B, long long ldb,
+                           long long b_hs, long long b_bs, const void* C, int c_dtype, long long ldc, long long c_hs,
+                           long long c_bs, int M, int N, int K, int in_dtype);
+int gemm_gen(const void* A, int a_mn, long long lda, long long a_hs, long long a_bs, const void* B, int b_mn, long long ldb,
+             long long b_hs, long long b_bs, void* C, int c_dtype, long long ldc, long long c_hs, long long c_bs,
+             int accumulate, int M, int N, int K, int nH, int nB, float alpha, int splits, cudaStream_t st);
+int gemm_gen_simt(const void* A, int a_mn, long long lda, long long a_hs, long long a_bs, const void* B, int b_mn,
+                  long long ldb, long long b_hs, long long b_bs, void* C, int c_dtype, long long ldc, long long c_hs,
+                  long long c_bs, int accumulate, int M, int N, int K, int nH, int nB, int in_dtype, float alpha,
+                  cudaStream_t st);
+
 }  // namespace cfm

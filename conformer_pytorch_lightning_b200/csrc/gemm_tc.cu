@@ -47,9 +47,10 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base,
                      const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = encode_tiled_fn();
   CFM_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
-  cuuint64_t gdim[3];
-  cuuint64_t gstr[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  CFM_CHECK_ARG(rank >= 2 && rank <= 5, "tensor map rank %d unsupported", rank);
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -310,3 +310,46 @@ def subsample_conv(x, w1, b1, w2, b2, ws, out):
 
 def subsample_ws_bytes(B, Tin, idim, C):
     return int(N.lib().cfm_subsample_ws_bytes(B, Tin, idim, C))
+
+
+def _operand(t, name):
+    """(nB, nH, MN, K) logical view -> (major flag, ld, head stride, batch stride); 2-D / 3-D views are unsqueezed."""
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    if t.dim() != 4:
+        raise RuntimeError(f"gemm_ex.{name}: expected a 2-D, 3-D or 4-D view")
+    if t.stride(3) == 1 and (t.stride(2) >= t.shape[3] or t.shape[2] == 1):
+        mn, ld = 0, t.stride(2) if t.shape[2] > 1 else max(t.shape[3], 1)
+    elif t.stride(2) == 1:
+        mn, ld = 1, t.stride(3) if t.shape[3] > 1 else max(t.shape[2], 1)
+    else:
+        raise RuntimeError(f"gemm_ex.{name}: one of the last two dimensions must have unit stride")
+    return t, mn, ld, t.stride(1), t.stride(0)
+
+
+def gemm_ex(a, b, c, *, alpha=1.0, accumulate=False, splits=0, engine=N.ENGINE_AUTO):
+    """c (+)= alpha * a @ b^T over the last two dims, batched over up to two leading dims (see cfm_gemm_ex).
+    a: (..., M, K) view, b: (..., N, K) view, c: (..., M, N) with unit stride along N.  Transposed operands are passed as
+    transposed VIEWS (x.t(), x.transpose(-1, -2)): nothing is copied, the kernel reads them MN-major."""
+    _req(a, "gemm_ex.a", contiguous=False)
+    _req(b, "gemm_ex.b", a.dtype, contiguous=False)
+    _req(c, "gemm_ex.c", contiguous=False)
+    a4, a_mn, lda, a_hs, a_bs = _operand(a, "a")
+    b4, b_mn, ldb, b_hs, b_bs = _operand(b, "b")
+    c4 = c
+    while c4.dim() < 4:
+        c4 = c4.unsqueeze(0)
+    nB, nH, M, K = a4.shape
+    Nn = b4.shape[2]
+    if b4.shape != (nB, nH, Nn, K) or c4.shape != (nB, nH, M, Nn):
+        raise RuntimeError(f"gemm_ex: shape mismatch a{tuple(a4.shape)} b{tuple(b4.shape)} c{tuple(c4.shape)}")
+    if Nn > 1 and c4.stride(3) != 1:
+        raise RuntimeError("gemm_ex.c: the last dimension must have unit stride")
+    if accumulate and c.dtype != torch.float32:
+        raise RuntimeError("gemm_ex: accumulation needs an fp32 output")
+    ensure_init(a)
+    N.check(N.lib().cfm_gemm_ex(a4.data_ptr(), a_mn, lda, a_hs, a_bs, b4.data_ptr(), b_mn, ldb, b_hs, b_bs, c4.data_ptr(),
+                                _DT[c.dtype], c4.stride(2) if M > 1 else max(Nn, 1), c4.stride(1), c4.stride(0),
+                                1 if accumulate else 0, M, Nn, K, nH, nB, _DT[a.dtype], float(alpha), int(splits), engine,
+                                _stream(a)))
+    return c

@@ -246,6 +246,82 @@ int64_t cfm_subsample_ws_bytes(int B, int Tin, int idim, int C);
 int cfm_subsample_conv(const float* x, int B, int Tin, int idim, const float* w1, const float* b1,
                        const void* w2, const float* b2, int C, void* ws, void* out, void* stream);
 
+/*
+ * General GEMM of the training path (backward of every nn.Linear / 1x1 Conv1d on the path, and the batched products of
+ * attention forward/backward, attention.py:84,96 and their autograd):
+ *     C[b][h] (M x N)  (+)=  alpha * opA(A[b][h]) (M x K)  opB(B[b][h])^T (N x K)
+ * a_mn_major / b_mn_major = 0: operand is K-major, element (mn, k) at base + mn*ld + k (nn.Linear forward layout);
+ *                         = 1: MN-major, element (mn, k) at base + k*ld + mn (the transposed view: no copy is made).
+ *   dgrad  dA = dC W   : A = dC (0), B = W (1, ldb = row stride of W)
+ *   wgrad  dW += dC^T X: A = dC (1), B = X (1), C = fp32 gradient, accumulate = 1 (split over K = tokens; the K slices
+ *                        are combined with TMA reduce-add stores)
+ * *_hs / *_bs: element strides of the head / batch dimension (nH, nB >= 1).  in_dtype CFM_F32 | CFM_BF16 (A and B);
+ * c_dtype CFM_F32 | CFM_BF16; accumulate needs an fp32 C.  splits: 0 = automatic.  tcgen05 engine: bf16 inputs,
+ * 16-byte aligned bases and strides; everything else runs on the CUDA-core engine.
+ */
+int cfm_gemm_ex(const void* A, int a_mn_major, int64_t lda, int64_t a_hs, int64_t a_bs,
+                const void* B, int b_mn_major, int64_t ldb, int64_t b_hs, int64_t b_bs,
+                void* C, int c_dtype, int64_t ldc, int64_t c_hs, int64_t c_bs, int accumulate,
+                int M, int N, int K, int nH, int nB, int in_dtype, float alpha, int splits, int engine, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * TRAINING path (BASELINE.json configs[4]): the pieces of forward that must save state and every non-GEMM backward.
+ * They implement the autograd of the reference's modules (module.py:49-69 drives fwd+bwd through encoder.py:54-75).
+ * `dtype` is the activation dtype (CFM_F32 | CFM_BF16); statistics, the residual stream x and all parameter
+ * gradients are fp32; gradient outputs named d<param> are ACCUMULATED (+=, atomics).  Dropout is counter based
+ * (Philox4x32-10 keyed by (seed, site), counter = element index): forward and backward pass the same (p, seed, site)
+ * and no mask is stored.  p = 0 disables it.  The reference's dropout sites: feedforward.py:19, attention.py:95,
+ * encoder_layer.py:58,62,66,69.
+ */
+/* y = rowmask(LN(x; g, b)) and the row statistics needed by the backward (encoder_layer.py:56,59,63,67,70). */
+int cfm_ln_fwd_train(const float* x, int rows, int d, const float* g, const float* b, void* y, int y_dtype,
+                     float* mean, float* rstd, const uint8_t* row_valid, float eps, void* stream);
+/* dx_out = (dx_in ? dx_in : 0) + LayerNorm-backward(rowmask(dy));  dg += sum dy*xhat;  db += sum dy. */
+int cfm_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd, const float* g,
+               const uint8_t* row_valid, const float* dx_in, float* dx_out, float* dg, float* db, int rows, int d,
+               void* stream);
+/* a = dropout(SiLU(h))  (feedforward.py:18-19) and its backward dh = da * mask * SiLU'(h), dbias += colsum(dh). */
+int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, float p, uint64_t seed, int site,
+                         void* stream);
+int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, float* dbias, int rows, int cols, int dtype, float p,
+                         uint64_t seed, int site, void* stream);
+/* x += alpha * rowmask * dropout(f)  (the residual adds of encoder_layer.py:58,62,66,69 with their dropout and the
+ * masked_fill of convolution.py:47-48) and its backward df = alpha * rowmask * mask * dx, dbias += colsum(df). */
+int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols, int dtype, float alpha, const uint8_t* row_valid,
+                          float p, uint64_t seed, int site, void* stream);
+int cfm_scale_dropout_bwd(const float* dx, void* df, float* dbias, int rows, int cols, int dtype, float alpha,
+                          const uint8_t* row_valid, float p, uint64_t seed, int site, void* stream);
+/* GLU over the channel halves of g (rows, 2d) (convolution.py:42) and its backward (dbias: 2d bias gradient of
+ * pointwise_conv1). */
+int cfm_glu_fwd(const void* g, void* u, int rows, int d, int dtype, void* stream);
+int cfm_glu_bwd(const float* du, const void* g, void* dg, float* dbias, int rows, int d, int dtype, void* stream);
+/* Backward of SiLU(BatchNorm1d(raw)) with BATCH statistics (convolution.py:44-45): sums[0..d) = dgamma, sums[d..2d) =
+ * dbeta of THIS call (overwritten), draw = gradient w.r.t. the depthwise-conv output. */
+int cfm_bn_silu_bwd(const void* dc, const float* raw, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, float* sums, void* draw, int rows, int d, int dtype, void* stream);
+/* Weight / bias gradient of the depthwise Conv1d (convolution.py:43): dw (k, d) += ..., dbias (d) += ...; the input
+ * gradient is cfm_dwconv with the tap-reversed filter. */
+int cfm_dwconv_wgrad(const void* dy, const void* u, float* dw, float* dbias, int B, int T, int d, int k, int dtype,
+                     void* stream);
+/* Masked softmax (+ dropout) over materialised scores S (B,H,Tq,Tp) fp32 -> P (and the dropped copy Pd when p > 0), mask
+ * semantics of attention.py:89-92; and its backward dS = P * (dP - rowsum(dP * P)), dP = dPd * dropout multiplier. */
+int cfm_softmax_fwd(const float* S, void* P, void* Pd, const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, int B, int H,
+                    int Tq, int Tk, int Tp, int dtype, float p, uint64_t seed, int site, void* stream);
+int cfm_softmax_bwd(const void* P, const float* dPd, void* dS, int B, int H, int Tq, int Tk, int Tp, int dtype, float p,
+                    uint64_t seed, int site, void* stream);
+/* out (cols) += column sums of x (rows, ld) -- bias gradients. */
+int cfm_colsum(const void* x, int64_t ld, float* out, int rows, int cols, int dtype, void* stream);
+
+/* CTC loss (decoder.py:18-23: log_softmax + nn.CTCLoss(reduction='sum'), blank = 0) on logits (B*T, ld), V valid
+ * columns.  fwd: nll[b]; bwd: dlogits = scale * (softmax - occupancy) for valid frames, 0 elsewhere (may alias logits).
+ * `ws` (cfm_ctc_loss_ws_bytes) carries lse / alpha / beta from fwd to bwd. */
+int64_t cfm_ctc_loss_ws_bytes(int B, int T, int Lmax);
+int cfm_ctc_loss_fwd(const void* logits, int64_t ld, int B, int T, int V, const int* labels, int Lmax, const int* in_len,
+                     const int* lab_len, float* nll, void* ws, int dtype, void* stream);
+int cfm_ctc_loss_bwd(const void* logits, int64_t ld, int B, int T, int V, int Vp, const int* labels, int Lmax,
+                     const int* in_len, const int* lab_len, const float* nll, const void* ws, float scale, void* dlogits,
+                     int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
