@@ -73,7 +73,7 @@ def _declare(lib):
     lib.cfm_scale_dropout_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _u64, _i, _p]
     lib.cfm_glu_fwd.argtypes = [_p, _p, _i, _i, _i, _p]
     lib.cfm_glu_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]
-    lib.cfm_bn_silu_bwd.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]
+    lib.cfm_bn_silu_bwd.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]
     lib.cfm_dwconv_wgrad.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]
     lib.cfm_softmax_fwd.argtypes = [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]
     lib.cfm_softmax_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]

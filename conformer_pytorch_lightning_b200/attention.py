@@ -87,7 +87,7 @@ class _MHSABase(nn.Module):
             if not (torch.equal(key, query) and torch.equal(value, query)):
                 raise NotImplementedError("native attention implements self-attention (query is key is value), "
                                           "the only way the reference encoder calls it (encoder_layer.py:60)")
-        engine.check_inference_only(self, self.dropout.p)
+        engine.check_inference_only(self, self.dropout.p, query)
         dtype = engine.resolve_dtype(self)
         B, T, d = query.shape
         y = query.reshape(B * T, d).to(dtype).contiguous()

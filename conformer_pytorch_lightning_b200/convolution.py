@@ -29,7 +29,7 @@ class ConvolutionModule(nn.Module):
         return self._derived.get(self, dtype, lambda dt: engine.conv_weights(self, dt))
 
     def forward(self, inputs, inputs_pad_mask, cache=torch.zeros((0, 0, 0, 0))):
-        engine.check_inference_only(self, 0.0)
+        engine.check_inference_only(self, 0.0, inputs)
         dtype = engine.resolve_dtype(self)
         B, T, d = inputs.shape
         row_valid = engine._row_valid(inputs_pad_mask, B, T)

@@ -399,9 +399,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_silu_bwd_apply_kernel(const T* __restrict__ dc, const float* __restrict__ raw, const float* __restrict__ mean,
                          const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         const float* __restrict__ sums, T* __restrict__ draw, int rows, int d) {
+                         const float* __restrict__ sums, T* __restrict__ draw, int rows, int d, int batch_stats) {
   constexpr int V = Vec<T>::N;
-  const float inv_n = 1.f / (float)rows;
+  // eval-mode BatchNorm (running statistics are constants): no correction terms
+  const float inv_n = batch_stats ? 1.f / (float)rows : 0.f;
   rowwise<V>(rows, d, nullptr, [&](int r, int c, float (&)[V]) {
     float g[V], x[V], mu[V], rs[V], ga[V], be[V], sg[V], sb[V];
     Vec<T>::load(dc + (size_t)r * d + c, g);
@@ -667,7 +668,8 @@ extern "C" int cfm_glu_bwd(const float* du, const void* g, void* dg, float* dbia
 }
 
 extern "C" int cfm_bn_silu_bwd(const void* dc, const float* raw, const float* mean, const float* rstd, const float* gamma,
-                               const float* beta, float* sums, void* draw, int rows, int d, int dtype, void* stream) {
+                               const float* beta, float* sums, void* draw, int rows, int d, int dtype, int batch_stats,
+                               void* stream) {
   CFM_CHECK_ARG(dc && raw && mean && rstd && gamma && beta && sums && draw, "cfm_bn_silu_bwd: null pointer");
   if (check_rc(rows, d, dtype, "cfm_bn_silu_bwd") != 0) return -1;
   if (rows == 0) return 0;
@@ -677,7 +679,7 @@ extern "C" int cfm_bn_silu_bwd(const void* dc, const float* raw, const float* me
                           (const T*)dc, raw, mean, rstd, gamma, beta, sums, rows, d)));
   CFM_LAUNCHED_K("bn_silu_bwd_stats");
   CFM_BY_DTYPE(dtype, (bn_silu_bwd_apply_kernel<T><<<rowwise_grid(rows, d, Vec<T>::N), 256, 0, st>>>(
-                          (const T*)dc, raw, mean, rstd, gamma, beta, sums, (T*)draw, rows, d)));
+                          (const T*)dc, raw, mean, rstd, gamma, beta, sums, (T*)draw, rows, d, batch_stats)));
   CFM_LAUNCHED_K("bn_silu_bwd_apply");
   return 0;
 }

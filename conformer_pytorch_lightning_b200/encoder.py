@@ -59,9 +59,13 @@ class ConformerEncoder(nn.Module):
 
     def encode_layers(self, outputs, inputs_attn_mask, pos_embed, inputs_pad_mask):
         """The measured path: layer loop + after_norm (encoder.py:72-74)."""
-        if self.training:                      # (walking all sub-modules for their dropout p costs ~0.1 ms of host time)
-            engine.check_inference_only(self, self._max_dropout())
         dtype = engine.resolve_dtype(self)
+        if self._training_path(outputs):
+            # differentiable / dropout-capable schedule: native forward that saves activations + native backward
+            # (training.py); the per-layer gradient buckets go to self.grad_sync (ddp.GradSync) when one is attached
+            from . import training
+            return training.run_stack(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask, pos_embed,
+                                      inputs_pad_mask, dtype, grad_sync=getattr(self, "grad_sync", None))
         batched_pos = pos_embed is None or pos_embed.numel() == outputs.size(0) * outputs.size(2)
         if (self.use_cuda_graphs and not self.training and outputs.is_cuda and batched_pos
                 and not torch.cuda.is_current_stream_capturing()):
@@ -147,6 +151,7 @@ class ConformerEncoder(nn.Module):
     def _bump(self):
         self.__dict__["_epoch"] = self.__dict__.get("_epoch", 0) + (1 << 40)
         self.__dict__["_plist"] = None
+        self.__dict__["_rg_list"] = None
 
     def train(self, mode=True):
         self._bump()
@@ -168,7 +173,20 @@ class ConformerEncoder(nn.Module):
             torch.ne(pad_u8, 0, out=plan["pm"])
 
     def _max_dropout(self):
-        return max([m.p for m in self.modules() if isinstance(m, nn.Dropout)] + [0.0])
+        return max([m.p for m in self.encoders.modules() if isinstance(m, nn.Dropout)] + [0.0])
+
+    def _training_path(self, x):
+        """Training schedule when the caller expects gradients (grad mode on and x or a layer parameter requires grad),
+        or when dropout must be applied (train() mode with a non-zero dropout in the layer stack)."""
+        if torch.is_grad_enabled():
+            if x.requires_grad:
+                return True
+            plist = self.__dict__.get("_rg_list")
+            if plist is None:
+                plist = self.__dict__["_rg_list"] = [p for m in (self.encoders, self.after_norm) for p in m.parameters()]
+            if any(p.requires_grad for p in plist):
+                return True
+        return self.training and self._max_dropout() > 0.0
 
     # ------------------------------------------------------------------ reference API
     def forward(self, inputs, input_lengths, decoding_chunk_size=0, num_decoding_chunk_size=-1):
@@ -201,8 +219,9 @@ class ConformerEncoder(nn.Module):
             next_cache_start = attention_key_size
         else:
             next_cache_start = max(attention_key_size - required_cache_size, 0)
-        if self.training:
-            engine.check_inference_only(self, self._max_dropout())
+        if self._training_path(outputs):
+            raise NotImplementedError("forward_chunk is an inference API (encoder.py:78 is only called under no_grad / "
+                                      "eval in the reference); call it under torch.no_grad() in eval() mode")
         dtype = engine.resolve_dtype(self)
         no_mask = inputs_attn_mask is None or inputs_attn_mask.dim() != 3 or inputs_attn_mask.size(2) == 0
         # graphs only for a bounded left context: with required_cache_size < 0 the cache grows every chunk, no shape

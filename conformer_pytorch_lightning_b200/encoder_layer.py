@@ -40,6 +40,9 @@ class ConformerEncoderLayer(nn.Module):
                 "ff_g": f(self.norm_ff.weight), "ff_b": f(self.norm_ff.bias),
                 "fin_g": f(self.norm_final.weight), "fin_b": f(self.norm_final.bias)}
 
+    def _max_dropout(self):
+        return max(self.dropout.p, self.self_attn.dropout.p, self.feed_forward.dropout.p, self.feed_forward_macaron.dropout.p)
+
     def derived_generation(self):
         return (self.feed_forward_macaron._derived.generation + self.feed_forward._derived.generation +
                 self.self_attn._derived.generation + self.conv_module._derived.generation)
@@ -48,8 +51,17 @@ class ConformerEncoderLayer(nn.Module):
                 inputs_pad_mask=torch.ones((0, 0, 0), dtype=torch.bool),
                 attn_cache=torch.ones((0, 0, 0), dtype=torch.bool),
                 cnn_cache=torch.ones((0, 0, 0), dtype=torch.bool)):
-        engine.check_inference_only(self, max(self.dropout.p, self.self_attn.dropout.p))
         dtype = engine.resolve_dtype(self)
+        if engine.wants_autograd(self, inputs) or (self.training and self._max_dropout() > 0.0):
+            # differentiable / dropout-capable schedule (training.py); the batched forward only (no streaming cache)
+            if attn_cache is not None and attn_cache.dim() == 4 and attn_cache.size(0) > 0:
+                raise NotImplementedError("training with a streaming attention cache is not implemented")
+            from . import training
+            out = training.run_stack(inputs.float(), [self], None, inputs_attn_mask, pos_embed, inputs_pad_mask, dtype)
+            B, T, d = inputs.shape
+            new_cnn_cache = torch.zeros((0, 0, 0), dtype=inputs.dtype, device=inputs.device)
+            new_attn_cache = torch.zeros((0, 0, 0, 0), dtype=inputs.dtype, device=inputs.device)
+            return out.to(inputs.dtype), inputs_attn_mask, new_attn_cache, new_cnn_cache
         out, caches = engine.run_layers(inputs.float(), [self], None, inputs_attn_mask, pos_embed, inputs_pad_mask,
                                         [attn_cache], True, dtype)
         new_cnn_cache = torch.zeros((0, 0, 0), dtype=inputs.dtype, device=inputs.device)

@@ -39,14 +39,30 @@ def resolve_dtype(module):
     return dt or torch.float32
 
 
-def check_inference_only(module, dropout_p):
-    """Round-1 scope: forward kernels only.  Eval always runs; training-mode forward (BatchNorm batch
-    statistics) runs under torch.no_grad() when all dropouts are 0; autograd is not wired yet."""
-    if module.training:
-        if dropout_p > 0.0:
-            raise NotImplementedError("native training-mode dropout is not implemented; set dropouts to 0 or call eval()")
-        if torch.is_grad_enabled():
-            raise NotImplementedError("backward kernels are not implemented yet: call under torch.no_grad()")
+def wants_autograd(module, *inputs):
+    """True when the caller expects a differentiable result: grad mode is on and an input or a parameter requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def check_inference_only(module, dropout_p, *inputs):
+    """Guard of the STANDALONE sub-module forwards (feed-forward / attention / convolution module called on their own):
+    they run the inference kernels, whose outputs carry no autograd graph.  Differentiable and dropout-capable execution
+    is implemented at the granularity the reference trains at -- ConformerEncoderLayer / ConformerEncoder (training.py)
+    -- so a call that expects gradients or dropout here raises instead of silently returning a detached tensor."""
+    for t in inputs:
+        if isinstance(t, torch.Tensor) and not t.is_cuda:
+            raise RuntimeError("expected a CUDA tensor (the B200 Conformer kernels have no CPU path)")
+    if module.training and dropout_p > 0.0:
+        raise NotImplementedError("dropout > 0 in training mode is implemented by ConformerEncoderLayer / ConformerEncoder "
+                                  "(conformer_pytorch_lightning_b200.training), not by the stand-alone sub-module forward")
+    if wants_autograd(module, *inputs):
+        raise NotImplementedError("this stand-alone sub-module forward is inference only (its output would be detached); "
+                                  "differentiate through ConformerEncoderLayer / ConformerEncoder, or call it under "
+                                  "torch.no_grad()")
 
 
 # --------------------------------------------------------------------------- workspace

@@ -24,7 +24,7 @@ class PositionwiseFeedForwardModule(nn.Module):
         return self._derived.get(self, dtype, lambda dt: engine.ffn_weights(self, dt))
 
     def forward(self, inputs):
-        engine.check_inference_only(self, self.dropout.p)
+        engine.check_inference_only(self, self.dropout.p, inputs)
         dtype = engine.resolve_dtype(self)
         shape = inputs.shape
         y = inputs.reshape(-1, shape[-1]).to(dtype).contiguous()

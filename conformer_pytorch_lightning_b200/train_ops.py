@@ -87,13 +87,14 @@ def glu_bwd(du, g, dg, dbias):
     return dg
 
 
-def bn_silu_bwd(dc, raw, mean, rstd, gamma, beta, sums, draw):
+def bn_silu_bwd(dc, raw, mean, rstd, gamma, beta, sums, draw, *, batch_stats=True):
     _req(dc, "bn_silu_bwd.dc")
     _req(raw, "bn_silu_bwd.raw", torch.float32)
     _req(draw, "bn_silu_bwd.draw", dc.dtype)
     rows, d = raw.shape
     N.check(N.lib().cfm_bn_silu_bwd(dc.data_ptr(), raw.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                    beta.data_ptr(), sums.data_ptr(), draw.data_ptr(), rows, d, _DT[dc.dtype], _stream(dc)))
+                                    beta.data_ptr(), sums.data_ptr(), draw.data_ptr(), rows, d, _DT[dc.dtype],
+                                    1 if batch_stats else 0, _stream(dc)))
     return draw
 
 

@@ -295,10 +295,11 @@ int cfm_scale_dropout_bwd(const float* dx, void* df, float* dbias, int rows, int
  * pointwise_conv1). */
 int cfm_glu_fwd(const void* g, void* u, int rows, int d, int dtype, void* stream);
 int cfm_glu_bwd(const float* du, const void* g, void* dg, float* dbias, int rows, int d, int dtype, void* stream);
-/* Backward of SiLU(BatchNorm1d(raw)) with BATCH statistics (convolution.py:44-45): sums[0..d) = dgamma, sums[d..2d) =
- * dbeta of THIS call (overwritten), draw = gradient w.r.t. the depthwise-conv output. */
+/* Backward of SiLU(BatchNorm1d(raw)) (convolution.py:44-45): sums[0..d) = dgamma, sums[d..2d) = dbeta of THIS call
+ * (overwritten), draw = gradient w.r.t. the depthwise-conv output.  batch_stats = 1: mean / rstd are the batch
+ * statistics of `raw` (training mode: the statistics depend on the input); 0: running statistics (eval mode). */
 int cfm_bn_silu_bwd(const void* dc, const float* raw, const float* mean, const float* rstd, const float* gamma,
-                    const float* beta, float* sums, void* draw, int rows, int d, int dtype, void* stream);
+                    const float* beta, float* sums, void* draw, int rows, int d, int dtype, int batch_stats, void* stream);
 /* Weight / bias gradient of the depthwise Conv1d (convolution.py:43): dw (k, d) += ..., dbias (d) += ...; the input
  * gradient is cfm_dwconv with the tap-reversed filter. */
 int cfm_dwconv_wgrad(const void* dy, const void* u, float* dw, float* dbias, int B, int T, int d, int k, int dtype,

@@ -146,12 +146,12 @@ def chunk_mask(T, chunk, left):
     return vis
 
 
-def encoder_embed(feats, lengths, sd, cfg):
+def encoder_embed(feats, lengths, sd, cfg, grad=False):
     """encoder.py:59-71 for the relative-position model without dynamic chunks: pad mask -> subsampling ->
     positions (table sliced by batch size, D2) -> attention mask (pad mask, AND static chunk mask if configured)."""
     B, Tin, _ = feats.shape
     pad = (torch.arange(Tin).unsqueeze(0) < lengths.unsqueeze(1).long()).unsqueeze(1)
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         x, pad = subsampling(feats, pad, sd)
     pos = rel_pos_table(cfg.get("max_len", 5000), cfg["encoder_dim"])[:B]
     attn = pad
@@ -181,3 +181,23 @@ def ctc_loss(encoder_out, encoder_out_lens, padded_labels, label_lengths, w, b):
     probs = logits.transpose(0, 1).log_softmax(2)
     loss = F.ctc_loss(probs.float(), padded_labels, encoder_out_lens, label_lengths, blank=0, reduction="sum")
     return loss / padded_labels.size(1)
+
+
+def train_step_grads(feats, lengths, labels, label_lengths, sd, ctc_w, ctc_b, cfg):
+    """Training-mode forward (dropout 0) + CTC loss + backward on torch's CPU autograd: the gradients the reference's
+    training_step (module.py:49-69 -> model.py:115-124 -> decoder.py:18-23) produces for the CTC branch.
+    Returns (loss, out, {state_dict key: grad}, {"ctc_lo.weight"/"ctc_lo.bias": grad}, bn_states)."""
+    leaves = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd.items()}
+    w = ctc_w.clone().requires_grad_()
+    b = ctc_b.clone().requires_grad_()
+    x, pos, pad, attn = encoder_embed(feats, lengths, leaves, cfg, grad=True)
+    st = [{"running_mean": leaves[f"encoders.{i}.conv_module.norm.running_mean"],
+           "running_var": leaves[f"encoders.{i}.conv_module.norm.running_var"], "num_batches_tracked": 0}
+          for i in range(cfg["encoder_num_layers"])]
+    out = encoder_layers_train(x, attn, pos, pad, leaves, cfg, bn_states=st)
+    out_lens = pad.squeeze(1).sum(1)
+    loss = ctc_loss(out, out_lens, labels, label_lengths, w, b)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if v.is_floating_point() and v.requires_grad}
+    return loss.detach(), out.detach(), grads, {"ctc_lo.weight": w.grad, "ctc_lo.bias": b.grad}, st

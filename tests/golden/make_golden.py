@@ -190,5 +190,52 @@ def main():
          **{k.replace(".", "__"): v for k, v in after.items()})
 
 
+def grad_sample(g, cap=2048):
+    """Strided subsample of a gradient tensor (keeps the fixture small) -- the test re-applies the same stride."""
+    flat = np.asarray(g, dtype=np.float32).reshape(-1)
+    stride = max(1, flat.size // cap)
+    return flat[::stride].copy()
+
+
+def case_train_grad():
+    """BASELINE configs[4] in miniature: training-mode forward + CTC loss + backward through the REAL reference encoder
+    and its CTCDecoder (decoder.py:7-23), static chunk-16 attention mask, every dropout 0 (module.py:49-69 is
+    loss.backward() on exactly this graph).  Stores the loss, the encoder output, and for EVERY parameter the gradient's
+    L2 norm and a strided subsample."""
+    from decoder import CTCDecoder  # reference
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, hidden_dim=512, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0,
+                          static_chunk_size=16)
+    seed, V, Lmax = 21, 300, 9
+    rs = np.random.RandomState(77)
+    feats = rs.standard_normal((3, 299, 80)).astype(np.float32)
+    lens = np.asarray([299, 250, 173], dtype=np.int32)
+    labels = rs.randint(1, V, size=(3, Lmax)).astype(np.int64)
+    labels[1, 4] = labels[1, 3]
+    lab_len = np.asarray([9, 7, 4], dtype=np.int64)
+    ctc_w = rs.uniform(-1 / 16, 1 / 16, size=(V, 256)).astype(np.float32)
+    ctc_b = rs.uniform(-1 / 16, 1 / 16, size=(V,)).astype(np.float32)
+    enc, _ = build_ref(cfg, seed)
+    enc.train()
+    dec = CTCDecoder(V, 256, 0.0)
+    dec.load_state_dict({"ctc_lo.weight": torch.from_numpy(ctc_w), "ctc_lo.bias": torch.from_numpy(ctc_b)})
+    out, mask = enc(torch.from_numpy(feats), torch.from_numpy(lens))
+    out_lens = mask.squeeze(1).sum(1)
+    loss = dec(out, out_lens, torch.from_numpy(labels), torch.from_numpy(lab_len))
+    loss.backward()
+    arrays = {}
+    for k, p in list(enc.named_parameters()) + [("ctc." + k, p) for k, p in dec.named_parameters()]:
+        key = k.replace(".", "__")
+        g = p.grad.detach().numpy()
+        arrays["gn__" + key] = np.float64(np.linalg.norm(g.astype(np.float64)))
+        arrays["gs__" + key] = grad_sample(g)
+    after = {k.replace(".", "__"): v.detach().numpy() for k, v in enc.state_dict().items() if "norm.running" in k}
+    save("m2_train_grad", cfg, seed, feats=feats, lens=lens, labels=labels, lab_len=lab_len, ctc_w=ctc_w, ctc_b=ctc_b,
+         loss=np.float64(loss.item()), out=out.detach().numpy(), out_lens=out_lens.numpy(), **arrays, **after)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "train_grad":
+        case_train_grad()
+    else:
+        main()
+        case_train_grad()

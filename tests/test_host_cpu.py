@@ -102,11 +102,15 @@ def test_cpu_tensors_raise_no_fallback():
         ffn(torch.randn(2, 5, 256))
 
 
-def test_training_guard():
+def test_training_on_cpu_raises_too():
+    """The training path (autograd + dropout) is native as well: CPU tensors raise, nothing falls back to PyTorch."""
     cfg = O.conformer_cfg("M", encoder_num_layers=1)
     enc = C.ConformerEncoder(cmvn=None, **encoder_kwargs(cfg)).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         enc(torch.randn(1, 100, 80), torch.tensor([100]))
+    dec = C.CTCDecoder(50, 256, 0.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dec(torch.randn(1, 10, 256), torch.tensor([10]), torch.ones(1, 3, dtype=torch.long), torch.tensor([3]))
 
 
 def test_product_never_imports_oracle():

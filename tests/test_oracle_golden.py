@@ -172,3 +172,36 @@ def test_torch_cpu_port_training_forward():
         assert max_rel(s["running_mean"].numpy(), g[key + "running_mean"]) < 1e-5
         assert max_rel(s["running_var"].numpy(), g[key + "running_var"]) < 1e-5
         assert s["num_batches_tracked"] == 4
+
+
+def grad_sample(g, cap=2048):
+    flat = np.asarray(g, dtype=np.float32).reshape(-1)
+    return flat[::max(1, flat.size // cap)]
+
+
+def test_torch_cpu_port_training_gradients_match_reference():
+    """CTC loss + every parameter gradient of the training-mode port equal the REAL reference's loss.backward()
+    (tests/golden/m2_train_grad.npz: norms and strided subsamples of all gradients)."""
+    import torch
+    from oracle import conformer_oracle_torch as OT
+    g = load_golden("m2_train_grad")
+    cfg = g["cfg"]
+    sd = OT.to_torch_sd(O.make_state_dict(cfg, g["weight_seed"]))
+    t = torch.from_numpy
+    loss, out, grads, cgrads, st = OT.train_step_grads(t(g["feats"]), t(g["lens"]), t(g["labels"]), t(g["lab_len"]), sd,
+                                                       t(g["ctc_w"]), t(g["ctc_b"]), cfg)
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    assert max_rel(out.numpy(), g["out"]) < TOL
+    n = 0
+    for k, gr in list(grads.items()) + [("ctc." + k, v) for k, v in cgrads.items()]:
+        key = k.replace(".", "__")
+        ref_s, ref_n = g["gs__" + key], float(g["gn__" + key])
+        if ref_n < 1e-5:                      # pos_bias_v / linear_pos: zero up to rounding (SURVEY D2)
+            assert float(gr.norm()) < 1e-4
+            continue
+        assert abs(float(gr.double().norm()) - ref_n) < 1e-3 * ref_n, k
+        assert max_rel(grad_sample(gr.numpy()), ref_s) < 2e-3, k
+        n += 1
+    assert n >= 70
+    for i, s in enumerate(st):
+        assert max_rel(s["running_mean"].numpy(), g[f"encoders__{i}__conv_module__norm__running_mean"]) < 1e-5
