@@ -175,6 +175,42 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_rank_cores(local, world):
+    """One process per GPU: give every rank its own slice of the host cores (NUMA-node local when the GPU's node is
+    known) so that the N Python launch loops and pinned-memory copies do not migrate over each other."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cores) < 2 * world:
+            return None
+        node_cores = None
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(local).pci_bus_id
+            dom = torch.cuda.get_device_properties(local).pci_domain_id
+            dev_id = torch.cuda.get_device_properties(local).pci_device_id
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+            node = int(open(path).read().strip())
+            if node >= 0:
+                txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+                nc = []
+                for part in txt.split(","):
+                    a, _, b = part.partition("-")
+                    nc += list(range(int(a), int(b or a) + 1))
+                node_cores = [c for c in nc if c in cores]
+        except Exception:
+            node_cores = None
+        per = len(cores) // world
+        mine = cores[local * per:(local + 1) * per]
+        if node_cores and len(node_cores) >= per:
+            # the ranks that share this NUMA node split its cores among themselves
+            k = local % max(1, len(node_cores) // per)
+            mine = node_cores[k * per:(k + 1) * per] or mine
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -189,6 +225,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    pinned_cores = pin_rank_cores(local, world)
     real_stdout = None
     if world > 1:
         # NCCL writes its banner / INFO log to stdout whenever it likes; stdout must carry exactly one JSON line, so for
@@ -443,7 +480,8 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: Conformer-{cfg_name} {cfg['encoder_num_layers']}L d={d} "
                                        f"encoder layers+after_norm, batch {B} x {WORKLOADS[args.workload][2]:.0f} s per GPU (T={T})",
-                           "per_gpu_batch": B, "timing": "CUDA events per step on the launch stream; 256 MiB write flushes L2 between steps"},
+                           "per_gpu_batch": B, "timing": "CUDA events per step on the launch stream; 256 MiB write flushes L2 between steps",
+                           "host_cores_per_rank": None if pinned_cores is None else len(pinned_cores)},
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(feats_host.numel() * 4 + lens_np.nbytes),
                         "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "serial_latency_ms": lat_ms,
@@ -554,6 +592,164 @@ def strong_scaling_leg(args, enc, cfg, dev, rank, world, dtype, flush, barrier):
                     "of the (B/N, T, d) outputs, D2H of the assembled batch on rank 0; wall clock, max over ranks"}
 
 
+def run_train(args):
+    """Workload C5 (BASELINE.json configs[4]): Conformer-M training step -- forward + CTC loss + backward + gradient
+    all-reduce + optimizer step -- with a static chunk-16 attention mask, bf16 compute, 16 utterances x 10 s per GPU
+    (batch 128 on 8 GPUs; weak scaling), dropout 0.1 as shipped (train.sh).  The layer stack's forward/backward and the
+    CTC head run on the native kernels (training.py, ctc.py); the sub-sampling front-end's autograd stays in PyTorch
+    (outside the measured path by north_star); gradients of layer i are all-reduced over NCCL while layers i-1.. are
+    still in backward (ddp.GradSync).  value = device-timed steps with the batch resident in HBM; e2e = the same step fed
+    from pinned host memory with the loss read back every step."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import build_encoder
+    from oracle import conformer_oracle as O       # cfg + seeded weights only
+    import conformer_pytorch_lightning_b200 as C
+    from conformer_pytorch_lightning_b200 import _native, ddp, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pin_rank_cores(local, world)
+    real_stdout = None
+    if world > 1:
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+    B, sec, V, Lmax = 16, 10.0, 5002, 40
+    tin, T = frames(sec)
+    cfg = O.conformer_cfg("M", static_chunk_size=16, dropout=0.1, attention_dropout=0.1, pos_enc_dropout=0.1)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    enc = build_encoder(cfg, 0, device=dev, compute_dtype=dtype).train()
+    dec = C.CTCDecoder(V, cfg["encoder_dim"], 0.0).to(dev)
+    dec.compute_dtype = dtype
+    ddp.broadcast_parameters(enc)
+    ddp.broadcast_parameters(dec)
+    sync = ddp.attach(enc) if world > 1 else None
+    other = [p for n, p in enc.named_parameters() if n.startswith("embed.")] + list(dec.parameters())
+    opt = torch.optim.Adam(list(enc.parameters()) + list(dec.parameters()), lr=1e-4, fused=True)
+    rs = np.random.RandomState(1234 + rank)
+    feats_host = torch.from_numpy(rs.standard_normal((B, tin, 80)).astype(np.float32)).pin_memory()
+    lens = torch.full((B,), tin, dtype=torch.int32, device=dev)
+    labels = torch.from_numpy(rs.randint(1, V - 1, size=(B, Lmax)).astype(np.int64)).to(dev)
+    lab_len = torch.full((B,), Lmax, dtype=torch.int64, device=dev)
+    feats_dev = feats_host.to(dev)
+    audio_s = B * ((tin - 1) * 160 + 400) / 16000.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(feats):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+            out, mask = enc(feats, lens)
+        loss = dec(out.float(), mask.squeeze(1).sum(1), labels, lab_len)
+        loss.backward()
+        if world > 1:
+            ddp.sync_grads(other)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step(feats_dev)
+    barrier()
+    n0 = _native.launch_count() + engine.GRAPH_REPLAYED_LAUNCHES[0]
+    total_ms = 0.0
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            step(feats_dev)
+            e_.record()
+            e_.synchronize()
+            total_ms += s_.elapsed_time(e_)
+    barrier()
+    launches = _native.launch_count() + engine.GRAPH_REPLAYED_LAUNCHES[0] - n0
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    value = world * audio_s / (ms / 1e3)
+    # e2e: batch from pinned host memory, loss read back on the host every step
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(5, args.steps // 2)
+    for _ in range(e2e_steps):
+        loss = step(feats_host.to(dev, non_blocking=True))
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(loss_host)
+    e2e_t = torch.tensor([1e3 * (time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+    barrier()
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item())
+    # per-phase device time of one step (events; eager): forward / backward / optimizer
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    opt.zero_grad(set_to_none=True)
+    ev[0].record()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+        out, mask = enc(feats_dev, lens)
+    loss = dec(out.float(), mask.squeeze(1).sum(1), labels, lab_len)
+    ev[1].record()
+    loss.backward()
+    if world > 1:
+        ddp.sync_grads(other)
+    ev[2].record()
+    opt.step()
+    ev[3].record()
+    torch.cuda.synchronize()
+    phases = {"forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]),
+              "optimizer_ms": ev[2].elapsed_time(ev[3])}
+    fam = {f: _native.kernel_launches(f) for f in ("gemm_tc", "gemm_gen", "gemm_gen_simt", "gemm_simt", "ln_bwd", "softmax_bwd",
+                                                   "ctc_grad", "dwconv_wgrad")}
+    pk = peaks()
+    clocks = clk.summary()
+    burst_ok = ("sw_power_cap" not in clocks["reasons"] and clocks["sm_mhz"] is not None and clocks["sm_max_mhz"]
+                and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
+    tf_peak = pk["tf_burst"] if burst_ok else pk["tf_sustained"]
+    algo_tf = 6.142 / 8.0                           # SURVEY 8d: C5 fwd+bwd of the layer stack per 16-utterance shard
+    ctc_tf = 3 * 2.0 * B * T * cfg["encoder_dim"] * V / 1e12
+    if rank == 0:
+        line = {"metric": "training audio-sec/sec (fwd + CTC loss + bwd + grad all-reduce + optimizer step)", "value": value,
+                "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"C5: Conformer-M training, CTC loss (V={V}, {Lmax} labels/utt), static chunk-16 mask, "
+                                       f"dropout 0.1, batch {B} x {sec:.0f} s per GPU (T={T}), Adam",
+                           "per_gpu_batch": B, "global_batch": B * world,
+                           "timing": "CUDA events per step on the launch stream; 256 MiB write flushes L2 between steps"},
+                "e2e": {"value": world * audio_s / (e2e_ms / 1e3), "unit": "audio-s/s",
+                        "h2d_bytes_per_step": int(feats_host.numel() * 4), "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                        "steps": e2e_steps,
+                        "api": "ConformerEncoder.forward (train mode, autograd) + CTCDecoder.forward + loss.backward() + "
+                               "ddp.GradSync per-layer all-reduce + torch.optim.Adam(fused).step(); features from pinned host "
+                               "memory and the loss read back on the host every step"},
+                "gpu_launches": launches, "phases": phases, "kernels_total": fam,
+                "roofline": {"bound": "tensor", "kernel": "whole step (layer stack fwd+bwd + CTC head GEMMs), algorithmic FLOP of "
+                             "SURVEY 8d (3 x forward) over the device-timed step",
+                             "achieved": (algo_tf + ctc_tf) / (ms / 1e3), "peak": tf_peak, "unit": "TFLOP/s",
+                             "frac": (algo_tf + ctc_tf) / (ms / 1e3) / tf_peak, "traffic": None},
+                "grad_allreduce": None if sync is None else {"buckets_per_step": sync.buckets_sent // max(1, (args.steps + max(3, args.warmup) + e2e_steps + 1)),
+                                                            "bytes_per_step": sync.bytes_sent // max(1, (args.steps + max(3, args.warmup) + e2e_steps + 1))},
+                "cpu_baseline": None, "clocks": clocks}
+        out_f = real_stdout if real_stdout is not None else sys.stdout
+        out_f.write(json.dumps(line) + "\n")
+        out_f.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def enc_make_pad(lens, max_len):
     from conformer_pytorch_lightning_b200.utils import make_pad_mask
     return make_pad_mask(lens, max_len).unsqueeze(1)
@@ -565,14 +761,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS) + ["C5"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU-baseline step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU bar")
     ap.add_argument("--profile", action="store_true", help="measured path only (for ncu): no e2e / probe / cpu legs")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "C5":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm covers the inference workloads C2-C4"}))
+            return
+        run_train(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -67,16 +67,16 @@ def _declare(lib):
     _u64 = ctypes.c_uint64
     lib.cfm_ln_fwd_train.argtypes = [_p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _f, _p]
     lib.cfm_ln_bwd.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]
-    lib.cfm_silu_dropout_fwd.argtypes = [_p, _p, _i, _i, _i, _f, _u64, _i, _p]
-    lib.cfm_silu_dropout_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _f, _u64, _i, _p]
-    lib.cfm_resid_dropout_add.argtypes = [_p, _p, _i, _i, _i, _f, _p, _f, _u64, _i, _p]
-    lib.cfm_scale_dropout_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _u64, _i, _p]
+    lib.cfm_silu_dropout_fwd.argtypes = [_p, _p, _i, _i, _i, _f, _p, _i, _p]
+    lib.cfm_silu_dropout_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _f, _p, _i, _p]
+    lib.cfm_resid_dropout_add.argtypes = [_p, _p, _i, _i, _i, _f, _p, _f, _p, _i, _p]
+    lib.cfm_scale_dropout_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _p, _i, _p]
     lib.cfm_glu_fwd.argtypes = [_p, _p, _i, _i, _i, _p]
     lib.cfm_glu_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]
     lib.cfm_bn_silu_bwd.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]
     lib.cfm_dwconv_wgrad.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]
-    lib.cfm_softmax_fwd.argtypes = [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]
-    lib.cfm_softmax_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _i, _p]
+    lib.cfm_softmax_fwd.argtypes = [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]
+    lib.cfm_softmax_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]
     lib.cfm_colsum.argtypes = [_p, _i64, _p, _i, _i, _i, _p]
     lib.cfm_ctc_loss_ws_bytes.argtypes = [_i, _i, _i]
     lib.cfm_ctc_loss_ws_bytes.restype = _i64

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_
 }
 
 struct Drop {
-  unsigned long long seed;
+  const unsigned long long* seed_dev;   // device scalar: a captured CUDA graph replays with a fresh seed
   uint32_t site;
   uint32_t thr;      // drop when random < thr  (thr = p * 2^32)
   float scale;       // 1 / (1 - p); p == 0: thr = 0, scale = 1
@@ -40,10 +40,11 @@ __device__ __forceinline__ void drop_mult(const Drop& d, unsigned long long e, f
     for (int i = 0; i < VEC; ++i) m[i] = 1.f;
     return;
   }
+  const unsigned long long seed = __ldg(d.seed_dev);
 #pragma unroll
   for (int q = 0; q < VEC / 4; ++q) {
     const unsigned long long c = (e >> 2) + q;
-    const uint4 r = philox4x32_10((uint32_t)d.seed, (uint32_t)(d.seed >> 32), (uint32_t)c, (uint32_t)(c >> 32), d.site, 0u);
+    const uint4 r = philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)c, (uint32_t)(c >> 32), d.site, 0u);
     m[4 * q + 0] = r.x < d.thr ? 0.f : d.scale;
     m[4 * q + 1] = r.y < d.thr ? 0.f : d.scale;
     m[4 * q + 2] = r.z < d.thr ? 0.f : d.scale;
@@ -51,10 +52,10 @@ __device__ __forceinline__ void drop_mult(const Drop& d, unsigned long long e, f
   }
 }
 
-inline Drop make_drop(float p, unsigned long long seed, int site) {
+inline Drop make_drop(float p, const uint64_t* seed_dev, int site) {
   Drop d;
-  d.seed = seed; d.site = (uint32_t)site;
-  if (p <= 0.f) { d.thr = 0u; d.scale = 1.f; }
+  d.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev); d.site = (uint32_t)site;
+  if (p <= 0.f || seed_dev == nullptr) { d.thr = 0u; d.scale = 1.f; }
   else {
     double t = (double)p * 4294967296.0;
     d.thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
@@ -599,7 +600,7 @@ static int check_rc(int rows, int cols, int dtype, const char* who) {
   return 0;
 }
 
-extern "C" int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, float p, uint64_t seed, int site,
+extern "C" int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, float p, const uint64_t* seed, int site,
                                     void* stream) {
   CFM_CHECK_ARG(h && a, "cfm_silu_dropout_fwd: null pointer");
   if (check_rc(rows, cols, dtype, "cfm_silu_dropout_fwd") != 0) return -1;
@@ -612,7 +613,7 @@ extern "C" int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, 
 }
 
 extern "C" int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, float* dbias, int rows, int cols, int dtype,
-                                    float p, uint64_t seed, int site, void* stream) {
+                                    float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(da && h && dh, "cfm_silu_dropout_bwd: null pointer");
   if (check_rc(rows, cols, dtype, "cfm_silu_dropout_bwd") != 0) return -1;
   if (rows == 0) return 0;
@@ -624,7 +625,7 @@ extern "C" int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, flo
 }
 
 extern "C" int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols, int dtype, float alpha,
-                                     const uint8_t* row_valid, float p, uint64_t seed, int site, void* stream) {
+                                     const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(x && f, "cfm_resid_dropout_add: null pointer");
   if (check_rc(rows, cols, dtype, "cfm_resid_dropout_add") != 0) return -1;
   if (rows == 0) return 0;
@@ -636,7 +637,7 @@ extern "C" int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols
 }
 
 extern "C" int cfm_scale_dropout_bwd(const float* dx, void* df, float* dbias, int rows, int cols, int dtype, float alpha,
-                                     const uint8_t* row_valid, float p, uint64_t seed, int site, void* stream) {
+                                     const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(dx && df, "cfm_scale_dropout_bwd: null pointer");
   if (check_rc(rows, cols, dtype, "cfm_scale_dropout_bwd") != 0) return -1;
   if (rows == 0) return 0;
@@ -702,7 +703,7 @@ extern "C" int cfm_dwconv_wgrad(const void* dy, const void* u, float* dw, float*
 }
 
 extern "C" int cfm_softmax_fwd(const float* S, void* P, void* Pd, const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, int B,
-                               int H, int Tq, int Tk, int Tp, int dtype, float p, uint64_t seed, int site, void* stream) {
+                               int H, int Tq, int Tk, int Tp, int dtype, float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(S && P, "cfm_softmax_fwd: null pointer");
   CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_softmax_fwd: bad dtype");
   CFM_CHECK_ARG(Tp >= Tk && Tp % 8 == 0, "cfm_softmax_fwd: row stride %d must be a multiple of 8 and >= Tk=%d", Tp, Tk);
@@ -718,7 +719,7 @@ extern "C" int cfm_softmax_fwd(const float* S, void* P, void* Pd, const uint8_t*
 }
 
 extern "C" int cfm_softmax_bwd(const void* P, const float* dPd, void* dS, int B, int H, int Tq, int Tk, int Tp, int dtype,
-                               float p, uint64_t seed, int site, void* stream) {
+                               float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(P && dPd && dS, "cfm_softmax_bwd: null pointer");
   CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_softmax_bwd: bad dtype");
   CFM_CHECK_ARG(Tp >= Tk && Tp % 8 == 0, "cfm_softmax_bwd: bad row stride");

@@ -65,7 +65,7 @@ class ConformerEncoder(nn.Module):
             # (training.py); the per-layer gradient buckets go to self.grad_sync (ddp.GradSync) when one is attached
             from . import training
             return training.run_stack(outputs.float(), list(self.encoders), self.after_norm, inputs_attn_mask, pos_embed,
-                                      inputs_pad_mask, dtype, grad_sync=getattr(self, "grad_sync", None))
+                                      inputs_pad_mask, dtype, grad_sync=getattr(self, "grad_sync", None), owner=self)
         batched_pos = pos_embed is None or pos_embed.numel() == outputs.size(0) * outputs.size(2)
         if (self.use_cuda_graphs and not self.training and outputs.is_cuda and batched_pos
                 and not torch.cuda.is_current_stream_capturing()):

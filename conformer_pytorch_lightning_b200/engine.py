@@ -115,12 +115,15 @@ class Derived:
     def __init__(self):
         self.slots = {}
         self.generation = 0
+        self.force = False        # one-shot: rebuild even if the key matches (used while capturing a training graph, so
+                                  # that the re-derivation itself becomes part of the graph and runs at every replay)
 
     def get(self, module, dtype, build):
         tensors = list(module.parameters(recurse=True)) + list(module.buffers(recurse=True))
         key = (module.training,) + tuple((p.data_ptr(), p._version) for p in tensors)
         slot = self.slots.get(dtype)
-        if slot is None or slot[0] != key:
+        force, self.force = self.force, False
+        if slot is None or slot[0] != key or force:
             with torch.no_grad():
                 new = build(dtype)
             old = slot[1] if slot is not None else None

@@ -8,6 +8,15 @@ from . import _native as N
 from .ops import _DT, _ptr, _req, _stream, ensure_init
 
 
+def _seed_ptr(seed, p):
+    """Dropout seeds live on the device (one int64 / uint64 element) so that CUDA graphs can replay with new seeds."""
+    if p <= 0.0 or seed is None:
+        return 0
+    if not (isinstance(seed, torch.Tensor) and seed.is_cuda and seed.dtype in (torch.int64, torch.uint64) and seed.numel() >= 1):
+        raise RuntimeError("dropout seed must be a CUDA int64 tensor with one element")
+    return seed.data_ptr()
+
+
 def ln_fwd(x, g, b, y, mean, rstd, *, row_valid=None, eps=1e-5):
     """y = rowmask(LN(x)); mean / rstd (rows,) fp32 saved for the backward."""
     _req(x, "ln_fwd.x", torch.float32)
@@ -36,7 +45,7 @@ def silu_dropout_fwd(h, a, *, p=0.0, seed=0, site=0):
     _req(a, "silu_dropout_fwd.a", h.dtype)
     rows, cols = h.shape
     ensure_init(h)
-    N.check(N.lib().cfm_silu_dropout_fwd(h.data_ptr(), a.data_ptr(), rows, cols, _DT[h.dtype], float(p), int(seed), int(site),
+    N.check(N.lib().cfm_silu_dropout_fwd(h.data_ptr(), a.data_ptr(), rows, cols, _DT[h.dtype], float(p), _seed_ptr(seed, p), int(site),
                                          _stream(h)))
     return a
 
@@ -46,7 +55,7 @@ def silu_dropout_bwd(da, h, dh, dbias, *, p=0.0, seed=0, site=0):
     _req(h, "silu_dropout_bwd.h", da.dtype)
     rows, cols = h.shape
     N.check(N.lib().cfm_silu_dropout_bwd(da.data_ptr(), h.data_ptr(), dh.data_ptr(), _ptr(dbias), rows, cols, _DT[h.dtype],
-                                         float(p), int(seed), int(site), _stream(h)))
+                                         float(p), _seed_ptr(seed, p), int(site), _stream(h)))
     return dh
 
 
@@ -56,7 +65,7 @@ def resid_dropout_add(x, f, *, alpha=1.0, row_valid=None, p=0.0, seed=0, site=0)
     rows, cols = x.shape
     ensure_init(x)
     N.check(N.lib().cfm_resid_dropout_add(x.data_ptr(), f.data_ptr(), rows, cols, _DT[f.dtype], float(alpha), _ptr(row_valid),
-                                          float(p), int(seed), int(site), _stream(x)))
+                                          float(p), _seed_ptr(seed, p), int(site), _stream(x)))
     return x
 
 
@@ -65,7 +74,7 @@ def scale_dropout_bwd(dx, df, dbias, *, alpha=1.0, row_valid=None, p=0.0, seed=0
     _req(df, "scale_dropout_bwd.df")
     rows, cols = dx.shape
     N.check(N.lib().cfm_scale_dropout_bwd(dx.data_ptr(), df.data_ptr(), _ptr(dbias), rows, cols, _DT[df.dtype], float(alpha),
-                                          _ptr(row_valid), float(p), int(seed), int(site), _stream(dx)))
+                                          _ptr(row_valid), float(p), _seed_ptr(seed, p), int(site), _stream(dx)))
     return df
 
 
@@ -118,7 +127,7 @@ def softmax_fwd(S, P, Pd, mask, *, Tk, p=0.0, seed=0, site=0):
         mrs = 0 if mask.shape[1] == 1 else mask.stride(1)
     ensure_init(S)
     N.check(N.lib().cfm_softmax_fwd(S.data_ptr(), P.data_ptr(), _ptr(Pd), _ptr(mask), mbs, mrs, B, H, Tq, Tk, Tp, _DT[P.dtype],
-                                    float(p), int(seed), int(site), _stream(S)))
+                                    float(p), _seed_ptr(seed, p), int(site), _stream(S)))
 
 
 def softmax_bwd(P, dPd, dS, *, Tk, p=0.0, seed=0, site=0):
@@ -127,7 +136,7 @@ def softmax_bwd(P, dPd, dS, *, Tk, p=0.0, seed=0, site=0):
     _req(dS, "softmax_bwd.dS", P.dtype)
     B, H, Tq, Tp = P.shape
     N.check(N.lib().cfm_softmax_bwd(P.data_ptr(), dPd.data_ptr(), dS.data_ptr(), B, H, Tq, Tk, Tp, _DT[P.dtype], float(p),
-                                    int(seed), int(site), _stream(P)))
+                                    _seed_ptr(seed, p), int(site), _stream(P)))
 
 
 def colsum(x, out):

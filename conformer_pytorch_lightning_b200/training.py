@@ -96,7 +96,7 @@ class TrainRun:
         self.layers, self.after_norm = layers, after_norm
         self.attn_mask = engine._mask_u8(attn_mask)
         self.row_valid = engine._row_valid(pad_mask, B, T)
-        self.B, self.T, self.dtype, self.seed = B, T, dtype, int(seed)
+        self.B, self.T, self.dtype, self.seed = B, T, dtype, seed        # seed: device int64 tensor, one element
         self.grad_sync = grad_sync
         self.saved = None
 
@@ -341,47 +341,61 @@ def _conv_bwd(dx, s, W, ln_g, layer, bk, run, n, d, p_out, site_out):
     return dx_out
 
 
+def backward_head(run, dx):
+    """after_norm backward (encoder.py:74).  Returns (dx, [g_weight, g_bias] or None)."""
+    after = run.saved[1]
+    if after is None:
+        return dx, None
+    d = dx.shape[-1]
+    gg, gb = torch.zeros(d, device=dx.device), torch.zeros(d, device=dx.device)
+    nxt = torch.empty_like(dx)
+    TO.ln_bwd(dx, after["x"], after["mean"], after["rstd"], engine._f32(run.after_norm.weight), nxt, gg, gb)
+    return nxt, [gg, gb]
+
+
+def backward_layer(run, li, dx, release=True):
+    """Backward of layer ``li``.  Returns (dx w.r.t. the layer input, the layer's flat gradient bucket)."""
+    saved = run.saved[0]
+    layer = run.layers[li]
+    n, d = dx.shape
+    dev = dx.device
+    Wl = layer.derived_weights(run.dtype)
+    sv = saved[li]
+    p = sv["p"]
+    H = layer.self_attn.num_heads
+    F = Wl["ff"]["w1"].shape[0]
+    k = Wl["conv"]["dw_w"].shape[0]
+    bucket = _Bucket(d, F, k, dev)
+    bk = bucket.v
+    base = li * SITES_PER_LAYER
+    nxt = torch.empty_like(dx)
+    TO.ln_bwd(dx, sv["fin"]["x"], sv["fin"]["mean"], sv["fin"]["rstd"], Wl["fin_g"], nxt, bk["ln_fin_g"], bk["ln_fin_b"])
+    dx = nxt
+    dx = _ffn_bwd(dx, sv["ff"], Wl["ff"], Wl["ff_g"], bk, "ff", n, d, run.dtype, p["ff"], p["layer"], run.seed,
+                  base + S_FF_IN, base + S_FF_OUT)
+    dx = _conv_bwd(dx, sv["conv"], Wl["conv"], Wl["conv_g"], layer, bk, run, n, d, p["layer"], base + S_CONV_OUT)
+    dx = _mhsa_bwd(dx, sv["mha"], Wl["mha"], Wl["mha_g"], bk, run, H, n, d, p["att"], p["layer"], base + S_ATT_P,
+                   base + S_ATT_OUT)
+    dx = _ffn_bwd(dx, sv["ffm"], Wl["ffm"], Wl["ffm_g"], bk, "ffm", n, d, run.dtype, p["ffm"], p["layer"], run.seed,
+                  base + S_FFM_IN, base + S_FFM_OUT)
+    if release:
+        saved[li] = None                                          # release this layer's activations
+    return dx, bucket
+
+
 def stack_backward(dout, run):
-    """Returns (dx_emb (B,T,d) fp32, [per-layer gradient lists in layer_param_list order], after_norm grads)."""
-    saved, after = run.saved
+    """Eager backward.  Returns (dx_emb (B,T,d) fp32, [per-layer gradient lists in layer_param_list order], after_norm
+    grads)."""
     B, T = run.B, run.T
     d = dout.shape[-1]
-    n = B * T
-    dev = dout.device
-    dx = dout.reshape(n, d).float().contiguous()
-    after_grads = None
-    if after is not None:
-        gg, gb = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
-        nxt = torch.empty_like(dx)
-        TO.ln_bwd(dx, after["x"], after["mean"], after["rstd"], engine._f32(run.after_norm.weight), nxt, gg, gb)
-        dx = nxt
-        after_grads = [gg, gb]
+    dx = dout.reshape(B * T, d).float().contiguous()
+    dx, after_grads = backward_head(run, dx)
     layer_grads = [None] * len(run.layers)
     for li in range(len(run.layers) - 1, -1, -1):
-        layer = run.layers[li]
-        Wl = layer.derived_weights(run.dtype)
-        sv = saved[li]
-        p = sv["p"]
-        H = layer.self_attn.num_heads
-        F = Wl["ff"]["w1"].shape[0]
-        k = Wl["conv"]["dw_w"].shape[0]
-        bucket = _Bucket(d, F, k, dev)
-        bk = bucket.v
-        base = li * SITES_PER_LAYER
-        nxt = torch.empty_like(dx)
-        TO.ln_bwd(dx, sv["fin"]["x"], sv["fin"]["mean"], sv["fin"]["rstd"], Wl["fin_g"], nxt, bk["ln_fin_g"], bk["ln_fin_b"])
-        dx = nxt
-        dx = _ffn_bwd(dx, sv["ff"], Wl["ff"], Wl["ff_g"], bk, "ff", n, d, run.dtype, p["ff"], p["layer"], run.seed,
-                      base + S_FF_IN, base + S_FF_OUT)
-        dx = _conv_bwd(dx, sv["conv"], Wl["conv"], Wl["conv_g"], layer, bk, run, n, d, p["layer"], base + S_CONV_OUT)
-        dx = _mhsa_bwd(dx, sv["mha"], Wl["mha"], Wl["mha_g"], bk, run, H, n, d, p["att"], p["layer"], base + S_ATT_P,
-                       base + S_ATT_OUT)
-        dx = _ffn_bwd(dx, sv["ffm"], Wl["ffm"], Wl["ffm_g"], bk, "ffm", n, d, run.dtype, p["ffm"], p["layer"], run.seed,
-                      base + S_FFM_IN, base + S_FFM_OUT)
-        saved[li] = None                                          # release this layer's activations
+        dx, bucket = backward_layer(run, li, dx)
         if run.grad_sync is not None:
             run.grad_sync.bucket_ready(bucket.flat)               # all-reduce overlaps the remaining layers' backward
-        layer_grads[li] = bucket.grads_for(layer, d)
+        layer_grads[li] = bucket.grads_for(run.layers[li], d)
     if run.grad_sync is not None:
         if after_grads is not None:
             for g in after_grads:
@@ -390,41 +404,178 @@ def stack_backward(dout, run):
     return dx.view(B, T, d), layer_grads, after_grads
 
 
+# ----------------------------------------------------------------------------------------------- CUDA-graph plans
+class TrainPlan:
+    """A training step of the stack is ~780 small launches; issued one by one from Python the GPU idles most of the
+    time.  Like the inference path, a (shape, dtype, mask layout, dropout configuration) is captured once into CUDA
+    graphs -- one for the forward of the whole stack, one per layer for the backward (so that each layer's gradient
+    bucket can be handed to the NCCL all-reduce between graph launches) -- and replayed afterwards.  Everything the
+    graphs touch is static: inputs are copied into the plan's buffers, saved activations live in the graphs' memory
+    pool, the dropout seed is a device scalar, the bf16 weight copies are re-derived INSIDE the forward graph."""
+
+    def __init__(self):
+        self.pool = None
+        self.fwd = None
+        self.bwd = None           # list of (graph, stage) in execution order
+        self.busy = False         # a forward whose backward has not run yet owns the static buffers
+        self.calls = 0
+
+
+def _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync):
+    cfg = tuple((l.training, l.conv_module.training, l.dropout.p, l.self_attn.dropout.p, l.feed_forward.dropout.p,
+                 l.feed_forward_macaron.dropout.p, l.conv_module.norm.momentum) for l in layers)
+    return (tuple(x_emb.shape), x_emb.device, dtype, None if attn_mask is None else tuple(attn_mask.shape),
+            None if pad_mask is None else tuple(pad_mask.shape), cfg, after_norm is not None, grad_sync is not None)
+
+
+def _refresh_derived(layers, dtype):
+    for layer in layers:
+        for m in (layer.feed_forward_macaron, layer.feed_forward, layer.self_attn, layer.conv_module):
+            m._derived.force = True
+        layer.derived_weights(dtype)
+
+
+def _capture_forward(plan, x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync):
+    dev = x_emb.device
+    B, T, d = x_emb.shape
+    plan.pool = torch.cuda.graph_pool_handle()
+    plan.x = torch.empty((B, T, d), dtype=torch.float32, device=dev)
+    am = engine._mask_u8(attn_mask)
+    pm = engine._mask_u8(pad_mask)
+    plan.am = None if am is None else torch.empty(am.shape, dtype=torch.bool, device=dev)
+    plan.pm = None if pm is None else torch.empty(pm.shape, dtype=torch.bool, device=dev)
+    plan.seed = torch.zeros(1, dtype=torch.int64, device=dev)
+    _fill_plan(plan, x_emb, am, pm, None)
+    plan.run = TrainRun(layers, after_norm, plan.am, plan.pm, B, T, dtype, plan.seed, grad_sync)
+    g = torch.cuda.CUDAGraph()
+    n0 = N.launch_count()
+    with torch.cuda.graph(g, pool=plan.pool, capture_error_mode="thread_local"):
+        _refresh_derived(layers, dtype)                # bf16 weight copies are re-derived at every replay
+        plan.out = stack_forward(plan.x, plan.run)
+    plan.fwd = g
+    plan.fwd_launches = N.launch_count() - n0
+
+
+def _fill_plan(plan, x_emb, am, pm, seed_host):
+    plan.x.copy_(x_emb)
+    if plan.am is not None:
+        torch.ne(am, 0, out=plan.am)
+    if plan.pm is not None:
+        torch.ne(pm, 0, out=plan.pm)
+    if seed_host is not None:
+        plan.seed.copy_(seed_host, non_blocking=True)
+
+
+def _capture_backward(plan, dout):
+    run = plan.run
+    B, T = run.B, run.T
+    d = dout.shape[-1]
+    plan.dout = torch.empty((B * T, d), dtype=torch.float32, device=dout.device)
+    plan.dout.copy_(dout.reshape(B * T, d))
+    stages = []
+    n0 = N.launch_count()
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=plan.pool, capture_error_mode="thread_local"):
+            res = fn()
+        stages.append(g)
+        return res
+    if run.grad_sync is None:
+        # one graph for the whole backward
+        def whole():
+            dx, after_grads = backward_head(run, plan.dout)
+            buckets = [None] * len(run.layers)
+            for li in range(len(run.layers) - 1, -1, -1):
+                dx, buckets[li] = backward_layer(run, li, dx, release=False)
+            return dx, after_grads, buckets
+        plan.dx, plan.after_grads, plan.buckets = capture(whole)
+        plan.stage_buckets = [None]
+    else:
+        dx, plan.after_grads = capture(lambda: backward_head(run, plan.dout))
+        plan.stage_buckets = [None]
+        plan.buckets = [None] * len(run.layers)
+        for li in range(len(run.layers) - 1, -1, -1):
+            dx, plan.buckets[li] = capture(lambda li=li, dx=dx: backward_layer(run, li, dx, release=False))
+            plan.stage_buckets.append(plan.buckets[li])
+        plan.dx = dx
+    plan.bwd = stages
+    plan.bwd_launches = N.launch_count() - n0
+
+
+def _replay_backward(plan, dout):
+    run = plan.run
+    B, T = run.B, run.T
+    d = dout.shape[-1]
+    if plan.bwd is None:
+        _capture_backward(plan, dout)
+    else:
+        plan.dout.copy_(dout.reshape(B * T, d))
+    sync = run.grad_sync
+    engine.GRAPH_REPLAYED_LAUNCHES[0] += plan.bwd_launches       # native kernels inside the replayed graphs
+    for g, bucket in zip(plan.bwd, plan.stage_buckets):
+        g.replay()
+        if sync is not None and bucket is not None:
+            sync.bucket_ready(bucket.flat)
+    if sync is not None:
+        if plan.after_grads is not None:
+            for t in plan.after_grads:
+                sync.bucket_ready(t)
+        sync.finish()
+    # the buckets are static graph memory: hand autograd private copies (param.grad may keep / alias what it is given)
+    layer_grads = []
+    for li, layer in enumerate(run.layers):
+        b = plan.buckets[li]
+        c = _Bucket.__new__(_Bucket)
+        c.flat = b.flat.clone()
+        c.v = {name: c.flat[v.storage_offset() - b.flat.storage_offset():][:v.numel()].view(v.shape) for name, v in b.v.items()}
+        layer_grads.append(c.grads_for(layer, d))
+    after = None if plan.after_grads is None else [t.clone() for t in plan.after_grads]
+    return plan.dx.view(B, T, d).clone(), layer_grads, after
+
+
 class EncoderStackFunction(torch.autograd.Function):
     """out = layers(x_emb) with the native forward / backward above.  ``params`` (the flattened parameter lists of the
     layers + after_norm) are passed so that autograd routes the returned gradients to them."""
 
     @staticmethod
-    def forward(ctx, x_emb, run, *params):
+    def forward(ctx, x_emb, run, plan, *params):
+        ctx.n_params = len(params)
+        ctx.plan = plan
+        if plan is not None:
+            plan.fwd.replay()
+            engine.GRAPH_REPLAYED_LAUNCHES[0] += plan.fwd_launches
+            plan.busy = True
+            ctx.run = plan.run
+            return plan.out.clone()
         out = stack_forward(x_emb, run)
         ctx.run = run
-        ctx.n_params = len(params)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
-        run = ctx.run
-        if run.saved is None:
-            raise RuntimeError("the native encoder backward can run only once per forward (activations are released)")
-        dx, layer_grads, after_grads = stack_backward(dout, run)
-        run.saved = None
+        run, plan = ctx.run, ctx.plan
+        if plan is not None:
+            if not plan.busy:
+                raise RuntimeError("the native encoder backward can run only once per forward")
+            dx, layer_grads, after_grads = _replay_backward(plan, dout.contiguous())
+            plan.busy = False
+        else:
+            if run.saved is None:
+                raise RuntimeError("the native encoder backward can run only once per forward (activations are released)")
+            dx, layer_grads, after_grads = stack_backward(dout, run)
+            run.saved = None
         flat = [g for lg in layer_grads for g in lg]
         if after_grads is not None:
             flat += after_grads
         assert len(flat) == ctx.n_params
-        return (dx, None) + tuple(flat)
+        return (dx, None, None) + tuple(flat)
 
 
-def needs_training_path(module, inputs, params_fn):
-    """True when the call must go through the differentiable / dropout-capable schedule."""
-    if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in params_fn())):
-        return True
-    return False
-
-
-def run_stack(x_emb, layers, after_norm, attn_mask, pos_embed, pad_mask, dtype, grad_sync=None):
-    """Differentiable (and dropout-capable) replacement of engine.run_layers for the batched forward."""
+def run_stack(x_emb, layers, after_norm, attn_mask, pos_embed, pad_mask, dtype, grad_sync=None, owner=None):
+    """Differentiable (and dropout-capable) replacement of engine.run_layers for the batched forward.  ``owner``: the
+    module that keeps the CUDA-graph plans (None: always eager)."""
     B, T, d = x_emb.shape
     for layer in layers:
         a = layer.self_attn
@@ -433,9 +584,30 @@ def run_stack(x_emb, layers, after_norm, attn_mask, pos_embed, pad_mask, dtype, 
                                       "(its extra output dropout, attention.py:177) is not implemented")
     if pos_embed is not None and pos_embed.numel() != B * d:
         raise NotImplementedError("the training path implements the batched forward (one position row per batch element)")
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item())           # follows torch.manual_seed
-    run = TrainRun(layers, after_norm, attn_mask, pad_mask, B, T, dtype, seed, grad_sync)
+    seed_host = torch.randint(0, 2 ** 62, (1,))                   # CPU generator: follows torch.manual_seed
     params = [p for layer in layers for p in layer_param_list(layer)]
     if after_norm is not None:
         params += [after_norm.weight, after_norm.bias]
-    return EncoderStackFunction.apply(x_emb, run, *params)
+    plan = None
+    if (owner is not None and getattr(owner, "use_cuda_graphs", False) and x_emb.is_cuda and torch.is_grad_enabled()
+            and not torch.cuda.is_current_stream_capturing()
+            and (pad_mask is None or pad_mask.dim() != 3 or pad_mask.size(2) == 0 or tuple(pad_mask.shape) == (B, 1, T))
+            and all(l.conv_module.norm.momentum is not None for l in layers)):
+        plans = owner.__dict__.setdefault("_train_plans", {})
+        key = _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync)
+        cand = plans.get(key)
+        if cand is None:
+            while len(plans) >= 4:
+                plans.pop(next(iter(plans)))
+            plans[key] = cand = TrainPlan()
+        cand.calls += 1
+        if cand.calls >= 2 and not cand.busy:                     # first call of a configuration runs eagerly (warm-up)
+            if cand.fwd is None:
+                _capture_forward(cand, x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync)
+            cand.run.grad_sync = grad_sync
+            _fill_plan(cand, x_emb, engine._mask_u8(attn_mask), engine._mask_u8(pad_mask), seed_host)
+            plan = cand
+    if plan is not None:
+        return EncoderStackFunction.apply(x_emb, None, plan, *params)
+    run = TrainRun(layers, after_norm, attn_mask, pad_mask, B, T, dtype, seed_host.to(x_emb.device), grad_sync)
+    return EncoderStackFunction.apply(x_emb, run, None, *params)

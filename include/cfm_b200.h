@@ -270,7 +270,8 @@ int cfm_gemm_ex(const void* A, int a_mn_major, int64_t lda, int64_t a_hs, int64_
  * `dtype` is the activation dtype (CFM_F32 | CFM_BF16); statistics, the residual stream x and all parameter
  * gradients are fp32; gradient outputs named d<param> are ACCUMULATED (+=, atomics).  Dropout is counter based
  * (Philox4x32-10 keyed by (seed, site), counter = element index): forward and backward pass the same (p, seed, site)
- * and no mask is stored.  p = 0 disables it.  The reference's dropout sites: feedforward.py:19, attention.py:95,
+ * and no mask is stored.  `seed` is a DEVICE pointer to one uint64 (so that a captured CUDA graph of a training step
+ * replays with a new seed); p = 0 (or a null seed) disables dropout.  The reference's dropout sites: feedforward.py:19, attention.py:95,
  * encoder_layer.py:58,62,66,69.
  */
 /* y = rowmask(LN(x; g, b)) and the row statistics needed by the backward (encoder_layer.py:56,59,63,67,70). */
@@ -281,16 +282,16 @@ int cfm_ln_bwd(const void* dy, int dy_dtype, const float* x, const float* mean, 
                const uint8_t* row_valid, const float* dx_in, float* dx_out, float* dg, float* db, int rows, int d,
                void* stream);
 /* a = dropout(SiLU(h))  (feedforward.py:18-19) and its backward dh = da * mask * SiLU'(h), dbias += colsum(dh). */
-int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, float p, uint64_t seed, int site,
+int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, float p, const uint64_t* seed, int site,
                          void* stream);
 int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, float* dbias, int rows, int cols, int dtype, float p,
-                         uint64_t seed, int site, void* stream);
+                         const uint64_t* seed, int site, void* stream);
 /* x += alpha * rowmask * dropout(f)  (the residual adds of encoder_layer.py:58,62,66,69 with their dropout and the
  * masked_fill of convolution.py:47-48) and its backward df = alpha * rowmask * mask * dx, dbias += colsum(df). */
 int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols, int dtype, float alpha, const uint8_t* row_valid,
-                          float p, uint64_t seed, int site, void* stream);
+                          float p, const uint64_t* seed, int site, void* stream);
 int cfm_scale_dropout_bwd(const float* dx, void* df, float* dbias, int rows, int cols, int dtype, float alpha,
-                          const uint8_t* row_valid, float p, uint64_t seed, int site, void* stream);
+                          const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream);
 /* GLU over the channel halves of g (rows, 2d) (convolution.py:42) and its backward (dbias: 2d bias gradient of
  * pointwise_conv1). */
 int cfm_glu_fwd(const void* g, void* u, int rows, int d, int dtype, void* stream);
@@ -307,9 +308,9 @@ int cfm_dwconv_wgrad(const void* dy, const void* u, float* dw, float* dbias, int
 /* Masked softmax (+ dropout) over materialised scores S (B,H,Tq,Tp) fp32 -> P (and the dropped copy Pd when p > 0), mask
  * semantics of attention.py:89-92; and its backward dS = P * (dP - rowsum(dP * P)), dP = dPd * dropout multiplier. */
 int cfm_softmax_fwd(const float* S, void* P, void* Pd, const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, int B, int H,
-                    int Tq, int Tk, int Tp, int dtype, float p, uint64_t seed, int site, void* stream);
+                    int Tq, int Tk, int Tp, int dtype, float p, const uint64_t* seed, int site, void* stream);
 int cfm_softmax_bwd(const void* P, const float* dPd, void* dS, int B, int H, int Tq, int Tk, int Tp, int dtype, float p,
-                    uint64_t seed, int site, void* stream);
+                    const uint64_t* seed, int site, void* stream);
 /* out (cols) += column sums of x (rows, ld) -- bias gradients. */
 int cfm_colsum(const void* x, int64_t ld, float* out, int rows, int cols, int dtype, void* stream);
 

@@ -96,6 +96,10 @@ from conformer_pytorch_lightning_b200 import train_ops as TO
 DTYPES = [torch.float32, torch.bfloat16]
 
 
+def _seed(v):
+    return torch.tensor([v], dtype=torch.int64, device="cuda")
+
+
 def _tol(dtype):
     return 2e-5 if dtype == torch.float32 else 1.2e-2
 
@@ -139,18 +143,18 @@ def test_silu_dropout_fwd_bwd(dtype):
     assert _rel(dbias, dh.float().sum(0)) < 1e-5
     # dropout: same mask in forward and backward, right rate and scale, deterministic in (seed, site)
     p = 0.1
-    TO.silu_dropout_fwd(h, a, p=p, seed=1234, site=5)
+    TO.silu_dropout_fwd(h, a, p=p, seed=_seed(1234), site=5)
     a2 = torch.empty_like(a)
-    TO.silu_dropout_fwd(h, a2, p=p, seed=1234, site=5)
+    TO.silu_dropout_fwd(h, a2, p=p, seed=_seed(1234), site=5)
     assert torch.equal(a, a2)
-    TO.silu_dropout_fwd(h, a2, p=p, seed=1234, site=6)
+    TO.silu_dropout_fwd(h, a2, p=p, seed=_seed(1234), site=6)
     assert not torch.equal(a, a2)
     nz = ref.detach().abs() > 1e-3
     kept = (a.float() != 0) & nz
     rate = 1 - kept.sum().item() / nz.sum().item()
     assert abs(rate - p) < 0.005
     assert _rel(a.float()[kept], (ref.detach() / (1 - p))[kept]) < _tol(dtype)
-    TO.silu_dropout_bwd(da, h, dh, None, p=p, seed=1234, site=5)
+    TO.silu_dropout_bwd(da, h, dh, None, p=p, seed=_seed(1234), site=5)
     big = nz & (da.float().abs() > 1e-2) & (hr.grad.abs() > 1e-3)
     assert torch.equal((dh.float() != 0) & big, kept & big)
 
@@ -165,14 +169,14 @@ def test_residual_dropout_pair(dtype):
     TO.resid_dropout_add(x, f, alpha=0.5, row_valid=valid)
     assert _rel(x, x0 + 0.5 * f.float() * valid[:, None]) < 1e-6
     x = x0.clone()
-    TO.resid_dropout_add(x, f, alpha=0.5, row_valid=valid, p=0.25, seed=7, site=3)
+    TO.resid_dropout_add(x, f, alpha=0.5, row_valid=valid, p=0.25, seed=_seed(7), site=3)
     mult = (x - x0) / (0.5 * f.float())                       # 0 or 1/(1-p) on valid rows
     m = mult[valid]
     assert ((m.abs() < 1e-3) | ((m - 1 / 0.75).abs() < 2e-2)).all()
     assert abs((m.abs() < 1e-3).float().mean().item() - 0.25) < 0.01
     dx = _rand(rows, cols, dtype=torch.float32, seed=20)
     df, dbias = torch.empty((rows, cols), dtype=dtype, device="cuda"), torch.zeros(cols, device="cuda")
-    TO.scale_dropout_bwd(dx, df, dbias, alpha=0.5, row_valid=valid, p=0.25, seed=7, site=3)
+    TO.scale_dropout_bwd(dx, df, dbias, alpha=0.5, row_valid=valid, p=0.25, seed=_seed(7), site=3)
     ref = 0.5 * dx * torch.where(mult.abs() < 1e-3, 0.0, 1 / 0.75) * valid[:, None]
     assert _rel(df.float(), ref) < _tol(dtype)
     assert _rel(dbias, df.float().sum(0)) < 1e-5
@@ -268,7 +272,7 @@ def test_softmax_fwd_bwd(dtype, T):
     assert float(dS[1, :, 5].float().abs().max()) == 0
     # dropout on the probabilities
     Pd = torch.empty_like(P)
-    TO.softmax_fwd(S, P, Pd, mask, Tk=T, p=0.1, seed=99, site=2)
+    TO.softmax_fwd(S, P, Pd, mask, Tk=T, p=0.1, seed=_seed(99), site=2)
     nz = P.float() > 1e-3
     dropped = (Pd.float() == 0) & nz
     assert abs(dropped.sum().item() / nz.sum().item() - 0.1) < 0.01
