@@ -375,10 +375,10 @@ int gemm_gen(const void* A, int a_mn, long long lda, long long a_hs, long long a
   const int tiles = p.nB * p.nH * p.m_tiles * p.n_tiles;
   if (p.out_mode != 2) splits = 1;
   else if (splits <= 0) {
-    // enough (tile, K-slice) work items to fill the chip, at least 4 K-steps of 64 per slice
-    splits = (2 * num_sms() + tiles - 1) / tiles;
-    if (splits > p.kb_total / 4) splits = p.kb_total / 4;
-    if (splits > 32) splits = 32;
+    // ONE wave of (tile, K-slice) work items: every extra slice costs a full fp32 reduce-add of the output tile
+    // (128 KB at ~31 B/clk/SM), so slices are only added until the chip is full, and keep >= 2 K-steps of 64 each
+    splits = num_sms() / tiles;
+    if (splits > p.kb_total / 2) splits = p.kb_total / 2;
   }
   if (splits < 1) splits = 1;
   if (splits > p.kb_total) splits = p.kb_total;

@@ -70,3 +70,67 @@ def test_two_gpu_sharded_forward_equals_single_gpu_bitwise():
         ref, _ = enc(torch.from_numpy(feats).cuda(), torch.from_numpy(lens).cuda())
     assert got.shape == tuple(ref.shape)
     assert np.array_equal(got, ref.cpu().numpy())          # bitwise
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    from conformer_pytorch_lightning_b200 import ddp
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0,
+                          static_chunk_size=16)
+    enc = build_encoder(cfg, 2, device=f"cuda:{rank}", compute_dtype=torch.bfloat16).train()
+    sync = ddp.attach(enc)
+    feats, lens = _inputs()
+    grads = []
+    for step in range(3):                                    # eager, graph capture, graph replay
+        enc.zero_grad(set_to_none=True)
+        out, _ = enc(torch.from_numpy(feats[rank::world]).cuda(), torch.from_numpy(lens[rank::world]).cuda())
+        out.square().mean().backward()
+        ddp.sync_grads([p for n, p in enc.named_parameters() if n.startswith("embed.")])
+        grads.append({k: p.grad.detach().float().cpu() for k, p in enc.named_parameters() if p.grad is not None})
+    q.put((rank, grads, sync.buckets_sent))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_gradient_allreduce_equals_mean_of_shard_gradients():
+    """Training on 2 GPUs: after the per-layer NCCL all-reduce (overlapped with the backward, eager and CUDA-graph
+    steps alike) every rank holds the MEAN of the two shards' gradients, which a single process reproduces by running
+    both shards itself."""
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0,
+                          static_chunk_size=16)
+    feats, lens = _inputs()
+    ref = None
+    for r in range(world):
+        enc = build_encoder(cfg, 2, compute_dtype=torch.bfloat16).train()
+        enc.use_cuda_graphs = False
+        out, _ = enc(torch.from_numpy(feats[r::world]).cuda(), torch.from_numpy(lens[r::world]).cuda())
+        out.square().mean().backward()
+        g = {k: p.grad.detach().float().cpu() / world for k, p in enc.named_parameters() if p.grad is not None}
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+    assert res[0][2] >= 3 * 3                                # (2 layers + after_norm) buckets x 3 steps went over NCCL
+    for rank, grads, _ in res:
+        for step_grads in grads:                             # weights never change: every step has the same gradients
+            for k, v in ref.items():
+                scale = float(v.abs().max()) + 1e-12
+                tol = 2e-2 if k.startswith("embed.") else 3e-3
+                assert float((step_grads[k] - v).abs().max()) < tol * scale + 1e-6, (rank, k)
+    for k in ref:                                            # and the two ranks agree
+        assert torch.allclose(res[0][1][-1][k], res[1][1][-1][k], rtol=0, atol=0)

@@ -60,3 +60,44 @@ def test_two_rank_sharded_forward_equals_single_rank():
         assert p.exitcode == 0
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def _grad_sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conformer_pytorch_lightning_b200 import ddp
+    sync = ddp.GradSync(average=True)
+    buckets = [torch.full((5,), float(rank + 1) * (i + 1)) for i in range(3)]      # "layer" buckets, last layer first
+    for b in reversed(buckets):
+        sync.bucket_ready(b)
+    sync.finish()
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank))
+    ddp.broadcast_parameters(lin, src=0)
+    lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+    lin.bias.grad = None
+    ddp.sync_grads(lin.parameters())
+    q.put((rank, [b.tolist() for b in buckets], lin.weight.detach().clone().tolist(), lin.weight.grad.tolist(), sync.buckets_sent))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_averages_buckets_world2():
+    """ddp.GradSync / sync_grads / broadcast_parameters over gloo, world size 2: every bucket ends as the mean over ranks
+    on every rank (the all-reduce the native backward issues per layer)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    procs = [ctx.Process(target=_grad_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, buckets, w, g, sent in res:
+        for i, b in enumerate(buckets):
+            assert b == [1.5 * (i + 1)] * 5                      # mean of (1, 2) * (i + 1)
+        assert all(v == 0.0 for row in w for v in row)           # rank 0's weights everywhere
+        assert all(v == 1.5 for row in g for v in row)
+        assert sent == 3
