@@ -14,14 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfm_b200.so")
 
 F32, BF16 = 0, 1
-EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_GLU, EPI_RESIDUAL = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_SILU, EPI_BIAS_GLU, EPI_RESIDUAL, EPI_BIAS_RELU = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 
 # every symbol include/cfm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "cfm_abi_version", "cfm_last_error", "cfm_init", "cfm_launch_count", "cfm_kernel_launches", "cfm_layernorm", "cfm_gemm", "cfm_gemm_ln", "cfm_ffn",
     "cfm_attention", "cfm_relpos_keys", "cfm_dwconv", "cfm_bn_stats", "cfm_bn_apply_silu", "cfm_subsample_ws_bytes",
-    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax", "cfm_gemm_ex",
+    "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax", "cfm_gemm_ex", "cfm_l2_prefetch", "cfm_l2_prefetch_multi",
     "cfm_ln_fwd_train", "cfm_ln_bwd", "cfm_silu_dropout_fwd", "cfm_silu_dropout_bwd", "cfm_resid_dropout_add",
     "cfm_scale_dropout_bwd", "cfm_glu_fwd", "cfm_glu_bwd", "cfm_bn_silu_bwd", "cfm_dwconv_wgrad", "cfm_softmax_fwd",
     "cfm_softmax_bwd", "cfm_colsum", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
@@ -65,6 +65,8 @@ def _declare(lib):
     lib.cfm_gemm_ex.argtypes = [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _i,
                                 _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]
     _u64 = ctypes.c_uint64
+    lib.cfm_l2_prefetch.argtypes = [_p, _i64, _i, _p]
+    lib.cfm_l2_prefetch_multi.argtypes = [_p, _p, _i, _i, _p]
     lib.cfm_ln_fwd_train.argtypes = [_p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _f, _p]
     lib.cfm_ln_bwd.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]
     lib.cfm_silu_dropout_fwd.argtypes = [_p, _p, _i, _i, _i, _f, _p, _i, _p]

@@ -83,18 +83,48 @@ def _check_head_dim(encoder_dim, num_heads):
 
 class _MHSABase(nn.Module):
     def _run(self, query, key, value, inputs_attn_mask, pos_embed, cache, out_dropout):
-        if key is not query or value is not query:
-            if not (torch.equal(key, query) and torch.equal(value, query)):
-                raise NotImplementedError("native attention implements self-attention (query is key is value), "
-                                          "the only way the reference encoder calls it (encoder_layer.py:60)")
         engine.check_inference_only(self, self.dropout.p, query)
         dtype = engine.resolve_dtype(self)
         B, T, d = query.shape
+        self_attn = (key is query and value is query) or (key.shape == query.shape and value.shape == query.shape and
+                                                          torch.equal(key, query) and torch.equal(value, query))
+        if not self_attn:
+            return self._cross(query, key, value, inputs_attn_mask, cache, dtype)
         y = query.reshape(B * T, d).to(dtype).contiguous()
         x = torch.zeros((B * T, d), dtype=torch.float32, device=y.device)
         new_cache = engine.mhsa_into(x, y, B, T, self.num_heads, self.derived_weights(dtype), inputs_attn_mask,
                                      pos_embed, cache, True, engine.thread_workspace())
         return x.view(B, T, d).to(query.dtype), new_cache.to(query.dtype)
+
+    def _cross(self, query, key, value, mask, cache, dtype):
+        """query, key and value are different tensors (attention.py:62-64 projects each with its own Linear; the
+        reference's encoder never does this, its decoder_layer.py does): three projection GEMMs, then the attention
+        kernel with Tq != Tk and the output projection.  For the relative variant the position term needs one position
+        row per batch element (constant along keys, softmax-invariant) -- anything else raises."""
+        import math as _m
+        B, Tq, d = query.shape
+        Tk = key.shape[1]
+        if key.shape[0] != B or value.shape != key.shape or key.shape[2] != d:
+            raise RuntimeError("attention: key / value must be (B, Tk, d) with the batch and model size of query")
+        if cache is not None and cache.dim() == 4 and cache.size(0) > 0:
+            raise NotImplementedError("cross-attention with a streaming cache is not implemented")
+        W = self.derived_weights(dtype)
+        H = self.num_heads
+        dev = query.device
+        ws = engine.thread_workspace()
+        q = ws.get("xq", (B * Tq, d), dtype, dev)
+        k = ws.get("xk", (B * Tk, d), dtype, dev)
+        v = ws.get("xv", (B * Tk, d), dtype, dev)
+        engine.ops.gemm(query.reshape(B * Tq, d).to(dtype).contiguous(), W["wqkv"][:d], W["bqkv"][:d].contiguous(), q, engine.N.EPI_BIAS)
+        engine.ops.gemm(key.reshape(B * Tk, d).to(dtype).contiguous(), W["wqkv"][d:2 * d], W["bqkv"][d:2 * d].contiguous(), k, engine.N.EPI_BIAS)
+        engine.ops.gemm(value.reshape(B * Tk, d).to(dtype).contiguous(), W["wqkv"][2 * d:], W["bqkv"][2 * d:].contiguous(), v, engine.N.EPI_BIAS)
+        ctx = ws.get("attn_ctx", (B * Tq, d), dtype, dev)
+        engine.ops.attention(q.view(B, Tq, H, 64), k.view(B, Tk, H, 64), v.view(B, Tk, H, 64), ctx.view(B, Tq, d),
+                             mask=engine._mask_u8(mask), scale=1.0 / _m.sqrt(64.0))
+        x = torch.zeros((B * Tq, d), dtype=torch.float32, device=dev)
+        engine.ops.gemm(ctx, W["wo"], W["bo"], x, engine.N.EPI_RESIDUAL, residual=x, alpha=1.0)
+        new_cache = torch.cat([k.view(B, Tk, H, 64).permute(0, 2, 1, 3), v.view(B, Tk, H, 64).permute(0, 2, 1, 3)], dim=-1).float()
+        return x.view(B, Tq, d).to(query.dtype), new_cache.to(query.dtype)
 
     def derived_weights(self, dtype):
         return self._derived.get(self, dtype, lambda dt: engine.mhsa_weights(self, dt))

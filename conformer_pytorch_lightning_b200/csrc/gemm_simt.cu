@@ -87,6 +87,8 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, cons
         ((T*)Cv)[off] = from_f32<T>(v);
       } else if constexpr (EPI == CFM_EPI_BIAS_SILU) {
         ((T*)Cv)[off] = from_f32<T>(act_silu<T>(v));
+      } else if constexpr (EPI == CFM_EPI_BIAS_RELU) {
+        ((T*)Cv)[off] = from_f32<T>(fmaxf(v, 0.f));
       } else if constexpr (EPI == CFM_EPI_BIAS_GLU) {
         const float g = acc2[i][j] + (bias ? bias[N + n] : 0.f);
         ((T*)Cv)[off] = from_f32<T>(v * act_sigmoid<T>(g));
@@ -177,6 +179,8 @@ gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, co
     ((T*)Cv)[off] = from_f32<T>(v);
   } else if constexpr (EPI == CFM_EPI_BIAS_SILU) {
     ((T*)Cv)[off] = from_f32<T>(act_silu<T>(v));
+  } else if constexpr (EPI == CFM_EPI_BIAS_RELU) {
+    ((T*)Cv)[off] = from_f32<T>(fmaxf(v, 0.f));
   } else if constexpr (EPI == CFM_EPI_BIAS_GLU) {
     g += bias ? bias[N + n] : 0.f;
     ((T*)Cv)[off] = from_f32<T>(v * act_sigmoid<T>(g));
@@ -207,6 +211,7 @@ int launch(const void* A, int lda, const void* W, const float* bias, void* C, in
     switch (epi) {
       case CFM_EPI_BIAS: launch_skinny<T, CFM_EPI_BIAS>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
       case CFM_EPI_BIAS_SILU: launch_skinny<T, CFM_EPI_BIAS_SILU>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
+      case CFM_EPI_BIAS_RELU: launch_skinny<T, CFM_EPI_BIAS_RELU>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
       case CFM_EPI_BIAS_GLU: launch_skinny<T, CFM_EPI_BIAS_GLU>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
       default: launch_skinny<T, CFM_EPI_RESIDUAL>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv, st); break;
     }
@@ -219,6 +224,9 @@ int launch(const void* A, int lda, const void* W, const float* bias, void* C, in
       break;
     case CFM_EPI_BIAS_SILU:
       gemm_simt_kernel<T, CFM_EPI_BIAS_SILU><<<grid, 256, 0, st>>>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv);
+      break;
+    case CFM_EPI_BIAS_RELU:
+      gemm_simt_kernel<T, CFM_EPI_BIAS_RELU><<<grid, 256, 0, st>>>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv);
       break;
     case CFM_EPI_BIAS_GLU:
       gemm_simt_kernel<T, CFM_EPI_BIAS_GLU><<<grid, 256, 0, st>>>(a, lda, w, bias, C, ldc, M, N, K, residual, alpha, rv);

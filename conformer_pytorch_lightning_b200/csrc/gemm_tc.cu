@@ -316,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int e = 0; e < 8; ++e) {
               float x = __uint_as_float(v[8 * j + e]) + bs[8 * j + e];
               if constexpr (EPI == CFM_EPI_BIAS_SILU) x = silu_fast(x);
+              if constexpr (EPI == CFM_EPI_BIAS_RELU) x = fmaxf(x, 0.f);
               if constexpr (GLU) x *= sigmoid_fast(__uint_as_float(g[8 * j + e]) + bs[OUT_BN + 8 * j + e]);
               f[e] = x;
             }
@@ -437,11 +438,13 @@ int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* 
     switch (epilogue) {
       case CFM_EPI_BIAS: return launch_tc<256, CFM_EPI_BIAS>(tmA, tmW, tmC, tmR, tmY, p, st);
       case CFM_EPI_BIAS_SILU: return launch_tc<256, CFM_EPI_BIAS_SILU>(tmA, tmW, tmC, tmR, tmY, p, st);
+      case CFM_EPI_BIAS_RELU: return launch_tc<256, CFM_EPI_BIAS_RELU>(tmA, tmW, tmC, tmR, tmY, p, st);
       default: return launch_tc<256, CFM_EPI_BIAS_GLU>(tmA, tmW, tmC, tmR, tmY, p, st);
     }
   }
   switch (epilogue) {
     case CFM_EPI_BIAS: return launch_tc<128, CFM_EPI_BIAS>(tmA, tmW, tmC, tmR, tmY, p, st);
+    case CFM_EPI_BIAS_RELU: return launch_tc<128, CFM_EPI_BIAS_RELU>(tmA, tmW, tmC, tmR, tmY, p, st);
     default: return launch_tc<128, CFM_EPI_BIAS_SILU>(tmA, tmW, tmC, tmR, tmY, p, st);
   }
 }

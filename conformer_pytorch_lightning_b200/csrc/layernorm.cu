@@ -115,3 +115,56 @@ extern "C" int cfm_layernorm(const float* x, int rows, int d, const float* g1, c
     default: return launch_ln<8>(x, rows, g1, b1, x_out, g2, b2, y, y_dtype, row_valid, eps, st);
   }
 }
+
+// ------------------------------------------------------------------ L2 prefetch of the next layer's weights
+// Every kernel of the stack is a single wave that leaves 8..24 SMs idle (124-140 CTAs on 148 SMs) and starts by pulling
+// its weights from HBM (they are cold: ~5.6 MB per layer, first touch of the step).  A few CTAs of this kernel run on the
+// idle SMs of the PREVIOUS layer's kernels (side stream, a parallel branch of the CUDA graph) and pull the next layer's
+// weights into L2, so the weight rings of the fused kernels see L2 latency instead of HBM latency.
+namespace cfm {
+namespace {
+__global__ void __launch_bounds__(256)
+l2_prefetch_kernel(const uint8_t* __restrict__ p, size_t bytes) {
+  const size_t lines = (bytes + 127) / 128;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p + i * 128));
+}
+}  // namespace
+}  // namespace cfm
+
+namespace cfm {
+namespace {
+struct PrefetchList { const uint8_t* p[8]; unsigned long long bytes[8]; int n; };
+__global__ void __launch_bounds__(256)
+l2_prefetch_multi_kernel(const PrefetchList pl) {
+  for (int t = 0; t < pl.n; ++t) {
+    const size_t lines = (pl.bytes[t] + 127) / 128;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+      asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pl.p[t] + i * 128));
+  }
+}
+}  // namespace
+}  // namespace cfm
+
+extern "C" int cfm_l2_prefetch_multi(const void* const* ptrs, const int64_t* bytes, int n, int blocks, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(ptrs != nullptr && bytes != nullptr && n >= 0 && n <= 8, "cfm_l2_prefetch_multi: up to 8 regions");
+  if (n == 0) return 0;
+  PrefetchList pl{};
+  pl.n = n;
+  for (int i = 0; i < n; ++i) { pl.p[i] = (const uint8_t*)ptrs[i]; pl.bytes[i] = (unsigned long long)bytes[i]; }
+  if (blocks <= 0) blocks = 16;
+  l2_prefetch_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pl);
+  CFM_LAUNCHED_K("l2_prefetch");
+  return 0;
+}
+
+extern "C" int cfm_l2_prefetch(const void* p, int64_t bytes, int blocks, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(p != nullptr && bytes >= 0, "cfm_l2_prefetch: bad arguments");
+  if (bytes == 0) return 0;
+  if (blocks <= 0) blocks = 16;
+  l2_prefetch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)p, (size_t)bytes);
+  CFM_LAUNCHED_K("l2_prefetch");
+  return 0;
+}

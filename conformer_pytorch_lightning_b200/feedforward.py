@@ -13,9 +13,9 @@ class PositionwiseFeedForwardModule(nn.Module):
     def __init__(self, input_dim, dropout, hidden_dim, activation='swish'):
         super().__init__()
         self.w_1 = nn.Linear(input_dim, hidden_dim)
-        if activation != 'swish':
-            raise NotImplementedError("only the 'swish' activation (the one the reference encoder uses) has a native epilogue")
-        self.activation = nn.SiLU()
+        # feedforward.py:10-14: 'relu' -> nn.ReLU, anything else -> nn.SiLU.  The encoder layer always takes the default;
+        # ReLU is served by the GEMM + ReLU epilogue chain (the fused FFN kernel is SiLU only)
+        self.activation = nn.ReLU() if activation == 'relu' else nn.SiLU()
         self.dropout = nn.Dropout(dropout)
         self.w_2 = nn.Linear(hidden_dim, input_dim)
         self._derived = engine.Derived()
@@ -29,5 +29,11 @@ class PositionwiseFeedForwardModule(nn.Module):
         shape = inputs.shape
         y = inputs.reshape(-1, shape[-1]).to(dtype).contiguous()
         x = torch.zeros((y.shape[0], shape[-1]), dtype=torch.float32, device=y.device)
-        engine.ffn_into(x, y, self.derived_weights(dtype), 1.0, engine.thread_workspace())
+        W = self.derived_weights(dtype)
+        if isinstance(self.activation, nn.ReLU):
+            h = engine.thread_workspace().get("ffn_h", (y.shape[0], W["w1"].shape[0]), y.dtype, y.device)
+            ops.gemm(y, W["w1"], W["b1"], h, N.EPI_BIAS_RELU)
+            ops.gemm(h, W["w2"], W["b2"], x, N.EPI_RESIDUAL, residual=x, alpha=1.0)
+        else:
+            engine.ffn_into(x, y, W, 1.0, engine.thread_workspace())
         return x.view(shape).to(inputs.dtype)

@@ -353,3 +353,12 @@ def gemm_ex(a, b, c, *, alpha=1.0, accumulate=False, splits=0, engine=N.ENGINE_A
                                 1 if accumulate else 0, M, Nn, K, nH, nB, _DT[a.dtype], float(alpha), int(splits), engine,
                                 _stream(a)))
     return c
+
+
+def l2_prefetch(tensors, stream, blocks=16):
+    """Warm up to 8 CUDA tensors into L2 from ``stream`` in one launch (see cfm_l2_prefetch_multi)."""
+    import ctypes
+    ts = list(tensors)[:8]
+    ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    sizes = (ctypes.c_int64 * len(ts))(*[t.numel() * t.element_size() for t in ts])
+    N.check(N.lib().cfm_l2_prefetch_multi(ptrs, sizes, len(ts), blocks, stream.cuda_stream))

@@ -42,6 +42,8 @@ extern "C" {
                                                                            residual adds of encoder_layer.py:58,62,66,69
                                                                            and the masked_fill of convolution.py:47-48 */
 
+#define CFM_EPI_BIAS_RELU 4  /* C[act]  = relu(A W^T + b)                  w_1 + ReLU (feedforward.py:10-11, activation='relu') */
+
 /* GEMM engines */
 #define CFM_ENGINE_AUTO 0    /* tcgen05 when dtype==BF16 and the shape is supported, else SIMT */
 #define CFM_ENGINE_SIMT 1    /* fp32-accumulating CUDA-core kernel (exact-order reference engine) */
@@ -245,6 +247,12 @@ int cfm_bn_apply_silu(const float* x, int rows, int d, const float* mean, const 
 int64_t cfm_subsample_ws_bytes(int B, int Tin, int idim, int C);
 int cfm_subsample_conv(const float* x, int B, int Tin, int idim, const float* w1, const float* b1,
                        const void* w2, const float* b2, int C, void* ws, void* out, void* stream);
+
+/* Pull `bytes` at p into L2 (prefetch.global.L2, no registers / shared memory: the CTAs run on SMs the concurrently
+ * running single-wave kernels leave idle).  Used to warm the NEXT layer's weights from a side stream. */
+int cfm_l2_prefetch(const void* p, int64_t bytes, int blocks, void* stream);
+/* the same for up to 8 regions in one launch (host arrays of n pointers / sizes) */
+int cfm_l2_prefetch_multi(const void* const* ptrs, const int64_t* bytes, int n, int blocks, void* stream);
 
 /*
  * General GEMM of the training path (backward of every nn.Linear / 1x1 Conv1d on the path, and the batched products of

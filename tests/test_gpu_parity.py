@@ -308,3 +308,37 @@ def test_graph_plans_are_lru_bounded():
         out2, _ = enc.forward_chunk_by_chunk(torch.randn(1, 67 + 64 * 5, 80, generator=g).cuda(), 16, 1)
         assert len(enc._plans) <= 4
     assert torch.isfinite(out).all() and torch.isfinite(out2).all()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_feedforward_relu_and_cross_attention_surface(dtype, tol):
+    """The two corners of the reference's module surface outside the encoder's own use: activation='relu'
+    (feedforward.py:10-11) and attention with key / value different from query (attention.py:62-64), vs the same
+    arithmetic in PyTorch fp32."""
+    import conformer_pytorch_lightning_b200 as C
+    torch.manual_seed(3)
+    ffn = C.PositionwiseFeedForwardModule(256, 0.0, 1024, activation='relu').cuda().eval()
+    ffn.compute_dtype = dtype
+    x = torch.randn(3, 70, 256, device="cuda")
+    with torch.no_grad():
+        got = ffn(x)
+        ref = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(x, ffn.w_1.weight, ffn.w_1.bias)),
+                                         ffn.w_2.weight, ffn.w_2.bias)
+    assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < tol
+    att = C.MultiHeadSelfAttentionModule(256, 4, 0.0).cuda().eval()
+    att.compute_dtype = dtype
+    q, kv = torch.randn(2, 70, 256, device="cuda"), torch.randn(2, 90, 256, device="cuda")
+    mask = torch.ones(2, 1, 90, dtype=torch.bool, device="cuda")
+    mask[1, :, 77:] = False
+    with torch.no_grad():
+        got, cache = att(q, kv, kv, mask)
+        lin = torch.nn.functional.linear
+        qq = lin(q, att.linear_q.weight, att.linear_q.bias).view(2, 70, 4, 64).transpose(1, 2)
+        kk = lin(kv, att.linear_k.weight, att.linear_k.bias).view(2, 90, 4, 64).transpose(1, 2)
+        vv = lin(kv, att.linear_v.weight, att.linear_v.bias).view(2, 90, 4, 64).transpose(1, 2)
+        s = (qq @ kk.transpose(-1, -2)) / 8.0
+        m = ~mask[:, None]
+        p = torch.softmax(s.masked_fill(m, float("-inf")), -1).masked_fill(m, 0.0)
+        ref = lin((p @ vv).transpose(1, 2).reshape(2, 70, 256), att.linear_out.weight, att.linear_out.bias)
+    assert tuple(cache.shape) == (2, 4, 90, 128)
+    assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < tol

@@ -41,5 +41,22 @@ elif which == "dwconv":
     w = torch.randn(15, d, device=dev); b = torch.randn(d, device=dev)
     for _ in range(3):
         ops.dwconv(x, w, b, y)
+elif which == "frontend":
+    # sub-sampling front-end (subsample_fused_kernel + the Linear GEMM) on the C2 batch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from _util import build_encoder
+    from oracle import conformer_oracle as O
+    enc = build_encoder(O.conformer_cfg("M", encoder_num_layers=1), 0, compute_dtype=torch.bfloat16)
+    feats = torch.randn(64, 998, 80, device=dev)
+    pad = torch.ones(64, 1, 998, dtype=torch.bool, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            enc.embed(feats, pad)
+elif which == "ctc":
+    # CTC greedy head: ctc_lo GEMM with the argmax epilogue (gemm_tc_kernel<256, 100>), V = 5002
+    x = torch.randn(M, d, device=dev).bfloat16()
+    w = (torch.randn(5002, d, device=dev) / 16).bfloat16(); b = torch.randn(5002, device=dev)
+    for _ in range(3):
+        ops.ctc_argmax(x, w, b)
 torch.cuda.synchronize()
 print("done")
