@@ -10,10 +10,11 @@ from .encoder_layer import ConformerEncoderLayer
 from .feedforward import PositionwiseFeedForwardModule
 from .pipeline import EncoderPipeline
 from .ctc import CTCDecoder, CTCGreedyHead
+from .frontend import Fbank, GlobalCMVN, load_cmvn
 from . import ddp
 from .utils import make_attn_mask, make_pad_mask, subsequent_chunk_mask
 
 __all__ = ["ConformerEncoder", "ConformerEncoderLayer", "RelativeMultiHeadSelfAttentionModule",
            "MultiHeadSelfAttentionModule", "RelativePositionalEncoding", "PositionalEncoding", "ConvolutionModule",
            "ConvolutionSubSampling", "PositionwiseFeedForwardModule", "make_pad_mask", "make_attn_mask",
-           "subsequent_chunk_mask", "EncoderPipeline", "CTCGreedyHead", "CTCDecoder", "ddp"]
+           "subsequent_chunk_mask", "EncoderPipeline", "CTCGreedyHead", "CTCDecoder", "ddp", "Fbank", "GlobalCMVN", "load_cmvn"]

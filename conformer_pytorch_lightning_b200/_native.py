@@ -25,6 +25,7 @@ EXPORTS = [
     "cfm_ln_fwd_train", "cfm_ln_bwd", "cfm_silu_dropout_fwd", "cfm_silu_dropout_bwd", "cfm_resid_dropout_add",
     "cfm_scale_dropout_bwd", "cfm_glu_fwd", "cfm_glu_bwd", "cfm_bn_silu_bwd", "cfm_dwconv_wgrad", "cfm_softmax_fwd",
     "cfm_softmax_bwd", "cfm_colsum", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
+    "cfm_fbank_frames", "cfm_fbank_power", "cfm_fbank_log_cmvn", "cfm_cmvn",
 ]
 
 _lib = None
@@ -65,6 +66,10 @@ def _declare(lib):
     lib.cfm_gemm_ex.argtypes = [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _i,
                                 _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]
     _u64 = ctypes.c_uint64
+    lib.cfm_fbank_frames.argtypes = [_p, _i64, _p, _p, _p, _i, _i, _f, _p]
+    lib.cfm_fbank_power.argtypes = [_p, _i, _p, _i, _i64, _i, _p]
+    lib.cfm_fbank_log_cmvn.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _p]
+    lib.cfm_cmvn.argtypes = [_p, _p, _p, _p, _i64, _i, _p]
     lib.cfm_l2_prefetch.argtypes = [_p, _i64, _i, _p]
     lib.cfm_l2_prefetch_multi.argtypes = [_p, _p, _i, _i, _p]
     lib.cfm_ln_fwd_train.argtypes = [_p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _f, _p]

@@ -332,6 +332,25 @@ int cfm_ctc_loss_bwd(const void* logits, int64_t ld, int B, int T, int V, int Vp
                      const int* in_len, const int* lab_len, const float* nll, const void* ws, float scale, void* dlogits,
                      int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Feature front-end (scope row f1): Kaldi-compatible log-mel filterbank + global CMVN, replacing
+ * torchaudio.compliance.kaldi.fbank as called at processor.py:185-191 and GlobalCMVN.forward (cmvn.py:22-33).  fp32.
+ * Pipeline: cfm_fbank_frames -> cfm_gemm_ex (DFT as a GEMM with a (514, 400) [cos | -sin] basis) -> cfm_fbank_power ->
+ * cfm_gemm_ex (mel filterbank) -> cfm_fbank_log_cmvn.
+ */
+/* wave (B, wave_bs) already in int16 range; n_samples (B); window (400) = povey; frames (B*m_max, 400): framing (25 ms /
+ * 10 ms, snip_edges), DC removal, pre-emphasis, window; frames past an utterance's last frame are zero. */
+int cfm_fbank_frames(const float* wave, int64_t wave_bs, const int* n_samples, const float* window, float* frames, int B,
+                     int m_max, float preemph, void* stream);
+/* spec (rows, ld_spec) = [re(bins) | im(bins)] -> power (rows, ld_pow), columns >= bins zeroed. */
+int cfm_fbank_power(const float* spec, int ld_spec, float* power, int ld_pow, int64_t rows, int bins, void* stream);
+/* out = (log(max(mel, eps)) - mean) * istd for valid frames, (0 - mean) * istd for padding frames (mean / istd may be
+ * null: plain log-mel with zero padding). */
+int cfm_fbank_log_cmvn(const float* mel, float* out, const int* n_samples, const float* mean, const float* istd, int B,
+                       int m_max, int nmel, void* stream);
+/* y = (x - mean[c]) * istd[c] over n elements with innermost size d (istd may be null: norm_var = False). */
+int cfm_cmvn(const float* x, float* y, const float* mean, const float* istd, int64_t n, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

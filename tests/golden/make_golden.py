@@ -233,9 +233,30 @@ def case_train_grad():
          loss=np.float64(loss.item()), out=out.detach().numpy(), out_lens=out_lens.numpy(), **arrays, **after)
 
 
+def case_fbank():
+    """The reference's feature call (processor.py:185-191) on its own samples/0.wav and 1.wav, dither 0."""
+    import scipy.io.wavfile as wavfile
+    import torchaudio.compliance.kaldi as kaldi
+    arrays = {}
+    for i in range(2):
+        sr, wav = wavfile.read(f"/root/reference/samples/{i}.wav")
+        assert sr == 16000 and wav.dtype == np.int16
+        w = torch.from_numpy(wav.astype(np.float32))[None]         # == torchaudio waveform * (1 << 15)
+        feat = kaldi.fbank(w, num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0, energy_floor=0.0,
+                           sample_frequency=16000)
+        arrays[f"wav{i}"] = wav
+        arrays[f"fbank{i}"] = feat.numpy()
+    path = os.path.join(HERE, "fbank_wav01.npz")
+    np.savez_compressed(path, **arrays)
+    print("fbank_wav01:", os.path.getsize(path) // 1000, "kB", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "train_grad":
+    if len(sys.argv) > 1 and sys.argv[1] == "fbank":
+        case_fbank()
+    elif len(sys.argv) > 1 and sys.argv[1] == "train_grad":
         case_train_grad()
     else:
         main()
         case_train_grad()
+        case_fbank()

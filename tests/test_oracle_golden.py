@@ -1,5 +1,7 @@
 """Pin the numpy oracle against outputs of the real reference (tests/golden/*.npz,
 made by tests/golden/make_golden.py in the build container).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -205,3 +207,17 @@ def test_torch_cpu_port_training_gradients_match_reference():
     assert n >= 70
     for i, s in enumerate(st):
         assert max_rel(s["running_mean"].numpy(), g[f"encoders__{i}__conv_module__norm__running_mean"]) < 1e-5
+
+
+def test_fbank_oracle_matches_reference_feature_call():
+    """oracle/fbank_oracle.py vs torchaudio.compliance.kaldi.fbank as the reference calls it (processor.py:185-191) on the
+    reference's samples/0.wav and 1.wav (tests/golden/fbank_wav01.npz); load_cmvn / cmvn vs their definitions."""
+    from oracle import fbank_oracle as FB
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fbank_wav01.npz"))
+    for i in range(2):
+        got = FB.fbank(z[f"wav{i}"].astype(np.float32))
+        assert got.shape == z[f"fbank{i}"].shape
+        assert max_rel(got, z[f"fbank{i}"]) < 1e-4
+    mean, istd = FB.load_cmvn_stats({"mean_stat": [10.0, 20.0], "var_stat": [60.0, 250.0], "frame_num": 2})
+    assert np.allclose(mean, [5.0, 10.0]) and np.allclose(istd, [1 / np.sqrt(5.0), 1 / np.sqrt(25.0)])
+    assert np.allclose(FB.cmvn(np.asarray([[6.0, 15.0]]), mean, istd), [[1 / np.sqrt(5.0), 1.0]])
