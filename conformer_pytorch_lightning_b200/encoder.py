@@ -40,6 +40,9 @@ class ConformerEncoder(nn.Module):
         self.use_dynamic_left_chunk = use_dynamic_left_chunk
         self.static_chunk_size = static_chunk_size
         self.compute_dtype = None
+        # dtype of the returned encoder states: None = the dtype of the sub-sampled features (fp32, like the reference's
+        # fp32 module); torch.bfloat16 halves the device->host traffic of a bf16 serving pipeline
+        self.output_dtype = None
         # CUDA-graph plans of the measured path, one per (batch, frames, dtype, mask layout); see _graph_layers
         self.use_cuda_graphs = os.environ.get("CFM_B200_CUDA_GRAPHS", "1") != "0"
         # least-recently-used plans are evicted beyond this many (a plan owns a graph + its static buffers; length-
@@ -122,7 +125,8 @@ class ConformerEncoder(nn.Module):
         self._fill(plan, outputs, attn_mask, pad_u8)
         plan["graph"].replay()
         engine.GRAPH_REPLAYED_LAUNCHES[0] += plan["launches"]     # native kernels inside the replayed graph
-        return plan["out"].clone()
+        # the plan's output buffer is overwritten by the next replay: hand out a copy (already in the output dtype)
+        return plan["out"].to(self.output_dtype, copy=True) if self.output_dtype is not None else plan["out"].clone()
 
     def _lookup_plan(self, key):
         """LRU lookup; a new key is registered (first call of a shape runs eagerly, the second captures)."""
@@ -199,7 +203,7 @@ class ConformerEncoder(nn.Module):
                                           self.use_dynamic_left_chunk, decoding_chunk_size, self.static_chunk_size,
                                           num_decoding_chunk_size)
         out = self.encode_layers(outputs, inputs_attn_mask, pos_embed, inputs_pad_mask)
-        return out.to(outputs.dtype), inputs_pad_mask
+        return out.to(self.output_dtype or outputs.dtype), inputs_pad_mask
 
     def forward_chunk(self, inputs, offset, required_cache_size, attn_cache, cnn_cache,
                       inputs_attn_mask=torch.ones((0, 0, 0))):

@@ -342,3 +342,16 @@ def test_feedforward_relu_and_cross_attention_surface(dtype, tol):
         ref = lin((p @ vv).transpose(1, 2).reshape(2, 70, 256), att.linear_out.weight, att.linear_out.bias)
     assert tuple(cache.shape) == (2, 4, 90, 128)
     assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) < tol
+
+
+def test_output_dtype_knob():
+    """encoder.output_dtype = bf16: the returned states are the fp32 states rounded to bf16 (eager and graph replay)."""
+    g = load_golden("m3_static16")
+    enc = build_encoder(g["cfg"], g["weight_seed"], compute_dtype=torch.bfloat16)
+    feats, lens = torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["lens"]).cuda()
+    with torch.no_grad():
+        ref = [enc(feats, lens)[0] for _ in range(3)]
+        enc.output_dtype = torch.bfloat16
+        got = [enc(feats, lens)[0] for _ in range(3)]
+    assert got[0].dtype == torch.bfloat16 and ref[0].dtype == torch.float32
+    assert all(torch.equal(o, ref[0].to(torch.bfloat16)) for o in got)
