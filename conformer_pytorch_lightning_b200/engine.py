@@ -330,7 +330,8 @@ def _row_valid(pad_mask, B, T):
     return m.view(B * T)
 
 
-def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_caches, want_cache, dtype, inplace=False):
+def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_caches, want_cache, dtype, inplace=False,
+               ws=None, out_buf=None):
     """Layer loop of encoder.py:72-74 / 109-118.
 
     inputs (B,T,d) fp32 (not modified unless ``inplace``: the CUDA-graph plans run on their own static input buffer, which
@@ -340,7 +341,7 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
     B, T, d = inputs.shape
     n = B * T
     dev = inputs.device
-    ws = thread_workspace()
+    ws = ws if ws is not None else thread_workspace()      # (a private workspace per concurrent sub-batch, see encoder)
     if inplace and inputs.dtype == torch.float32 and inputs.is_contiguous():
         x = inputs.view(n, d)
     else:
@@ -400,7 +401,7 @@ def run_layers(inputs, layers, after_norm, attn_mask, pos_embed, pad_mask, attn_
         else:
             ffn_into(x, y2, Wl["ff"], 0.5, ws)
             if after_norm is not None:
-                out = torch.empty((n, d), dtype=torch.float32, device=dev)
+                out = out_buf.view(n, d) if out_buf is not None else torch.empty((n, d), dtype=torch.float32, device=dev)
                 ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], g2=_f32(after_norm.weight), b2=_f32(after_norm.bias), y=out)
             else:
                 ops.layernorm(x, Wl["fin_g"], Wl["fin_b"], x_out=x)
