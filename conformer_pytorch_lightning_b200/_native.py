@@ -26,6 +26,7 @@ EXPORTS = [
     "cfm_scale_dropout_bwd", "cfm_glu_fwd", "cfm_glu_bwd", "cfm_bn_silu_bwd", "cfm_dwconv_wgrad", "cfm_softmax_fwd",
     "cfm_softmax_bwd", "cfm_colsum", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
     "cfm_fbank_frames", "cfm_fbank_power", "cfm_fbank_log_cmvn", "cfm_cmvn",
+    "cfm_joint_add_tanh", "cfm_joint_tanh_bwd", "cfm_rnnt_loss_ws_bytes", "cfm_rnnt_loss_fwd", "cfm_rnnt_loss_bwd",
 ]
 
 _lib = None
@@ -66,6 +67,12 @@ def _declare(lib):
     lib.cfm_gemm_ex.argtypes = [_p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _p, _i, _i64, _i64, _i64, _i,
                                 _i, _i, _i, _i, _i, _i, _f, _i, _i, _p]
     _u64 = ctypes.c_uint64
+    lib.cfm_joint_add_tanh.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _p]
+    lib.cfm_joint_tanh_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]
+    lib.cfm_rnnt_loss_ws_bytes.argtypes = [_i, _i, _i]
+    lib.cfm_rnnt_loss_ws_bytes.restype = _i64
+    lib.cfm_rnnt_loss_fwd.argtypes = [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]
+    lib.cfm_rnnt_loss_bwd.argtypes = [_p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p]
     lib.cfm_fbank_frames.argtypes = [_p, _i64, _p, _p, _p, _i, _i, _f, _p]
     lib.cfm_fbank_power.argtypes = [_p, _i, _p, _i, _i64, _i, _p]
     lib.cfm_fbank_log_cmvn.argtypes = [_p, _p, _p, _p, _p, _i, _i, _i, _p]
@@ -92,7 +99,7 @@ def _declare(lib):
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("cfm_last_error", "cfm_launch_count", "cfm_kernel_launches", "cfm_abi_version", "cfm_subsample_ws_bytes", "cfm_ctc_ws_bytes",
-                        "cfm_ctc_loss_ws_bytes"):
+                        "cfm_ctc_loss_ws_bytes", "cfm_rnnt_loss_ws_bytes"):
             fn.restype = _i
 
 

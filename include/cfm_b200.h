@@ -351,6 +351,24 @@ int cfm_fbank_log_cmvn(const float* mel, float* out, const int* n_samples, const
 /* y = (x - mean[c]) * istd[c] over n elements with innermost size d (istd may be null: norm_var = False). */
 int cfm_cmvn(const float* x, float* y, const float* mean, const float* istd, int64_t n, int d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * RNN-T joint + loss (scope row f4): joint.py:20-38 and torchaudio.functional.rnnt_loss as called at model.py:95-113.
+ * The three Linear layers of the joint run on cfm_gemm / cfm_gemm_ex; these are the pieces in between.
+ */
+/* z[b,t,u,:] = tanh(e[b,t,:] + p[b,u,:]);  e (B*T, J), p (B*U1, J), z (B*T*U1, J). */
+int cfm_joint_add_tanh(const void* e, const void* p, void* z, int B, int T, int U1, int J, int dtype, void* stream);
+/* dz <- dz * (1 - z^2) in place, de (B*T, J) = sum over u, dp (B*U1, J) = sum over t. */
+int cfm_joint_tanh_bwd(void* dz, const void* z, void* de, void* dp, int B, int T, int U1, int J, int dtype, void* stream);
+/* Transducer loss on logits (B*T*U1, ld), V valid columns, fused log-softmax: fwd -> nll[b]; bwd -> dlogits (may alias
+ * logits) = scale * d nll_b / d logits, zeros outside each utterance's (t_len, u_len) lattice and in columns [V, Vp).
+ * targets (B, Umax) int32, U1 = Umax + 1.  ws (cfm_rnnt_loss_ws_bytes) carries lse / alpha / beta from fwd to bwd. */
+int64_t cfm_rnnt_loss_ws_bytes(int B, int T, int U1);
+int cfm_rnnt_loss_fwd(const void* logits, int64_t ld, int B, int T, int U1, int V, int blank, const int* targets, int Umax,
+                      const int* t_len, const int* u_len, float* nll, void* ws, int dtype, void* stream);
+int cfm_rnnt_loss_bwd(const void* logits, int64_t ld, int B, int T, int U1, int V, int Vp, int blank, const int* targets,
+                      int Umax, const int* t_len, const int* u_len, const float* nll, const void* ws, float scale,
+                      void* dlogits, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
