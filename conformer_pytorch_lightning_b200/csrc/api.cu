@@ -257,14 +257,15 @@ extern "C" int cfm_attention(const void* q, int64_t q_bs, int64_t q_ts, const vo
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_ok = key_bias == nullptr && scale > 0.f &&
                      attention_tc_supported(q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, B, H, Tq, Tk, dtype);
-  if (engine == CFM_ENGINE_TC) {
-    CFM_CHECK_ARG(tc_ok, "cfm_attention: tcgen05 engine does not support this shape/dtype");
+  if (engine == CFM_ENGINE_TC) CFM_CHECK_ARG(tc_ok, "cfm_attention: tcgen05 engine does not support this shape/dtype");
+  if (tc_ok && engine != CFM_ENGINE_SIMT) {
+    // more than one 128-row query tile per (batch, head): the two-tile ping-pong kernel (CFM_B200_ATTN_PP=0 disables)
+    static const bool pp_off = env_is("CFM_B200_ATTN_PP", "0");
+    if (Tq > 128 && !pp_off)
+      return attention_pp(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs, scale, st);
     return attention_tc(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
                         key_bias, scale, dtype, st);
   }
-  if (engine == CFM_ENGINE_AUTO && tc_ok)
-    return attention_tc(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
-                        key_bias, scale, dtype, st);
   return attention_simt(q, q_bs, q_ts, k, k_bs, k_ts, v, v_bs, v_ts, out, B, H, Tq, Tk, mask, mask_bs, mask_rs,
                         key_bias, scale, dtype, st);
 }

@@ -236,6 +236,10 @@ int attention_tc(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
                  const uint8_t* mask, int64_t mask_bs, int64_t mask_rs, const float* key_bias,
                  float scale, int dtype, cudaStream_t st);
 int attention_tc_init();
+// two-query-tile ping-pong organisation for long query ranges (attention_pp.cu); same contract as attention_tc
+int attention_pp(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts, const void* v,
+                 int64_t v_bs, int64_t v_ts, void* out, int B, int H, int Tq, int Tk, const uint8_t* mask, int64_t mask_bs,
+                 int64_t mask_rs, float scale, cudaStream_t st);
 
 // general GEMM of the training path (gemm_gen.cu): C (+)= alpha * opA(A) opB(B)^T, transposed operands, (head, batch) dims
 bool gemm_gen_tc_supported(const void* A, long long lda, long long a_hs, long long a_bs, const void* B, long long ldb,

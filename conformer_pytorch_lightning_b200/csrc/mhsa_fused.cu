@@ -278,8 +278,14 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_ld32(tmem_srow + c * 32, v);
         tmem_ld_wait();
         if (vis[c] == 0xffffffffu) {
+          // four independent chains instead of one 32-deep FMNMX dependency chain
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) m_part = fmaxf(m_part, __uint_as_float(v[e]));
+          for (int e = 4; e < 32; e += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[e])); m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[e + 2])); m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+          }
+          m_part = fmaxf(m_part, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         } else if (vis[c] != 0u) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -305,13 +311,19 @@ mhsa_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (!((vis[c] >> e) & 1u)) v[e] = 0xff800000u;  // -inf
         }
         uint32_t pk[16];
+        float la = 0.f, lb = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
+        for (int e = 0; e < 32; e += 4) {
           const float p0 = ex2_fast(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_m));
           const float p1 = ex2_fast(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_m));
-          l += p0 + p1;
+          const float p2 = ex2_fast(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, neg_m));
+          const float p3 = ex2_fast(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
+          la += p0 + p1;
+          lb += p2 + p3;
           pk[e >> 1] = pack_bf16x2(p0, p1);
+          pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
         }
+        l += la + lb;
         // this row's 16-byte chunks 4c'..4c'+3 (c' = 4 grp + c) of the 32-chunk P row: atom = c'/2
         const int cc0 = 4 * (grp * 4 + c);
 #pragma unroll

@@ -53,7 +53,7 @@ def _counts(names):
     return {n: _native.kernel_launches(n) for n in names}
 
 
-FUSED = ("ffn_fused", "mhsa_fused", "conv_fused", "attention_tc", "gemm_tc", "gemm_simt", "dwconv")
+FUSED = ("ffn_fused", "mhsa_fused", "conv_fused", "attention_tc", "attention_pp", "gemm_tc", "gemm_simt", "dwconv")
 
 
 @pytest.mark.parametrize("name", ["C2", "C3", "C4"])
@@ -82,9 +82,9 @@ def test_fullsize_bf16_measured_path_vs_oracle(name):
         # per pass: 13 chained feed-forward launches (12 layers) and one fused convolution module per layer
         assert ran["ffn_fused"] == L + 1 and ran["conv_fused"] == L and ran["dwconv"] == 0
     if name == "C2":
-        assert ran["mhsa_fused"] == L and ran["attention_tc"] == 0
+        assert ran["mhsa_fused"] == L and ran["attention_tc"] + ran["attention_pp"] == 0
     if name == "C4" and ran["mhsa_fused"] == 0:
-        assert ran["attention_tc"] == L               # long sequences: flash kernel + residual GEMM
+        assert ran["attention_pp"] == L               # long sequences: ping-pong flash kernel + residual GEMM
 
 
 @pytest.mark.parametrize("name", ["C2", "C3", "C4"])

@@ -35,6 +35,14 @@ elif which == "attn":
     mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
     for _ in range(3):
         ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, mask=mask, scale=0.125)
+elif which == "attn_long":
+    B, T, H = 16, 1498, 4
+    qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
+    out = torch.empty(B, T, H * 64, device=dev, dtype=torch.bfloat16)
+    lens = torch.randint(T // 2, T + 1, (B,), device=dev)
+    mask = (torch.arange(T, device=dev)[None, :] < lens[:, None]).unsqueeze(1)
+    for _ in range(3):
+        ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, mask=mask, scale=0.125)
 elif which == "dwconv":
     B, T = 64, 248
     x = torch.randn(B, T, d, device=dev).bfloat16(); y = torch.empty_like(x)
