@@ -83,7 +83,7 @@ def _declare(lib):
     lib.cfm_ln_bwd.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]
     lib.cfm_silu_dropout_fwd.argtypes = [_p, _p, _i, _i, _i, _f, _p, _i, _p]
     lib.cfm_silu_dropout_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _f, _p, _i, _p]
-    lib.cfm_resid_dropout_add.argtypes = [_p, _p, _i, _i, _i, _f, _p, _f, _p, _i, _p]
+    lib.cfm_resid_dropout_add.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _p, _i, _p]
     lib.cfm_scale_dropout_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _f, _p, _f, _p, _i, _p]
     lib.cfm_glu_fwd.argtypes = [_p, _p, _i, _i, _i, _p]
     lib.cfm_glu_bwd.argtypes = [_p, _p, _p, _p, _i, _i, _i, _p]

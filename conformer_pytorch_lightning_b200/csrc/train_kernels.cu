@@ -140,7 +140,7 @@ __device__ __forceinline__ void rowwise(int rows, int cols, float* __restrict__ 
 inline dim3 rowwise_grid(int rows, int cols, int vec) {
   const int gx = (cols + 32 * vec - 1) / (32 * vec);
   int gy = (rows + 7) / 8;
-  const int cap = max(1, 2 * num_sms() / gx);
+  const int cap = max(1, 4 * num_sms() / gx);
   if (gy > cap) gy = cap;
   return dim3(gx, max(gy, 1));
 }
@@ -295,19 +295,22 @@ silu_dropout_bwd_kernel(const T* da, const T* __restrict__ h, T* dh, float* __re
 // x += alpha * rowmask * dropout(f)
 template <typename T>
 __global__ void __launch_bounds__(256)
-resid_dropout_add_kernel(float* x, const T* __restrict__ f, int rows, int cols, float alpha,
+resid_dropout_add_kernel(const float* x_in, float* x_out, const T* __restrict__ f, int rows, int cols, float alpha,
                          const uint8_t* __restrict__ row_valid, Drop drop) {
   constexpr int V = Vec<T>::N;
   rowwise<V>(rows, cols, nullptr, [&](int r, int c0, float (&)[V]) {
-    if (row_valid != nullptr && row_valid[r] == 0) return;
     const size_t e = (size_t)r * cols + c0;
     float v[V], m[V], xv[V];
-    Vec<T>::load(f + e, v);
-    drop_mult<V>(drop, e, m);
-    load_f32<V>(x + e, xv);
+    load_f32<V>(x_in + e, xv);
+    if (row_valid == nullptr || row_valid[r] != 0) {
+      Vec<T>::load(f + e, v);
+      drop_mult<V>(drop, e, m);
 #pragma unroll
-    for (int i = 0; i < V; ++i) xv[i] = fmaf(alpha * m[i], v[i], xv[i]);
-    store_f32<V>(x + e, xv);
+      for (int i = 0; i < V; ++i) xv[i] = fmaf(alpha * m[i], v[i], xv[i]);
+    } else if (x_in == x_out) {
+      return;
+    }
+    store_f32<V>(x_out + e, xv);
   });
 }
 // df = alpha * rowmask * mask * dx   (fp32 -> T);  dbias += colsum(df)
@@ -624,14 +627,15 @@ extern "C" int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, flo
   return 0;
 }
 
-extern "C" int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols, int dtype, float alpha,
+extern "C" int cfm_resid_dropout_add(const float* x_in, float* x, const void* f, int rows, int cols, int dtype, float alpha,
                                      const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream) {
   CFM_CHECK_ARG(x && f, "cfm_resid_dropout_add: null pointer");
+  if (x_in == nullptr) x_in = x;
   if (check_rc(rows, cols, dtype, "cfm_resid_dropout_add") != 0) return -1;
   if (rows == 0) return 0;
   const Drop dr = make_drop(p, seed, site);
   CFM_BY_DTYPE(dtype, (resid_dropout_add_kernel<T><<<rowwise_grid(rows, cols, Vec<T>::N), 256, 0, (cudaStream_t)stream>>>(
-                          x, (const T*)f, rows, cols, alpha, row_valid, dr)));
+                          x_in, x, (const T*)f, rows, cols, alpha, row_valid, dr)));
   CFM_LAUNCHED_K("resid_dropout_add");
   return 0;
 }

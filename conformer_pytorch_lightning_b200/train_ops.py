@@ -59,12 +59,13 @@ def silu_dropout_bwd(da, h, dh, dbias, *, p=0.0, seed=0, site=0):
     return dh
 
 
-def resid_dropout_add(x, f, *, alpha=1.0, row_valid=None, p=0.0, seed=0, site=0):
+def resid_dropout_add(x, f, *, x_in=None, alpha=1.0, row_valid=None, p=0.0, seed=0, site=0):
+    """x = (x_in if given else x) + alpha * rowmask * dropout(f)."""
     _req(x, "resid_dropout_add.x", torch.float32)
     _req(f, "resid_dropout_add.f")
     rows, cols = x.shape
     ensure_init(x)
-    N.check(N.lib().cfm_resid_dropout_add(x.data_ptr(), f.data_ptr(), rows, cols, _DT[f.dtype], float(alpha), _ptr(row_valid),
+    N.check(N.lib().cfm_resid_dropout_add(_ptr(x_in), x.data_ptr(), f.data_ptr(), rows, cols, _DT[f.dtype], float(alpha), _ptr(row_valid),
                                           float(p), _seed_ptr(seed, p), int(site), _stream(x)))
     return x
 

@@ -122,8 +122,7 @@ def _ffn_fwd(x_in, W, ln_g, ln_b, n, d, dtype, p_in, p_out, seed, site_in, site_
     else:
         f = torch.empty((n, d), dtype=dtype, device=dev)
         ops.gemm(a, W["w2"], W["b2"], f, N.EPI_BIAS)
-        x_out.copy_(x_in)
-        TO.resid_dropout_add(x_out, f, alpha=0.5, p=p_out, seed=seed, site=site_out)
+        TO.resid_dropout_add(x_out, f, x_in=x_in, alpha=0.5, p=p_out, seed=seed, site=site_out)
     sv[tag] = dict(x=x_in, y=y, mean=mean, rstd=rstd, h=h, a=a)
     return x_out
 
@@ -153,8 +152,7 @@ def _mhsa_fwd(x_in, W, ln_g, ln_b, run, H, n, d, p_att, p_out, site_p, site_out,
     else:
         f = torch.empty((n, d), dtype=dtype, device=dev)
         ops.gemm(ctx, W["wo"], W["bo"], f, N.EPI_BIAS)
-        x_out.copy_(x_in)
-        TO.resid_dropout_add(x_out, f, alpha=1.0, p=p_out, seed=run.seed, site=site_out)
+        TO.resid_dropout_add(x_out, f, x_in=x_in, alpha=1.0, p=p_out, seed=run.seed, site=site_out)
     sv["mha"] = dict(x=x_in, y=y, mean=mean, rstd=rstd, qkv=qkv, P=P, Pd=Pd, ctx=ctx, Tp=Tp)
     return x_out
 
@@ -203,8 +201,7 @@ def _conv_fwd(x_in, W, ln_g, ln_b, module, run, n, d, p_out, site_out, sv):
     else:
         f = torch.empty((n, d), dtype=dtype, device=dev)
         ops.gemm(c, W["w2"], W["b2"], f, N.EPI_BIAS)
-        x_out.copy_(x_in)
-        TO.resid_dropout_add(x_out, f, alpha=1.0, row_valid=rv, p=p_out, seed=run.seed, site=site_out)
+        TO.resid_dropout_add(x_out, f, x_in=x_in, alpha=1.0, row_valid=rv, p=p_out, seed=run.seed, site=site_out)
     sv["conv"] = dict(x=x_in, y=y, mean=mean, rstd=rstd, g=g, u=u, raw=raw, bmean=bmean, brstd=brstd, c=c,
                       batch_stats=batch_stats)
     return x_out

@@ -294,10 +294,11 @@ int cfm_silu_dropout_fwd(const void* h, void* a, int rows, int cols, int dtype, 
                          void* stream);
 int cfm_silu_dropout_bwd(const void* da, const void* h, void* dh, float* dbias, int rows, int cols, int dtype, float p,
                          const uint64_t* seed, int site, void* stream);
-/* x += alpha * rowmask * dropout(f)  (the residual adds of encoder_layer.py:58,62,66,69 with their dropout and the
- * masked_fill of convolution.py:47-48) and its backward df = alpha * rowmask * mask * dx, dbias += colsum(df). */
-int cfm_resid_dropout_add(float* x, const void* f, int rows, int cols, int dtype, float alpha, const uint8_t* row_valid,
-                          float p, const uint64_t* seed, int site, void* stream);
+/* x = x_in + alpha * rowmask * dropout(f)  (the residual adds of encoder_layer.py:58,62,66,69 with their dropout and the
+ * masked_fill of convolution.py:47-48; x_in null or == x: in place) and its backward df = alpha * rowmask * mask * dx,
+ * dbias += colsum(df). */
+int cfm_resid_dropout_add(const float* x_in, float* x, const void* f, int rows, int cols, int dtype, float alpha,
+                          const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream);
 int cfm_scale_dropout_bwd(const float* dx, void* df, float* dbias, int rows, int cols, int dtype, float alpha,
                           const uint8_t* row_valid, float p, const uint64_t* seed, int site, void* stream);
 /* GLU over the channel halves of g (rows, 2d) (convolution.py:42) and its backward (dbias: 2d bias gradient of
