@@ -130,11 +130,6 @@ extern "C" int cfm_ffn(const void* y, int ld_in, const void* W1, const float* b1
   if (engine == CFM_ENGINE_TC)
     CFM_CHECK_ARG(fused_ok, "cfm_ffn: fused tcgen05 path does not support M=%d d=%d F=%d dtype=%d", M, d, F, dtype);
   if (fused_ok && engine != CFM_ENGINE_SIMT) {
-    // CFM_B200_FFN_MODE: "pair" = tcgen05 cta_group::2 kernel (ffn_pair.cu), anything else = ffn_fused.cu
-    static const bool pair_mode = env_is("CFM_B200_FFN_MODE", "pair");
-    if (pair_mode)
-      return ffn_pair(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
-                      eps, (cudaStream_t)stream);
     return ffn_fused(y, ld_in, W1, b1, W2, b2, X, ldx, M, F, alpha, ln_mode, g1, be1, g2, be2, Y, ld_out, y_row_valid,
                      eps, (cudaStream_t)stream);
   }

@@ -211,10 +211,6 @@ struct FfnModule {               // one PositionwiseFeedForwardModule + the Laye
 bool ffn_chain_supported(int M, int d, int F, int dtype, const FfnModule* a, const FfnModule& b, int Np);
 int ffn_chain(const void* y_in, const FfnModule* a, const FfnModule& b, float* X, int M, int F, void* y_out,
               const uint8_t* y_row_valid, float eps, const void* Wp, const float* bp, void* P, int Np, cudaStream_t st);
-int ffn_pair(const void* y_in, int ld_in, const void* W1, const float* b1, const void* W2, const float* b2, float* X,
-             int ldx, int M, int F, float alpha, int ln_mode, const float* g1, const float* be1, const float* g2,
-             const float* be2, void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st);
-
 bool mhsa_fused_supported(int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs, int64_t v_ts, int B, int H,
                           int Tq, int Tk, int d, int dtype, bool has_key_bias);
 int mhsa_fused(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64_t k_bs, int64_t k_ts, const void* v,

@@ -1,3 +1,6 @@
+// EXPERIMENT, not part of libcfm_b200.so (removed from the product build in round 2): cta_group::2 variant of the fused
+// feed-forward kernel.  Numerically correct, 45.9 us vs 30.8 us for ffn_fused.cu; kept as the starting point for the
+// 'two tiles in flight per SM' lead of DESIGN.md section 8.  Builds against csrc/*.cuh.
 // Fused macaron feed-forward, CTA-pair edition (tcgen05 cta_group::2) for sm_100a, d = 256.
 //
 // Same algorithm and schedule as ffn_fused.cu (see there), but every tcgen05.mma spans the two SMs of a 2-CTA
