@@ -117,6 +117,6 @@ class ConvolutionSubSampling(nn.Module):
         scratch = ws.get("subsample_ws", (ops.subsample_ws_bytes(B, tin, idim, c),), torch.uint8, inputs.device)
         act = ws.get("subsample_act", (B * t2, f2 * c), torch.bfloat16, inputs.device)
         ops.subsample_conv(inputs.contiguous(), W["w1"], W["b1"], W["w2"], W["b2"], scratch, act)
-        out = torch.zeros((B * t2, c), dtype=torch.float32, device=inputs.device)
-        ops.gemm(act, W["w3"], W["b3"], out, ops.N.EPI_RESIDUAL, residual=out, alpha=1.0)
+        out = torch.empty((B * t2, c), dtype=torch.float32, device=inputs.device)
+        ops.gemm(act, W["w3"], W["b3"], out, ops.N.EPI_RESIDUAL, residual=None, alpha=1.0)     # fp32 output, no residual
         return out.view(B, t2, c)

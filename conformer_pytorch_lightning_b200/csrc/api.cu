@@ -72,7 +72,7 @@ extern "C" int cfm_gemm(const void* A, int lda, const void* W, const float* bias
   CFM_CHECK_ARG(A && W && C, "cfm_gemm: null A/W/C");
   CFM_CHECK_ARG(dtype == CFM_F32 || dtype == CFM_BF16, "cfm_gemm: bad dtype %d", dtype);
   CFM_CHECK_ARG(epilogue >= CFM_EPI_BIAS && epilogue <= CFM_EPI_BIAS_RELU, "cfm_gemm: bad epilogue %d", epilogue);
-  CFM_CHECK_ARG(epilogue != CFM_EPI_RESIDUAL || residual != nullptr, "cfm_gemm: EPI_RESIDUAL needs residual");
+  // EPI_RESIDUAL with residual == nullptr: fp32 output without a residual operand, X = alpha * rowmask(A W^T + b)
   CFM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lda >= K && ldc >= N, "cfm_gemm: bad shape M=%d N=%d K=%d lda=%d ldc=%d",
                 M, N, K, lda, ldc);
   if (M == 0) return 0;

@@ -94,7 +94,7 @@ gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, cons
         ((T*)Cv)[off] = from_f32<T>(v * act_sigmoid<T>(g));
       } else {
         if (!valid) v = 0.f;
-        ((float*)Cv)[off] = residual[off] + alpha * v;
+        ((float*)Cv)[off] = (residual ? residual[off] : 0.f) + alpha * v;
       }
     }
   }
@@ -187,7 +187,7 @@ gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, co
   } else {
     const bool valid = (row_valid == nullptr) || (row_valid[m] != 0);
     if (!valid) v = 0.f;
-    ((float*)Cv)[off] = residual[off] + alpha * v;
+    ((float*)Cv)[off] = (residual ? residual[off] : 0.f) + alpha * v;
   }
 }
 

@@ -105,6 +105,7 @@ struct GemmParams {
   float alpha, eps;
   int M, N, K;                  // N = number of OUTPUT columns (GLU: W has 2N rows)
   int ln_mode;                  // 0 none, 1 y = LN1(X), 2 X = LN1(.), y = LN2(X)
+  int no_resid;                 // RESIDUAL epilogue without a residual operand: X = alpha * rowmask(acc + bias) (fp32 output)
   unsigned long long* keys;     // ARGMAX epilogue: per-row packed (ordered logit, ~column), combined with atomicMax
   int n_valid;                  // ARGMAX: columns >= n_valid are padding (W rows zero-filled by TMA)
 };
@@ -337,12 +338,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
         constexpr int RG = C::kBufs / 2;                  // staging tiles per warpgroup
         uint8_t* gring = ring + grp * RG * kBufBytes;
-        if (elected) resid_prefetch<BN, RG, 128, 2>(gring, res_bar + grp * RG, &tmR, n0, m0, grp);   // lands during the main loop
+        if (elected && !p.no_resid) resid_prefetch<BN, RG, 128, 2>(gring, res_bar + grp * RG, &tmR, n0, m0, grp);   // lands during the main loop
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
         ResidParams rp{p.row_valid, p.y_row_valid, p.alpha, p.eps, p.ln_mode, p.M};
+        ResidOpts ro;
+        ro.no_residual = p.no_resid != 0;
         resid_ln_epilogue<BN, RG, 128, 2>(taddr, r, m0, n0, elected, bar_id, gring, res_bar + grp * RG, ring_phase, sparam, &tmC,
-                                          &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sparam + 5 * BN));
+                                          &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sparam + 5 * BN), -1, -1, ro);
         mbar_arrive(tempty_bar + acc);
       }
     }
@@ -419,6 +422,8 @@ int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* 
   p.g1 = g1; p.b1 = b1; p.g2 = g2; p.b2 = b2;
   p.alpha = alpha; p.eps = eps; p.M = M; p.N = N; p.K = K; p.ln_mode = ln_mode;
   if (epilogue == CFM_EPI_RESIDUAL) {
+    p.no_resid = residual == nullptr ? 1 : 0;
+    if (residual == nullptr) residual = X;           // (tensor map only; never loaded)
     CFM_CHECK_ARG(aligned16(X) && aligned16(residual), "cfm_gemm(tc): X/residual must be 16-byte aligned");
     if ((rc = make_2d(&tmC, true, X, M, N, ldx, BM)) != 0) return rc;
     if ((rc = make_2d(&tmR, true, residual, M, N, ldx, BM)) != 0) return rc;

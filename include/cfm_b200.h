@@ -38,7 +38,8 @@ extern "C" {
 #define CFM_EPI_BIAS_SILU 1  /* C[act]  = silu(A W^T + b)                  w_1 + SiLU (feedforward.py:17-18)          */
 #define CFM_EPI_BIAS_GLU  2  /* C[act]  = (A Wa^T + ba) * sigmoid(A Wb^T + bb), W = [Wa;Wb]
                                                                            pointwise_conv1 + GLU (convolution.py:41-42) */
-#define CFM_EPI_RESIDUAL  3  /* X[f32]  = R + alpha * rowmask(A W^T + b)   w_2 / linear_out / pointwise_conv2 + the
+#define CFM_EPI_RESIDUAL  3  /* X[f32]  = R + alpha * rowmask(A W^T + b)   (R may be null: plain fp32 output)
+                                                                           w_2 / linear_out / pointwise_conv2 + the
                                                                            residual adds of encoder_layer.py:58,62,66,69
                                                                            and the masked_fill of convolution.py:47-48 */
 

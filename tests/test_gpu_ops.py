@@ -601,3 +601,19 @@ def test_ctc_greedy_head_matches_oracle_decode():
                 seq.append(t)
             prev = t
         assert hyps[b] == seq
+
+
+@pytest.mark.parametrize("engine", [N.ENGINE_TC, N.ENGINE_SIMT])
+def test_gemm_fp32_output_without_residual(engine):
+    """EPI_RESIDUAL with residual = None: X = alpha * rowmask(A W^T + b) in fp32 (the front-end Linear writes its fp32
+    output this way instead of accumulating onto a zeroed buffer)."""
+    M, K, Nn = 1000, 256, 256
+    a = rnd(M, K, dtype=torch.bfloat16, seed=41)
+    w = rnd(Nn, K, dtype=torch.bfloat16, seed=42)
+    bias = rnd(Nn, dtype=torch.float32, seed=43)
+    out = torch.full((M, Nn), float("nan"), dtype=torch.float32, device=DEV)
+    rv = (torch.arange(M, device=DEV) % 9 != 4)
+    ops.gemm(a, w, bias, out, N.EPI_RESIDUAL, residual=None, alpha=0.5, row_valid=rv, engine=engine)
+    ref = 0.5 * (a.float() @ w.float().t() + bias) * rv[:, None]
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 1e-5
