@@ -194,8 +194,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             if constexpr (CL == 1) {
               tma_load_2d(dst, tm, w_full + stage, col, row);
               tma_load_2d(dst + kAtom, tm, w_full + stage, col, row + 128);
-            } else {           // each CTA fetches 128 of the 256 rows and multicasts them
-              tma_load_2d_mc(dst + crank * kAtom, tm, w_full + stage, col, row + crank * 128, kMask);
+            } else {           // each CTA fetches 256 / CL of the 256 rows and multicasts them to the whole cluster
+              tma_load_2d_mc(dst + crank * (kPiece / CL), tm, w_full + stage, col, row + crank * (256 / CL), kMask);
             }
           }
           __syncwarp();
@@ -214,7 +214,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             tma_load_2d(dst, &tmWp, w_full + stage, col, row);
             tma_load_2d(dst + kAtom, &tmWp, w_full + stage, col, row + 128);
           } else {
-            tma_load_2d_mc(dst + crank * kAtom, &tmWp, w_full + stage, col, row + crank * 128, kMask);
+            tma_load_2d_mc(dst + crank * (kPiece / CL), &tmWp, w_full + stage, col, row + crank * (256 / CL), kMask);
           }
         }
         __syncwarp();
@@ -538,16 +538,19 @@ bool ffn_fused_supported(int ld_in, int ldx, int ld_out, int M, int d, int F, in
 static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n, float* X, int ldx, int M, int F,
                       void* y_out, int ld_out, const uint8_t* y_row_valid, float eps, cudaStream_t st,
                       const void* Wp = nullptr, const float* bp = nullptr, void* P = nullptr, int Np = 0) {
-  static const int cl_env = env_is("CFM_B200_FFN_CLUSTER", "1") ? 1 : 2;
+  // cluster size along M: the CTAs of a cluster share every weight piece through TMA multicast (CFM_B200_FFN_CLUSTER)
+  static const int cl_env = env_is("CFM_B200_FFN_CLUSTER", "1") ? 1 : (env_is("CFM_B200_FFN_CLUSTER", "4") ? 4 : 2);
   CFM_SMEM_OPT_IN(ffn_fused_kernel<1>, kSmemBytes);
   CFM_SMEM_OPT_IN(ffn_fused_kernel<2>, kSmemBytes);
+  CFM_SMEM_OPT_IN(ffn_fused_kernel<4>, kSmemBytes);
   const int CL = cl_env;
+  const int wbox = CL == 4 ? 64 : 128;         // rows of a weight piece one CTA fetches per TMA
   CUtensorMap tmA, tmW1[2], tmW2[2], tmX, tmY;
   int rc;
   if ((rc = make_2d_map(&tmA, false, y_in, M, D, ld_in)) != 0) return rc;
   for (int i = 0; i < n; ++i) {
-    if ((rc = make_2d_map(&tmW1[i], false, mods[i].W1, F, D, D)) != 0) return rc;
-    if ((rc = make_2d_map(&tmW2[i], false, mods[i].W2, D, F, F)) != 0) return rc;
+    if ((rc = make_2d_map(&tmW1[i], false, mods[i].W1, F, D, D, wbox)) != 0) return rc;
+    if ((rc = make_2d_map(&tmW2[i], false, mods[i].W2, D, F, F, wbox)) != 0) return rc;
   }
   if (n == 1) { tmW1[1] = tmW1[0]; tmW2[1] = tmW2[0]; }
   if ((rc = make_2d_map(&tmX, true, X, M, D, ldx)) != 0) return rc;
@@ -556,7 +559,7 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   if (ln_last != 0 && Wp == nullptr && (rc = make_2d_map(&tmY, false, y_out, M, D, ld_out)) != 0) return rc;
   CUtensorMap tmWp = tmW1[0], tmP = tmA;
   if (Wp != nullptr) {
-    if ((rc = make_2d_map(&tmWp, false, Wp, Np, D, D)) != 0) return rc;
+    if ((rc = make_2d_map(&tmWp, false, Wp, Np, D, D, wbox)) != 0) return rc;
     if ((rc = make_2d_map(&tmP, false, P, M, Np, Np)) != 0) return rc;
   }
   FfnParams p;
@@ -572,6 +575,9 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
   if (CL == 1)
     CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1[0], tmW2[0], tmW1[1],
+                           tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
+  else if (CL == 4)
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<4>, dim3(grid), dim3(kThreads), kSmemBytes, st, 4, tmA, tmW1[0], tmW2[0], tmW1[1],
                            tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   else
     CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],

@@ -35,6 +35,17 @@ elif which == "attn":
     mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
     for _ in range(3):
         ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, mask=mask, scale=0.125)
+elif which == "gemm512":
+    # Conformer-L (C3) shapes: the feed-forward GEMMs at d = 512
+    Ml, dl = 15936, 512
+    y = torch.randn(Ml, dl, device=dev).bfloat16()
+    w1 = (torch.randn(F, dl, device=dev) / 22).bfloat16(); b1 = torch.randn(F, device=dev)
+    w2 = (torch.randn(dl, F, device=dev) / 45).bfloat16(); b2 = torch.randn(dl, device=dev)
+    h = torch.empty(Ml, F, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(Ml, dl, device=dev)
+    for _ in range(3):
+        ops.gemm(y, w1, b1, h, N.EPI_BIAS_SILU)
+        ops.gemm(h, w2, b2, x, N.EPI_RESIDUAL, residual=x, alpha=0.5)
 elif which == "attn_long":
     B, T, H = 16, 1498, 4
     qkv = torch.randn(B, T, 3, H, 64, device=dev).bfloat16()
