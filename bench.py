@@ -744,6 +744,45 @@ def run_train(args):
     torch.cuda.synchronize()
     phases = {"forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]),
               "optimizer_ms": ev[2].elapsed_time(ev[3])}
+    # same-box GPU bar: the reference's training arithmetic as eager PyTorch autograd on this GPU (ATen port of the
+    # reference modules: F.linear / conv1d / layer_norm / batch_norm / softmax / F.ctc_loss, bf16 autocast, dropout 0 --
+    # dropout would only add kernels), forward + backward without the optimizer step
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        from oracle import conformer_oracle_torch as OT
+        cfg0 = dict(cfg, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0)
+        sd_g = {k: (v.to(dev).requires_grad_() if v.is_floating_point() and "running" not in k else v.to(dev))
+                for k, v in OT.to_torch_sd(O.make_state_dict(cfg0, 0)).items()}
+        w_g = dec.ctc_lo.weight.detach().clone().requires_grad_()
+        b_g = dec.ctc_lo.bias.detach().clone().requires_grad_()
+        leaves = [v for v in sd_g.values() if v.requires_grad] + [w_g, b_g]
+        pos_g = OT.rel_pos_table(cfg0["max_len"], cfg0["encoder_dim"])[:B].to(dev)
+        Tin = feats_dev.size(1)
+        pad_g = (torch.arange(Tin, device=dev).unsqueeze(0) < lens.unsqueeze(1).long()).unsqueeze(1)
+        chunk_g = OT.chunk_mask(T, 16, -1).to(dev).unsqueeze(0)
+
+        def eager_step():
+            for v in leaves:
+                v.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                x, pad2 = OT.subsampling(feats_dev, pad_g, sd_g)
+                out_e = OT.encoder_layers_train(x, pad2 & chunk_g, pos_g, pad2, sd_g, cfg0)
+            loss_e = OT.ctc_loss(out_e.float(), pad2.squeeze(1).sum(1), labels, lab_len, w_g, b_g)
+            loss_e.backward()
+        for _ in range(2):
+            eager_step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(4):
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            eager_step()
+            e_.record()
+            e_.synchronize()
+            ts.append(s_.elapsed_time(e_))
+        eager = {"bf16_autocast_fwd_bwd_ms": float(np.median(ts)), "ours_fwd_bwd_ms": phases["forward_ms"] + phases["backward_ms"],
+                 "what": "eager PyTorch autograd (ATen port of the reference modules + F.ctc_loss) on the same B200, bf16 "
+                         "autocast, dropout 0, forward + backward of one 16-utterance batch, no optimizer step"}
     fam = {f: _native.kernel_launches(f) for f in ("gemm_tc", "gemm_gen", "gemm_gen_simt", "gemm_simt", "ln_bwd", "softmax_bwd",
                                                    "ctc_grad", "dwconv_wgrad")}
     pk = peaks()
@@ -774,7 +813,7 @@ def run_train(args):
                              "frac": (algo_tf + ctc_tf) / (ms / 1e3) / tf_peak, "traffic": None},
                 "grad_allreduce": None if sync is None else {"buckets_per_step": sync.buckets_sent // max(1, (args.steps + max(3, args.warmup) + e2e_steps + 1)),
                                                             "bytes_per_step": sync.bytes_sent // max(1, (args.steps + max(3, args.warmup) + e2e_steps + 1))},
-                "cpu_baseline": None, "clocks": clocks}
+                "cpu_baseline": None, "clocks": clocks, "extra": {"eager_gpu_baseline": eager}}
         out_f = real_stdout if real_stdout is not None else sys.stdout
         out_f.write(json.dumps(line) + "\n")
         out_f.flush()
