@@ -238,36 +238,35 @@ class RNNPredictor(nn.Module):
 @torch.no_grad()
 def basic_greedy_search(predictor, joint, encoder_out, encoder_out_lens, blank=0, n_steps=64, cache=None,
                         pred_input_step=None):
-    """model.py:221-269: frame-synchronous greedy decoding of ONE utterance (encoder_out (1, T, E)); at most ``n_steps``
-    non-blank symbols per frame.  Returns (hyps, (pred_input_step, cache))."""
+    """Frame-synchronous greedy transducer decoding of ONE utterance (semantics of model.py:221-269): at every encoder
+    frame the joint is evaluated on (frame, current predictor output); a non-blank argmax is emitted, fed back through
+    the predictor (whose LSTM state advances only then) and the same frame is tried again, up to ``n_steps`` symbols per
+    frame; a blank moves on to the next frame.  encoder_out (1, T, E).  Returns (hyps, (last symbol, predictor state))
+    so that a streaming caller can continue from where it stopped."""
     dev = encoder_out.device
-    padding = torch.zeros(1, 1, device=dev)
-    if pred_input_step is None:
-        pred_input_step = torch.tensor([blank], device=dev).reshape(1, 1)
-    else:
-        pred_input_step = pred_input_step.to(dev)
-    if cache is None:
-        cache = predictor.init_state(pred_input_step)
-    else:
-        cache = (cache[0].to(dev), cache[1].to(dev))
-    new_cache = []
-    t, hyps, prev_out_nblk, pred_out_step, per_frame_noblk = 0, [], True, None, 0
+    no_padding = torch.zeros(1, 1, device=dev)
+    symbol = (torch.tensor([[blank]], device=dev) if pred_input_step is None else pred_input_step.to(dev))
+    state = predictor.init_state(symbol) if cache is None else (cache[0].to(dev), cache[1].to(dev))
+    hyps = []
+    pred_out, next_state = None, None
+    refresh = True                       # the predictor output is stale (start, or a symbol was just emitted)
     n_frames = int(encoder_out_lens)
-    while t < n_frames:
-        encoder_out_step = encoder_out[:, t:t + 1, :]
-        if prev_out_nblk:
-            pred_out_step, new_cache = predictor.forward_step(pred_input_step, padding, cache)
-        joint_out_step = joint(encoder_out_step, pred_out_step)              # (1, 1, 1, V): native joint step
-        joint_out_max = int(joint_out_step.float().log_softmax(dim=-1).argmax(dim=-1).squeeze())
-        if joint_out_max != blank:
-            hyps.append(joint_out_max)
-            prev_out_nblk = True
-            per_frame_noblk += 1
-            pred_input_step = torch.tensor([joint_out_max], device=dev).reshape(1, 1)
-            cache = new_cache
-        if joint_out_max == blank or per_frame_noblk >= n_steps:
-            if joint_out_max == blank:
-                prev_out_nblk = False
-            t += 1
-            per_frame_noblk = 0
-    return hyps, (pred_input_step, cache)
+    for t in range(n_frames):
+        frame = encoder_out[:, t:t + 1, :]
+        emitted = 0
+        while True:
+            if refresh:
+                pred_out, next_state = predictor.forward_step(symbol, no_padding, state)
+            logits = joint(frame, pred_out)                                   # (1, 1, 1, V): native joint step
+            best = int(logits.float().log_softmax(dim=-1).argmax(dim=-1).squeeze())
+            if best == blank:
+                refresh = False
+                break
+            hyps.append(best)
+            symbol = torch.tensor([[best]], device=dev)
+            state = next_state
+            refresh = True
+            emitted += 1
+            if emitted >= n_steps:
+                break
+    return hyps, (symbol, state)

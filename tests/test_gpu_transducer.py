@@ -84,17 +84,44 @@ def test_rnnt_loss_alone_matches_torchaudio_on_fp32_logits():
     assert _rel(ln.grad, lr.grad) < 1e-4
 
 
-def test_greedy_search_equals_reference_loop_with_torch_joint():
+def _reference_greedy(predictor, joint_fn, encoder_out, n_frames, blank, n_steps):
+    """Test-side restatement of the reference's loop (model.py:221-269), statement by statement, with a torch joint."""
+    dev = encoder_out.device
+    padding = torch.zeros(1, 1, device=dev)
+    pred_input_step = torch.tensor([blank], device=dev).reshape(1, 1)
+    cache = predictor.init_state(pred_input_step)
+    new_cache = []
+    t, hyps, prev_out_nblk, pred_out_step, per_frame_noblk = 0, [], True, None, 0
+    while t < n_frames:
+        encoder_out_step = encoder_out[:, t:t + 1, :]
+        if prev_out_nblk:
+            pred_out_step, new_cache = predictor.forward_step(pred_input_step, padding, cache)
+        joint_out_max = int(joint_fn(encoder_out_step, pred_out_step).log_softmax(dim=-1).argmax(dim=-1).squeeze())
+        if joint_out_max != blank:
+            hyps.append(joint_out_max)
+            prev_out_nblk = True
+            per_frame_noblk += 1
+            pred_input_step = torch.tensor([joint_out_max], device=dev).reshape(1, 1)
+            cache = new_cache
+        if joint_out_max == blank or per_frame_noblk >= n_steps:
+            if joint_out_max == blank:
+                prev_out_nblk = False
+            t += 1
+            per_frame_noblk = 0
+    return hyps, (pred_input_step, cache)
+
+
+@pytest.mark.parametrize("n_steps", [1, 4])
+def test_greedy_search_equals_reference_loop_with_torch_joint(n_steps):
     torch.manual_seed(3)
     V = 40
     joint = C.TransducerJoint(V, 256, 256, 512).cuda().eval()
+    with torch.no_grad():
+        joint.ffn_out.bias[0] -= 1.0            # make blanks rarer so that several symbols per frame occur
     pred = C.RNNPredictor(V, 64, 256, 128, 0.0, 2, dropout=0.0).cuda().eval()
     enc_out = torch.randn(1, 23, 256, device="cuda") * 2
-
-    class TorchJoint(torch.nn.Module):
-        def forward(self, e, p):
-            return _torch_joint(joint, e, p)
-    hyps, (last, cache) = C.basic_greedy_search(pred, joint, enc_out, torch.tensor(23), blank=0, n_steps=4)
-    ref, (last_r, cache_r) = C.basic_greedy_search(pred, TorchJoint(), enc_out, torch.tensor(23), blank=0, n_steps=4)
+    with torch.no_grad():
+        ref, (last_r, cache_r) = _reference_greedy(pred, lambda e, p: _torch_joint(joint, e, p), enc_out, 23, 0, n_steps)
+    hyps, (last, cache) = C.basic_greedy_search(pred, joint, enc_out, torch.tensor(23), blank=0, n_steps=n_steps)
     assert hyps == ref and len(hyps) > 0
     assert torch.equal(last, last_r) and torch.allclose(cache[0], cache_r[0])
