@@ -14,6 +14,7 @@ backward of layers i-1, ....
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 
@@ -402,6 +403,10 @@ def stack_backward(dout, run):
 
 
 # ----------------------------------------------------------------------------------------------- CUDA-graph plans
+class _Token:
+    pass
+
+
 class TrainPlan:
     """A training step of the stack is ~780 small launches; issued one by one from Python the GPU idles most of the
     time.  Like the inference path, a (shape, dtype, mask layout, dropout configuration) is captured once into CUDA
@@ -414,8 +419,14 @@ class TrainPlan:
         self.pool = None
         self.fwd = None
         self.bwd = None           # list of (graph, stage) in execution order
-        self.busy = False         # a forward whose backward has not run yet owns the static buffers
+        self.pending = None       # weak reference to the autograd node of a forward whose backward has not run yet: it
+                                  # owns the static buffers.  A node that died without a backward (a forward whose loss was
+                                  # dropped) releases them.
         self.calls = 0
+
+    @property
+    def busy(self):
+        return self.pending is not None and self.pending() is not None
 
 
 def _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync):
@@ -542,7 +553,8 @@ class EncoderStackFunction(torch.autograd.Function):
         if plan is not None:
             plan.fwd.replay()
             engine.GRAPH_REPLAYED_LAUNCHES[0] += plan.fwd_launches
-            plan.busy = True
+            ctx.token = _Token()                       # dies with the autograd node
+            plan.pending = weakref.ref(ctx.token)
             ctx.run = plan.run
             return plan.out.clone()
         out = stack_forward(x_emb, run)
@@ -554,10 +566,10 @@ class EncoderStackFunction(torch.autograd.Function):
     def backward(ctx, dout):
         run, plan = ctx.run, ctx.plan
         if plan is not None:
-            if not plan.busy:
+            if plan.pending is None or plan.pending() is not getattr(ctx, "token", None):
                 raise RuntimeError("the native encoder backward can run only once per forward")
             dx, layer_grads, after_grads = _replay_backward(plan, dout.contiguous())
-            plan.busy = False
+            plan.pending = None
         else:
             if run.saved is None:
                 raise RuntimeError("the native encoder backward can run only once per forward (activations are released)")

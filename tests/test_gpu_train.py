@@ -230,3 +230,36 @@ def test_cuda_graph_training_plan_equals_eager(p_drop):
             # (the front-end's backward is PyTorch / cuDNN: its atomics make embed.* gradients run-to-run noisy)
             tol = 1e-1 if k.startswith("embed.") else 5e-2        # bf16 + atomic order; the exact check is the output
             assert float((g[k] - g_r[k]).abs().max()) < tol * scale, k
+
+
+def test_training_plan_is_released_by_a_dropped_forward_and_survives_accumulation():
+    """A forward whose loss is dropped (no backward) must not block the CUDA-graph plan for ever, and two forwards before
+    one backward (gradient accumulation) stay correct: the second runs eagerly."""
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0)
+    enc = build_encoder(cfg, 6, compute_dtype=torch.bfloat16).train()
+    rs = np.random.RandomState(9)
+    feats = torch.from_numpy(rs.standard_normal((2, 300, 80)).astype(np.float32)).cuda()
+    lens = torch.tensor([300, 260], dtype=torch.int32).cuda()
+    for _ in range(3):                                   # eager, capture, replay
+        enc.zero_grad(set_to_none=True)
+        enc(feats, lens)[0].square().mean().backward()
+    plan = next(iter(enc._train_plans.values()))
+    assert plan.fwd is not None and not plan.busy
+    out, _ = enc(feats, lens)                            # forward only ...
+    assert plan.busy
+    del out                                              # ... and its graph is dropped
+    import gc
+    gc.collect()
+    assert not plan.busy
+    enc.zero_grad(set_to_none=True)
+    o1, _ = enc(feats, lens)                             # plan
+    o2, _ = enc(feats * 0.5, lens)                       # plan is busy: eager schedule
+    (o1.square().mean() + o2.square().mean()).backward()
+    g_acc = enc.encoders[0].feed_forward.w_1.weight.grad.clone()
+    enc.use_cuda_graphs = False
+    enc.zero_grad(set_to_none=True)
+    o1, _ = enc(feats, lens)
+    o2, _ = enc(feats * 0.5, lens)
+    (o1.square().mean() + o2.square().mean()).backward()
+    g_ref = enc.encoders[0].feed_forward.w_1.weight.grad
+    assert float((g_acc - g_ref).abs().max()) < 2e-2 * float(g_ref.abs().max())
