@@ -15,6 +15,7 @@
 #include "cfm_common.cuh"
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace cfm {
 namespace {
@@ -35,12 +36,28 @@ struct AttnPPParams {
   int H, Tq, Tk;
   float scale_log2;
   int mask_aligned8;
+  long long* trace;     // optional clock64 timeline of CTA (0,0,0) (tools/attn_pp_trace.py); nullptr in production
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic constant, minimax cubic
+// for 2^f on [-0.5, 0.5] (relative error < 1e-4, far below the bf16 rounding of P), n added into the exponent field.
+// x <= -125 (masked keys are -inf) returns exactly 0 like ex2.approx.ftz.
+__device__ __forceinline__ float ex2_fma(float x) {
+  const float xc = fmaxf(x, -125.f);
+  const float xf = xc + 12582912.f;
+  const float n = xf - 12582912.f;
+  const float f = xc - n;
+  float p = fmaf(f, 0.05520738f, 0.24262359f);
+  p = fmaf(p, f, 0.69325767f);
+  p = fmaf(p, f, 0.99992728f);
+  const float r = __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+  return x > -125.f ? r : 0.f;
 }
 
 __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8) {
@@ -63,6 +80,7 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8)
   return bits;
 }
 
+template <bool kToken, bool kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
@@ -84,6 +102,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int i0 = blockIdx.x * (NQ * QT);
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.Tk + KT - 1) / KT;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define PTR(slot) do { if (tr && lane == 0) p.trace[(slot)] = clock64(); } while (0)
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
@@ -135,9 +155,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     };
+    PTR(0);
     mbar_wait(q_full, 0);
     mbar_wait(kv_full, 0);
     tc_fence_after();
+    PTR(1);
     issue_s(0, 0);
     issue_s(1, 0);
     for (int j = 0; j < n_kv; ++j) {
@@ -146,6 +168,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int q = 0; q < NQ; ++q) {
         mbar_wait(p_ready + q, j & 1);          // P_q(j) in smem, S_q(j) read out, O_q(j-1) drained
         tc_fence_after();
+        if (j < 6) PTR(16 + (j * 2 + q) * 2);
         if (elect_one()) {
           const uint64_t dv = umma_desc_sw128(smem_u32(sKV + s * 2 * kTile + kTile));
           const uint32_t pa = smem_u32(sP + q * kPBytes);
@@ -163,6 +186,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (q == 0) { mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1); tc_fence_after(); }
           issue_s(q, j + 1);                    // S_q is free: group q has read S_q(j) (p_ready above)
         }
+        if (j < 6) PTR(16 + (j * 2 + q) * 2 + 1);
       }
     }
   } else if (warp < 8) {
@@ -182,14 +206,27 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int c = 0; c < DK; ++c) o[c] = 0.f;
 
+    // The two groups take turns in the MUFU-bound ex2 pass (a token passed through two named barriers): started together
+    // they stay in phase, fight for the MUFU during their ex2 passes and idle together while the P V products are in
+    // flight (measured: 4.35 k cycles per tile and group).  With the token one group's ex2 pass runs alone while the
+    // other waits for its S tile, takes the row maximum and folds the previous P V product into its registers.
+    const bool bcast_mask = p.mask != nullptr && p.mask_rs == 0;
+    // (B,1,Tk) key-padding mask: each thread fetches one byte per tile, ONE TILE AHEAD (the dependent global load used to
+    // sit at the top of every iteration: ~600 exposed cycles per tile)
+    uint8_t mbyte = (bcast_mask && r < p.Tk) ? __ldg(p.mask + b * p.mask_bs + r) : (uint8_t)0;
+    float alpha_prev = 1.f;
 #pragma unroll 1
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
       const int j0 = j * KT;
       uint32_t vis[4];
-      if (p.mask != nullptr && p.mask_rs == 0) {
+      if (bcast_mask) {
         const int jj = j0 + r;
-        const bool on = (jj < p.Tk) && (__ldg(p.mask + b * p.mask_bs + jj) != 0);
+        const bool on = (jj < p.Tk) && (mbyte != 0);
+        {
+          const int jn = jj + KT;
+          mbyte = (j + 1 < n_kv && jn < p.Tk) ? __ldg(p.mask + b * p.mask_bs + jn) : (uint8_t)0;
+        }
         const uint32_t w = __ballot_sync(0xffffffffu, on);
         uint32_t* sv = svis + (g * 2 + (j & 1)) * 4;
         if (lane == 0) sv[wq] = w;
@@ -213,8 +250,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           vis[c] = bits;
         }
       }
+      if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 0);
       mbar_wait(s_full + g, ph);
       tc_fence_after();
+      if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 1);
       // Only two warps share a scheduler here, so the ~250-cycle latency of every tcgen05.ld is exposed unless the loads
       // are batched / software-pipelined in registers: pass 1 fetches the row in two 64-column halves (2 exposed
       // latencies instead of 4), pass 2 fetches chunk c+1 before it computes chunk c (1 exposed latency instead of 4).
@@ -247,14 +286,34 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       m_tile *= p.scale_log2;
+      if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 2);
       const float m_new = fmaxf(m_run, m_tile);
       const bool any = m_new != -CUDART_INF_F;
       const float alpha = any ? exp2f(m_run - m_new) : 1.f;
       const float neg_m = any ? -m_new : 0.f;
+      // O_tile(j-1) = P(j-1) V(j-1) -> registers with ITS rescale factor, now (it was issued when P(j-1) was published and has
+      // had the whole max pass of this tile to complete); must be consumed before P(j) is published (P V(j) overwrites it)
+      if (j > 0) {
+        mbar_wait(o_full + g, (j - 1) & 1);
+        tc_fence_after();
+        if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 4);
+        uint32_t va[32], vb[32];
+        tmem_ld32(tmem_o, va);
+        tmem_ld32(tmem_o + 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha_prev, __uint_as_float(va[e]));
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[32 + e] = fmaf(o[32 + e], alpha_prev, __uint_as_float(vb[e]));
+        if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 5);
+      }
       float l_tile = 0.f;
       uint32_t vbuf[2][32];
       tmem_ld32(tmem_s, vbuf[0]);
       tmem_ld_wait();
+      // take the MUFU token: group 1 after group 0's pass of the same tile, group 0 after group 1's pass of the previous tile
+      if (kToken ? g == 1 : (g == 1 && j == 0)) asm volatile("bar.sync 3, 256;" ::: "memory");
+      else if (kToken && g == 0 && j > 0) asm volatile("bar.sync 4, 256;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t (&v)[32] = vbuf[c & 1];
@@ -271,7 +330,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float p0 = ex2_fast(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_m));
           const float p1 = ex2_fast(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_m));
           const float p2 = ex2_fast(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, neg_m));
-          const float p3 = ex2_fast(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
+          const float p3 = (kPoly ? ex2_fma : ex2_fast)(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
           la += p0 + p1;
           lb += p2 + p3;
           pk[e >> 1] = pack_bf16x2(p0, p1);
@@ -291,21 +350,26 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready + g);
-      // O_tile = P V of this tile -> registers with the online rescale (the other group's ex2 pass runs meanwhile)
-      mbar_wait(o_full + g, ph);
-      tc_fence_after();
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld32(tmem_o, va);
-        tmem_ld32(tmem_o + 32, vb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha, __uint_as_float(va[e]));
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[32 + e] = fmaf(o[32 + e], alpha, __uint_as_float(vb[e]));
-      }
-      tc_fence_before();
+      // hand the MUFU token over
+      if (kToken ? g == 0 : (g == 0 && j == 0)) asm volatile("bar.arrive 3, 256;" ::: "memory");
+      else if (kToken && g == 1 && j + 1 < n_kv) asm volatile("bar.arrive 4, 256;" ::: "memory");
+      if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 3);
+      alpha_prev = alpha;
     }
+    // the last tile's P V product
+    mbar_wait(o_full + g, (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+      uint32_t va[32], vb[32];
+      tmem_ld32(tmem_o, va);
+      tmem_ld32(tmem_o + 32, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha_prev, __uint_as_float(va[e]));
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[32 + e] = fmaf(o[32 + e], alpha_prev, __uint_as_float(vb[e]));
+    }
+    tc_fence_before();
     if (row_ok) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Tq + i) * p.H * DK + h * DK);
@@ -336,7 +400,6 @@ int attention_pp(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   CFM_CHECK_ARG(scale > 0.f, "cfm_attention(pp): scale must be positive");
   CFM_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                   reinterpret_cast<uintptr_t>(out)) & 15) == 0, "cfm_attention(pp): q/k/v/out must be 16-byte aligned");
-  CFM_SMEM_OPT_IN(attention_pp_kernel, kSmemBytes);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_tmap3(&tmQ, q, B, Tq, H, q_bs, q_ts)) != 0) return rc;
@@ -347,9 +410,20 @@ int attention_pp(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   p.mask = mask; p.mask_bs = mask_bs; p.mask_rs = mask_rs;
   p.H = H; p.Tq = Tq; p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = nullptr;
+  if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + NQ * QT - 1) / (NQ * QT), H, B);
-  CFM_CUDA_OK(launch_pdl(attention_pp_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
+  static const int variant = env_is("CFM_B200_ATTN_PP_VARIANT", "token") ? 1 : env_is("CFM_B200_ATTN_PP_VARIANT", "poly") ? 2 : 0;
+#define CFM_PP_LAUNCH(TOK, POLY)                                                                              \
+  do {                                                                                                        \
+    CFM_SMEM_OPT_IN((attention_pp_kernel<TOK, POLY>), kSmemBytes);                                            \
+    CFM_CUDA_OK(launch_pdl(attention_pp_kernel<TOK, POLY>, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p)); \
+  } while (0)
+  if (variant == 1) CFM_PP_LAUNCH(true, false);
+  else if (variant == 2) CFM_PP_LAUNCH(false, true);
+  else CFM_PP_LAUNCH(false, false);
+#undef CFM_PP_LAUNCH
   CFM_LAUNCHED_K("attention_pp");
   return 0;
 }
