@@ -13,8 +13,15 @@ std::atomic<int64_t> g_launches{0};
 struct KernelCounter { std::atomic<const char*> name{nullptr}; std::atomic<int64_t> n{0}; };
 static KernelCounter g_kernels[96];
 
+static void count_named(const char* name);
 void count_launch(const char* name) {
   g_launches.fetch_add(1);
+  count_named(name);
+}
+// a variant of a kernel family ("gemm_tc_pair" inside "gemm_tc"): named counter only, the launch itself is counted by
+// count_launch under the family name
+void count_variant(const char* name) { count_named(name); }
+static void count_named(const char* name) {
   for (auto& k : g_kernels) {
     const char* cur = k.name.load(std::memory_order_acquire);
     if (cur == nullptr) {

@@ -45,21 +45,6 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic constant, minimax cubic
-// for 2^f on [-0.5, 0.5] (relative error < 1e-4, far below the bf16 rounding of P), n added into the exponent field.
-// x <= -125 (masked keys are -inf) returns exactly 0 like ex2.approx.ftz.
-__device__ __forceinline__ float ex2_fma(float x) {
-  const float xc = fmaxf(x, -125.f);
-  const float xf = xc + 12582912.f;
-  const float n = xf - 12582912.f;
-  const float f = xc - n;
-  float p = fmaf(f, 0.05520738f, 0.24262359f);
-  p = fmaf(p, f, 0.69325767f);
-  p = fmaf(p, f, 0.99992728f);
-  const float r = __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
-  return x > -125.f ? r : 0.f;
-}
-
 __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8) {
   uint32_t bits = 0;
   if (aligned8) {
@@ -80,7 +65,6 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8)
   return bits;
 }
 
-template <bool kToken, bool kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
@@ -206,10 +190,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int c = 0; c < DK; ++c) o[c] = 0.f;
 
-    // The two groups take turns in the MUFU-bound ex2 pass (a token passed through two named barriers): started together
-    // they stay in phase, fight for the MUFU during their ex2 passes and idle together while the P V products are in
-    // flight (measured: 4.35 k cycles per tile and group).  With the token one group's ex2 pass runs alone while the
-    // other waits for its S tile, takes the row maximum and folds the previous P V product into its registers.
+    // Started together the two groups stay in phase: they fight for the MUFU during their ex2 passes and idle together
+    // while the P V products are in flight (clock trace: 4.35 k cycles per tile and group).  Group 1 therefore starts one
+    // ex2 pass late (see below): 4.0 k.  Measured dead ends (tools/attn_pp_trace.py): a strict token
+    // that lets only one group into the ex2 pass at a time (a pass takes 2.0 k cycles alone, 2.3 k for both groups
+    // together: the pass is latency / issue bound per warp, not MUFU bound), and a cubic-polynomial ex2 on the FMA pipe
+    // for a quarter or half of the elements (more instructions per warp: 4.9 k).
     const bool bcast_mask = p.mask != nullptr && p.mask_rs == 0;
     // (B,1,Tk) key-padding mask: each thread fetches one byte per tile, ONE TILE AHEAD (the dependent global load used to
     // sit at the top of every iteration: ~600 exposed cycles per tile)
@@ -311,9 +297,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t vbuf[2][32];
       tmem_ld32(tmem_s, vbuf[0]);
       tmem_ld_wait();
-      // take the MUFU token: group 1 after group 0's pass of the same tile, group 0 after group 1's pass of the previous tile
-      if (kToken ? g == 1 : (g == 1 && j == 0)) asm volatile("bar.sync 3, 256;" ::: "memory");
-      else if (kToken && g == 0 && j > 0) asm volatile("bar.sync 4, 256;" ::: "memory");
+      // group 1 starts its first ex2 pass after group 0's: from then on one group's MUFU-bound pass overlaps the other's
+      // S wait / row maximum / O fold instead of both fighting for the MUFU and idling together
+      if (g == 1 && j == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t (&v)[32] = vbuf[c & 1];
@@ -330,7 +316,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float p0 = ex2_fast(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_m));
           const float p1 = ex2_fast(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_m));
           const float p2 = ex2_fast(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, neg_m));
-          const float p3 = (kPoly ? ex2_fma : ex2_fast)(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
+          const float p3 = ex2_fast(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
           la += p0 + p1;
           lb += p2 + p3;
           pk[e >> 1] = pack_bf16x2(p0, p1);
@@ -350,9 +336,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready + g);
-      // hand the MUFU token over
-      if (kToken ? g == 0 : (g == 0 && j == 0)) asm volatile("bar.arrive 3, 256;" ::: "memory");
-      else if (kToken && g == 1 && j + 1 < n_kv) asm volatile("bar.arrive 4, 256;" ::: "memory");
+      if (g == 0 && j == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
       if (wq == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 3);
       alpha_prev = alpha;
     }
@@ -414,16 +398,8 @@ int attention_pp(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + NQ * QT - 1) / (NQ * QT), H, B);
-  static const int variant = env_is("CFM_B200_ATTN_PP_VARIANT", "token") ? 1 : env_is("CFM_B200_ATTN_PP_VARIANT", "poly") ? 2 : 0;
-#define CFM_PP_LAUNCH(TOK, POLY)                                                                              \
-  do {                                                                                                        \
-    CFM_SMEM_OPT_IN((attention_pp_kernel<TOK, POLY>), kSmemBytes);                                            \
-    CFM_CUDA_OK(launch_pdl(attention_pp_kernel<TOK, POLY>, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p)); \
-  } while (0)
-  if (variant == 1) CFM_PP_LAUNCH(true, false);
-  else if (variant == 2) CFM_PP_LAUNCH(false, true);
-  else CFM_PP_LAUNCH(false, false);
-#undef CFM_PP_LAUNCH
+  CFM_SMEM_OPT_IN(attention_pp_kernel, kSmemBytes);
+  CFM_CUDA_OK(launch_pdl(attention_pp_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
   CFM_LAUNCHED_K("attention_pp");
   return 0;
 }

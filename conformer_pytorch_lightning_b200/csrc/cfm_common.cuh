@@ -37,6 +37,7 @@ extern std::atomic<int64_t> g_launches;
 // every kernel launch goes through this so that bench.py can report `gpu_launches`; the per-kernel counters
 // (cfm_kernel_launches("ffn_fused") ...) let the tests assert WHICH engine served a call
 void count_launch(const char* name);
+void count_variant(const char* name);
 #define CFM_LAUNCHED_K(name)                            \
   do {                                                  \
     ::cfm::count_launch(name);                          \

@@ -79,9 +79,13 @@ constexpr int BK = 64;        // K per stage    = one 128-byte swizzle atom of b
 constexpr int UK = 16;        // K per tcgen05.mma (bf16)
 constexpr int kMaxSmem = 232448;
 
-template <int BN, bool RESID> struct Cfg {
+// PAIR: the tile is 256 rows x BN columns on the two SMs of a 2-CTA cluster (tcgen05 cta_group::2): every CTA stages its own
+// 128 A rows and only HALF of the W rows, so the shared-memory fill and the B-operand reads per SM are halved (the
+// single-CTA kernel reads 96 B/clk of operands and fills 96 B/clk by TMA against the 128 B/clk one SM's shared memory
+// serves) and the smaller stage buys a deeper ring.
+template <int BN, bool RESID, bool PAIR = false> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue warps: every epilogue is latency bound with one warp per scheduler, so two warpgroups split the tile's
   // columns (2 warps / SMSP); the residual/LN epilogue exchanges its partial row sums through shared memory
@@ -90,7 +94,7 @@ template <int BN, bool RESID> struct Cfg {
   static constexpr int kBufs = 4;                                  // staging ring (2 per warpgroup)
   static constexpr int kParamFloats = RESID ? 5 * BN + 1024 : BN;  // bias (+ LN gammas/betas + row-sum exchange)
   static constexpr int kFixed = kBufs * kBufBytes + kParamFloats * 4 + 256 /*barriers*/ + 1024 /*align slack*/;
-  static constexpr int kStages = (kMaxSmem - kFixed) / kStageBytes > 6 ? 6 : (kMaxSmem - kFixed) / kStageBytes;
+  static constexpr int kStages = (kMaxSmem - kFixed) / kStageBytes > (PAIR ? 8 : 6) ? (PAIR ? 8 : 6) : (kMaxSmem - kFixed) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -108,13 +112,14 @@ struct GemmParams {
   int no_resid;                 // RESIDUAL epilogue without a residual operand: X = alpha * rowmask(acc + bias) (fp32 output)
   unsigned long long* keys;     // ARGMAX epilogue: per-row packed (ordered logit, ~column), combined with atomicMax
   int n_valid;                  // ARGMAX: columns >= n_valid are padding (W rows zero-filled by TMA)
+  int pair;                     // host-side: launch the cta_group::2 kernel (W tensor map holds half-tile boxes)
 };
 constexpr int EPI_ARGMAX = 100; // internal epilogue of cfm_ctc_argmax: no C tile at all
 
 
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL>::kThreads), 1)
+template <int BN, int EPI, bool PAIR>
+__global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC,   // F1: bf16 output; RESIDUAL: fp32 X store
                const __grid_constant__ CUtensorMap tmR,   // RESIDUAL: fp32 residual load
@@ -122,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const GemmParams p) {
   constexpr bool GLU = (EPI == CFM_EPI_BIAS_GLU);
   constexpr bool RESID = (EPI == CFM_EPI_RESIDUAL);
-  using C = Cfg<BN, RESID>;
+  using C = Cfg<BN, RESID, PAIR>;
   constexpr int OUT_BN = GLU ? BN / 2 : BN;      // output columns per tile
   // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
   // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
@@ -137,10 +142,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + C::kBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  constexpr int TM = PAIR ? 2 * BM : BM;            // rows per scheduled tile (pair: 128 per CTA)
+  const int m_tiles = (p.M + TM - 1) / TM;
   const int n_tiles = p.N / OUT_BN;
   const int total = m_tiles * n_tiles;
   const int kb_count = p.K / BK;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_off = (int)crank * BM;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -150,28 +161,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, C::kEpiThreads); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, (PAIR ? 2 : 1) * C::kEpiThreads); }
     for (int s = 0; s < C::kBufs; ++s) mbar_init(res_bar + s, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_2sm<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();           // both CTAs' barriers initialised, TMEM allocated in both SMs
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
+  // shared::cluster addresses of the LEADER's barriers this CTA signals (pair: operand bytes of both CTAs are credited
+  // to the leader's full barriers; the leader collects both CTAs' accumulator drains)
+  [[maybe_unused]] const uint32_t full_ldr = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;
+  [[maybe_unused]] const uint32_t tempty_ldr = PAIR ? mapa_u32(smem_u32(tempty_bar), 0) : 0u;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0, phase = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int m0 = (t / n_tiles) * BM, nb = t % n_tiles;
+    for (int t = tile0; t < total; t += tstep) {
+      const int m0 = (t / n_tiles) * TM + m_off, nb = t % n_tiles;
       for (int kb = 0; kb < kb_count; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
+          if constexpr (PAIR) {
+            if (leader) mbar_expect_tx(full_bar + stage, 2 * C::kStageBytes);
+            const uint32_t bar = full_ldr + stage * 8;
+            tma_load_2d_2sm(sa, &tmA, bar, kb * BK, m0);
+            // the pair's B operand is CTA 0's rows followed by CTA 1's: GLU -> value half | gate half
+            if constexpr (GLU) tma_load_2d_2sm(sb, &tmW, bar, kb * BK, (int)crank * p.N + nb * OUT_BN);
+            else tma_load_2d_2sm(sb, &tmW, bar, kb * BK, nb * BN + (int)crank * (BN / 2));
+          } else {
           mbar_expect_tx(full_bar + stage, C::kStageBytes);
           tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m0);
           if constexpr (GLU) {   // value half and gate half of [Wa;Wb] side by side in one B tile
@@ -180,19 +207,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(sb, &tmW, full_bar + stage, kb * BK, nb * BN);
           }
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues; pair: leader CTA only) ==========
+    constexpr uint32_t idesc = umma_idesc_bf16(TM, BN);
     int stage = 0, phase = 0, it = 0;
     bool have = false;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = tile0; t < total; t += tstep, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(tempty_bar + acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+      if constexpr (PAIR) mbar_wait_cluster(tempty_bar + acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
+      else mbar_wait(tempty_bar + acc, acc_phase ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < kb_count; ++kb) {
@@ -208,10 +237,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the 16-byte-unit start address
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
+          if constexpr (PAIR) {                         // multicast: the slot / accumulator barriers of BOTH CTAs
+            umma_commit_2sm(empty_bar + stage, 0x3);
+            if (kb == kb_count - 1) umma_commit_2sm(tfull_bar + acc, 0x3);
+          } else {
           umma_commit(empty_bar + stage);             // frees the smem slot when these MMAs retire
           if (kb == kb_count - 1) umma_commit(tfull_bar + acc);   // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -229,9 +264,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ring_phase = 0;                          // bit b = parity of the next completion of res_bar[b]
     int sub_cnt = 0;                                  // F1: running staging-buffer counter
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    auto release_acc = [&](int a) {
+      if constexpr (PAIR) mbar_arrive_cluster(tempty_ldr + a * 8);
+      else mbar_arrive(tempty_bar + a);
+    };
+    for (int t = tile0; t < total; t += tstep, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * OUT_BN;
+      const int m0 = (t / n_tiles) * TM + m_off, n0 = (t % n_tiles) * OUT_BN;
       const uint32_t taddr = tmem_base + lane_base + acc * BN;
 
       // ---- per-tile parameters -> smem (previous tile's readers are past their last bar.sync); each warpgroup
@@ -279,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           tc_fence_before();
-          mbar_arrive(tempty_bar + acc);
+          release_acc(acc);
           const int row = m0 + r;
           if (row < p.M && best > -CUDART_INF_F) {
             uint32_t u = __float_as_uint(best);
@@ -332,7 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar + acc);
+        release_acc(acc);
         }
       } else {
         // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
@@ -346,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ro.no_residual = p.no_resid != 0;
         resid_ln_epilogue<BN, RG, 128, 2>(taddr, r, m0, n0, elected, bar_id, gring, res_bar + grp * RG, ring_phase, sparam, &tmC,
                                           &tmR, &tmY, rp, grp, 3, reinterpret_cast<float2*>(sparam + 5 * BN), -1, -1, ro);
-        mbar_arrive(tempty_bar + acc);
+        release_acc(acc);
       }
     }
     if (elected) bulk_wait_read<0>();   // the stores only have to be done READING shared memory before the CTA retires
@@ -354,20 +393,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<C::kTmemCols>(tmem_base);
+  if constexpr (PAIR) cluster_sync_all();           // nobody frees TMEM / exits while the peer's MMAs may still touch it
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int EPI, bool PAIR>
+int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                   const CUtensorMap& tmY, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR>;
+  CFM_SMEM_OPT_IN((gemm_tc_kernel<BN, EPI, PAIR>), C::kSmemBytes);
+  constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  const int total = ((p.M + TM - 1) / TM) * (p.N / OUT_BN);
+  const int slots = PAIR ? num_sms() / 2 : num_sms();
+  const int grid = (total < slots ? total : slots) * (PAIR ? 2 : 1);
+  CFM_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, EPI, PAIR>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, PAIR ? 2 : 1, tmA,
+                         tmW, tmC, tmR, tmY, p));
+  CFM_LAUNCHED_K("gemm_tc");
+  if (PAIR) count_variant("gemm_tc_pair");
+  return 0;
+}
+
+// CTA pairs (256-row tiles) pay where the main loop is long: measured on the BASELINE shapes (tools/gemm_shapes_bench.py,
+// L2 flushed) K=2048/N=512 54.3 -> 50.2 us, K=2048/N=256 37.9 -> 35.8, K=512/N=1536 35.8 -> 33.8; short-K tiles with a
+// heavy epilogue lose (K=256/N=2048 + SiLU 29.6 -> 35.7, K=512/N=512 + residual 29.7 -> 31.7: the cluster-scope
+// accumulator hand-back and the 2-CTA launch granularity cost more than the halved operand traffic saves).
+// CFM_B200_GEMM_PAIR=0/1 forces the choice (measurement switch).
+inline bool use_pair(int M, int N, int K, int epilogue) {
+  static const bool off = env_is("CFM_B200_GEMM_PAIR", "0"), on = env_is("CFM_B200_GEMM_PAIR", "1");
+  if (off || M <= BM) return false;
+  if (on) return true;
+  return K >= 1024 || (K >= 512 && N >= 1024 && epilogue == CFM_EPI_BIAS);
 }
 
 template <int BN, int EPI>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
               const CUtensorMap& tmY, const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL>;
-  CFM_SMEM_OPT_IN((gemm_tc_kernel<BN, EPI>), C::kSmemBytes);
-  constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
-  const int total = ((p.M + BM - 1) / BM) * (p.N / OUT_BN);
-  const int grid = total < num_sms() ? total : num_sms();
-  CFM_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmA, tmW, tmC, tmR, tmY, p));
-  CFM_LAUNCHED_K("gemm_tc");
-  return 0;
+  if (p.pair) return launch_tc_impl<BN, EPI, true>(tmA, tmW, tmC, tmR, tmY, p, st);
+  return launch_tc_impl<BN, EPI, false>(tmA, tmW, tmC, tmR, tmY, p, st);
 }
 
 // output-tile width: 256 when it divides N (fewer, fatter tiles), else 128
@@ -413,11 +479,13 @@ int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* 
   CFM_CHECK_ARG(aligned16(A) && aligned16(W), "cfm_gemm(tc): A/W must be 16-byte aligned");
   const int bn = pick_bn(N, epilogue);
   const int w_rows = (epilogue == CFM_EPI_BIAS_GLU) ? 2 * N : N;
+  const bool pair = use_pair(M, N, K, epilogue);
   CUtensorMap tmA, tmW, tmC, tmR, tmY;
   int rc;
   if ((rc = make_2d(&tmA, false, A, M, K, lda, BM)) != 0) return rc;
-  if ((rc = make_2d(&tmW, false, W, w_rows, K, K, (epilogue == CFM_EPI_BIAS_GLU) ? 128 : bn)) != 0) return rc;
+  if ((rc = make_2d(&tmW, false, W, w_rows, K, K, (epilogue == CFM_EPI_BIAS_GLU) ? 128 : (pair ? bn / 2 : bn))) != 0) return rc;
   GemmParams p{};
+  p.pair = pair ? 1 : 0;
   p.bias = bias; p.row_valid = row_valid; p.y_row_valid = y_row_valid;
   p.g1 = g1; p.b1 = b1; p.g2 = g2; p.b2 = b2;
   p.alpha = alpha; p.eps = eps; p.M = M; p.N = N; p.K = K; p.ln_mode = ln_mode;
@@ -462,8 +530,10 @@ int gemm_tc_argmax(const void* A, int lda, const void* W, const float* bias, int
   CUtensorMap tmA, tmW;
   int rc;
   if ((rc = make_2d(&tmA, false, A, M, K, lda, BM)) != 0) return rc;
-  if ((rc = make_2d(&tmW, false, W, V, K, K, 256)) != 0) return rc;     // rows >= V of the last block: zero-filled
+  const bool pair = use_pair(M, n_pad, K, EPI_ARGMAX);
+  if ((rc = make_2d(&tmW, false, W, V, K, K, pair ? 128 : 256)) != 0) return rc;     // rows >= V of the last block: zero-filled
   GemmParams p{};
+  p.pair = pair ? 1 : 0;
   p.bias = bias; p.M = M; p.N = n_pad; p.K = K; p.keys = keys; p.n_valid = V;
   return launch_tc<256, EPI_ARGMAX>(tmA, tmW, tmA, tmA, tmA, p, st);
 }

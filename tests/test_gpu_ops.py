@@ -1,6 +1,7 @@
 """Op-level parity of every C-ABI kernel against a plain PyTorch fp32 restatement of the same
 reference statements (level 1).  Runs on the B200 box: pytest -m gpu."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -183,10 +184,14 @@ def test_errors_are_reported_not_thrown_across_abi():
 
 
 @pytest.mark.parametrize("M,Nn,K", [(128, 256, 256), (200, 256, 2048), (1000, 2048, 256), (333, 768, 256), (4096, 512, 512),
-                                    (15872, 2048, 256), (777, 384, 128), (64, 128, 64)])
+                                    (15872, 2048, 256), (777, 384, 128), (64, 128, 64),
+                                    # long-K shapes run on CTA pairs (cta_group::2, 256-row tiles): odd tile counts leave a
+                                    # phantom half tile past M, N = 128 uses 64-row W boxes
+                                    (300, 256, 1024), (1000, 512, 2048), (129, 128, 1024), (4000, 1536, 512)])
 def test_gemm_tcgen05(M, Nn, K):
     """tcgen05/TMEM/TMA engine vs fp32 matmul of the same bf16 operands (and vs the SIMT engine)."""
     dt = torch.bfloat16
+    pairs0 = N.kernel_launches("gemm_tc_pair")
     a = rnd(M, K, dtype=dt)
     w = rnd(Nn, K, dtype=dt, scale=1 / math.sqrt(K), seed=1)
     bias = rnd(Nn, seed=3)
@@ -220,6 +225,8 @@ def test_gemm_tcgen05(M, Nn, K):
     ops.gemm(abig[:, :K], w, bias, obig[:, :Nn], N.EPI_BIAS, engine=N.ENGINE_TC)
     assert rel_err(obig[:, :Nn].float(), abig[:, :K].float() @ wf.t() + bias) < 6e-3
     assert float(obig[:, Nn:].abs().max()) == 0.0
+    if os.environ.get("CFM_B200_GEMM_PAIR") is None and M > 128:
+        assert (N.kernel_launches("gemm_tc_pair") > pairs0) == (K >= 1024 or (K >= 512 and Nn >= 1024))
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,kind", [(2, 4, 248, 248, "pad"), (3, 4, 74, 74, "chunk"), (2, 8, 130, 130, "left"),
