@@ -32,7 +32,11 @@ constexpr int kAtom = 16384;    // one swizzle atom tile: 128 rows x 64 k bf16
 constexpr int kPiece = 32768;   // one weight piece = one ring slot = 512 tensor-pipe cycles of MMA work per barrier wait
                                 //   G1: W1 rows [256 p,+256) x 64 k   (4 MMAs N=256)
                                 //   G2: W2 rows [0,256) x 64 hidden-k (4 MMAs N=256)
-constexpr int NST = 3;          // weight ring depth
+constexpr int NST = 3;          // weight ring depth (single-CTA kernel: 3 x 32 KB)
+constexpr int kSlotPair = kPiece / 2;   // CTA-pair kernel: each CTA holds HALF of every weight piece (its 128 of the 256
+constexpr int NST_PAIR = 6;             // rows) -> the same 96 KB hold a 6-deep ring
+static_assert(NST * kPiece == NST_PAIR * kSlotPair, "both kernels share one shared-memory layout");
+constexpr int kMaxStages = NST_PAIR;
 constexpr int kABytes = BM * D * 2;            // 64 KB
 constexpr int kHBytes = BM * HC * 2;           // 32 KB per H buffer
 #ifndef CFM_FFN_SILU_GROUPS
@@ -86,7 +90,14 @@ __device__ __forceinline__ void job_of(int jx, int NP, bool& g1, int& idx) {
 // CL = thread-block cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on adjacent
 // 128-token tiles in lock-step and share every weight piece: each CTA fetches half of the piece's rows and
 // TMA-multicasts it into both CTAs' rings, halving the L2 -> SM weight traffic (2 MB per tile otherwise).
-template <int CL>
+//
+// PAIR: tcgen05 cta_group::2.  The two CTAs of a cluster own adjacent 128-token tiles; every MMA spans both SMs (M = 256),
+// issued by the leader CTA, and takes rows [0,128) of its B operand from the leader's shared memory and rows [128,256)
+// from the peer's.  Per SM this halves the weight fill (TMA) and the B-operand reads -- the shared-memory port is what
+// holds the single-CTA kernel at ~50 % tensor-pipe activity -- and the ring gets twice as deep.  Barriers the MMA issuer
+// waits on live in the leader and collect warp-aggregated remote arrivals from both CTAs; barriers the other warps wait
+// on are signalled in both CTAs by multicast commits.
+template <int CL, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16, box 64 x 128
                  const __grid_constant__ CUtensorMap tmW1,   // W1 (F, 256) bf16, box 64 x 128
@@ -109,9 +120,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
                                                   // the last MMA of the tile and is only ever written by this CTA's own TMA
   float* sb1 = reinterpret_cast<float*>(sW + NST * kPiece);   // [2][HC]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb1 + 2 * HC);
-  uint64_t* w_full = bars;                    // [NST]
-  uint64_t* w_empty = w_full + NST;           // [NST]
-  uint64_t* a_full = w_empty + NST;           // [1]
+  constexpr int kNst = PAIR ? NST_PAIR : NST;
+  constexpr int kSlot = PAIR ? kSlotPair : kPiece;
+  static_assert(!PAIR || CL == 1, "the pair kernel does not multicast");
+  uint64_t* w_full = bars;                    // [kNst]
+  uint64_t* w_empty = w_full + kMaxStages;    // [kNst]
+  uint64_t* a_full = w_empty + kMaxStages;    // [1]
   uint64_t* s_full = a_full + 1;              // [1]  S accumulator of a chunk pair complete (MMA commit)
   uint64_t* s_empty = s_full + 1;             // [1]  S read by all SiLU threads
   uint64_t* h_full = s_empty + 1;             // [2][2]  64-column half of H[b] written by the SiLU threads
@@ -123,17 +137,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint64_t* y_ready = a_ready + 1;            // [1]  projection tail: y of the last module written into sH (256 arrivals)
   uint64_t* q_full = y_ready + 1;             // [2]  projection accumulator complete (MMA commit)
   uint64_t* q_empty = q_full + 2;             // [2]  projection accumulator read out (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 2);
+  uint64_t* pair_done = q_empty + 2;          // [1]  PAIR: both CTAs' final epilogues finished (leader's instance)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pair_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
   // zero-fills their loads and clips their stores) so that the shared weight ring stays in lock-step
-  const int m_tiles = ((p.M + BM - 1) / BM + CL - 1) / CL * CL;
+  // (PAIR: m_tiles counts 256-row pair tiles; the peer of the last pair may lie completely past M)
+  const int m_tiles = PAIR ? ((p.M + BM - 1) / BM + 1) / 2 : ((p.M + BM - 1) / BM + CL - 1) / CL * CL;
   const int NC = p.F / HC;
   const int NP = NC / 2;                     // pairs of hidden chunks (F % 256 == 0)
   const int n_jobs = 3 * NP;
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const uint32_t crank = (CL > 1 || PAIR) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (1u << CL) - 1u;
+  const bool leader = !PAIR || crank == 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  const int m_off = PAIR ? (int)crank * BM : 0;
+  // arrivals on the barriers the MMA issuer waits on: per thread (single CTA) or one remote arrive per warp on the
+  // leader's instance (pair)
+  constexpr uint32_t kArrSilu = PAIR ? 2 * (kSiluThreads / 32) : kSiluThreads;
+  constexpr uint32_t kArr256 = PAIR ? 2 * 8 : 256;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
@@ -142,39 +167,67 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     if (p.np_blocks > 0) { prefetch_tmap(&tmWp); prefetch_tmap(&tmP); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
+    for (int s = 0; s < kNst; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, CL); }
     mbar_init(a_full, 1);
-    mbar_init(s_full, 1); mbar_init(s_empty, kSiluThreads);
+    mbar_init(s_full, 1); mbar_init(s_empty, kArrSilu);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(h_full + 2 * s, kSiluThreads); mbar_init(h_full + 2 * s + 1, kSiluThreads); mbar_init(h_empty + s, 1);
+      mbar_init(h_full + 2 * s, kArrSilu); mbar_init(h_full + 2 * s + 1, kArrSilu); mbar_init(h_empty + s, 1);
     }
     mbar_init(y_full, 1);
     mbar_init(tile_done, 256);
     for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
-    mbar_init(a_ready, 256); mbar_init(y_ready, 256);
-    for (int s = 0; s < 2; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 256); }
+    mbar_init(a_ready, kArr256); mbar_init(y_ready, kArr256);
+    for (int s = 0; s < 2; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, kArr256); }
+    mbar_init(pair_done, kArr256);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_2sm<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
+  if constexpr (CL > 1 || PAIR) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
+  // shared::cluster address of the LEADER's copy of a barrier = local shared::cta address + ldr_off
+  [[maybe_unused]] const uint32_t ldr_off = PAIR ? mapa_u32(smem_u32(bars), 0) - smem_u32(bars) : 0u;
+  // arrive on a barrier the MMA issuer waits on
+  auto arrive_mma = [&](uint64_t* bar) {
+    if constexpr (PAIR) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(bar) + ldr_off);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  // the MMA issuer's waits / probes on those barriers (cluster-scope acquire when the peer CTA arrives on them)
+  auto wait_mma = [&](uint64_t* bar, uint32_t parity) {
+    if constexpr (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+  };
+  auto test_mma = [&](uint64_t* bar, uint32_t parity) {
+    if constexpr (PAIR) return mbar_test_cluster(bar, parity); else return mbar_test(bar, parity);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0, phase = 0, it = 0;
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
-      const int m0 = t * BM;
+    for (int t = tile0; t < m_tiles; t += tstep, ++it) {   // gridDim.x is a multiple of CL
+      const int m0 = t * TM + m_off;
       if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // sA / sH / ring of the previous tile are dead
       if (elect_one()) {
+        if constexpr (PAIR) {
+          if (leader) mbar_expect_tx(a_full, 2 * kABytes);
+#pragma unroll
+          for (int ka = 0; ka < D / 64; ++ka) tma_load_2d_2sm(sA + ka * kAtom, &tmA, smem_u32(a_full) + ldr_off, ka * 64, m0);
+        } else {
         mbar_expect_tx(a_full, kABytes);
 #pragma unroll
         for (int ka = 0; ka < D / 64; ++ka) tma_load_2d(sA + ka * kAtom, &tmA, a_full, ka * 64, m0);
+        }
       }
       __syncwarp();
       for (int sg = 0; sg < p.n_stages; ++sg) {
@@ -185,13 +238,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         for (int pc = 0; pc < n_pc; ++pc) {
           mbar_wait(w_empty + stage, phase ^ 1);      // CL == 2: both CTAs have released this slot
           if (elect_one()) {
-            uint8_t* dst = sW + stage * kPiece;
-            mbar_expect_tx(w_full + stage, kPiece);
+            uint8_t* dst = sW + stage * kSlot;
+            if (!PAIR || leader) mbar_expect_tx(w_full + stage, kPiece);
             // G1: W1 rows [256 c, +256) x k [64 pc, +64);  G2: W2 rows [0,256) x hidden k [128 c + 64 pc, +64)
             const CUtensorMap* tm = g1 ? (sg ? &tmW1b : &tmW1) : (sg ? &tmW2b : &tmW2);
             const int col = g1 ? pc * 64 : c * HC + pc * 64;
             const int row = g1 ? c * 256 : 0;
-            if constexpr (CL == 1) {
+            if constexpr (PAIR) {      // this CTA's 128 of the piece's 256 rows; bytes credited to the leader's barrier
+              tma_load_2d_2sm(dst, tm, smem_u32(w_full + stage) + ldr_off, col, row + (int)crank * 128);
+            } else if constexpr (CL == 1) {
               tma_load_2d(dst, tm, w_full + stage, col, row);
               tma_load_2d(dst + kAtom, tm, w_full + stage, col, row + 128);
             } else {           // each CTA fetches 256 / CL of the 256 rows and multicasts them to the whole cluster
@@ -199,7 +254,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
             }
           }
           __syncwarp();
-          if (++stage == NST) { stage = 0; phase ^= 1; }
+          if (++stage == kNst) { stage = 0; phase ^= 1; }
         }
       }
       }
@@ -207,10 +262,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       for (int pc = 0; pc < 4 * p.np_blocks; ++pc) {
         mbar_wait(w_empty + stage, phase ^ 1);
         if (elect_one()) {
-          uint8_t* dst = sW + stage * kPiece;
-          mbar_expect_tx(w_full + stage, kPiece);
+          uint8_t* dst = sW + stage * kSlot;
+          if (!PAIR || leader) mbar_expect_tx(w_full + stage, kPiece);
           const int col = (pc & 3) * 64, row = (pc >> 2) * 256;
-          if constexpr (CL == 1) {
+          if constexpr (PAIR) {
+            tma_load_2d_2sm(dst, &tmWp, smem_u32(w_full + stage) + ldr_off, col, row + (int)crank * 128);
+          } else if constexpr (CL == 1) {
             tma_load_2d(dst, &tmWp, w_full + stage, col, row);
             tma_load_2d(dst + kAtom, &tmWp, w_full + stage, col, row + 128);
           } else {
@@ -218,40 +275,55 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           }
         }
         __syncwarp();
-        if (++stage == NST) { stage = 0; phase ^= 1; }
+        if (++stage == kNst) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, 256);    // G1: 256 hidden units of a chunk pair, G2: 256 outputs
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues; pair: leader CTA only) ==========
+    constexpr uint32_t idesc = umma_idesc_bf16(TM, 256);    // G1: 256 hidden units of a chunk pair, G2: 256 outputs
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+      if constexpr (PAIR) umma_bf16_2sm(d, da, db, idesc, acc); else umma_bf16(d, da, db, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {           // barrier other warps wait on: both CTAs' instances in pair mode
+      if constexpr (PAIR) umma_commit_2sm(bar, 0x3); else umma_commit(bar);
+    };
+    auto commit_slot = [&](uint64_t* bar) {
+      if constexpr (PAIR) umma_commit_2sm(bar, 0x3);
+      else if constexpr (CL == 1) umma_commit(bar);
+      else umma_commit_mc(bar, kMask);
+    };
     int stage = 0, phase = 0, it = 0;
     bool have = false;   // w_full of the current slot already seen complete by the probe issued before the previous MMAs
     uint32_t n_se = 0, n_hf0 = 0, n_hf1 = 0;
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
-      if (it > 0) mbar_wait(tile_done, (it - 1) & 1);     // Y accumulator drained by the previous epilogue
+    for (int t = tile0; t < m_tiles; t += tstep, ++it) {   // gridDim.x is a multiple of CL
+      if (it > 0) {                                        // Y accumulator(s) drained by the previous epilogue(s)
+        if constexpr (PAIR) mbar_wait_cluster(pair_done, (it - 1) & 1); else mbar_wait(tile_done, (it - 1) & 1);
+      }
       const uint32_t a_addr = smem_u32(sA), h_addr = smem_u32(sH);
       bool job_ready = false;           // the next job's S/H barrier was already seen complete
       auto next_slot_probe = [&]() {
-        const int ns = (stage + 1 == NST) ? 0 : stage + 1;
-        have = mbar_test(w_full + ns, (stage + 1 == NST) ? (phase ^ 1) : phase);
+        const int ns = (stage + 1 == kNst) ? 0 : stage + 1;
+        have = mbar_test(w_full + ns, (stage + 1 == kNst) ? (phase ^ 1) : phase);
       };
-      auto advance = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
+      auto advance = [&]() { if (++stage == kNst) { stage = 0; phase ^= 1; } };
       for (int sg = 0; sg < p.n_stages; ++sg) {
       // input tile: from TMA (first module) or written by the first module's epilogue, which also left X / alpha in Y
-      if (sg == 0) mbar_wait(a_full, it & 1); else mbar_wait(a_ready, it & 1);
+      if (p.trace && blockIdx.x == 0 && lane == 0 && sg == 0) p.trace[10 * 64 + 0] = clock64();
+      if (sg == 0) mbar_wait(a_full, it & 1); else wait_mma(a_ready, it & 1);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[10 * 64 + 1 + sg] = clock64();
       const uint32_t y_acc0 = sg;                         // chained module: accumulate onto the parked residual
       // The issuing warp runs in lock-step with the tensor pipe (it accepts only a few MMAs ahead), so every cycle
       // between two issue blocks is an idle pipe cycle.  The job sequence is therefore written out without any per-job
       // decoding, and the barrier of the NEXT issue block (ring slot or S/H hand-over) is probed non-blockingly
       // before the current block's MMAs are issued.
       // probe used while issuing the last piece of a job: is the barrier of the following job complete?
-      auto probe_g1 = [&]() { return mbar_test(s_empty, (n_se & 1) ^ 1); };
-      auto probe_g2 = [&](int c) { const int b = c & 1; return mbar_test(h_full + 2 * b, (b ? n_hf1 : n_hf0) & 1); };
+      auto probe_g1 = [&]() { return test_mma(s_empty, (n_se & 1) ^ 1); };
+      auto probe_g2 = [&](int c) { const int b = c & 1; return test_mma(h_full + 2 * b, (b ? n_hf1 : n_hf0) & 1); };
 
       auto do_g1 = [&](int pr, int next_kind, int next_c) {    // next_kind: 1 = G1, 2 = G2, 0 = none
         if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[0 * 64 + pr] = clock64();
-        if (!job_ready) mbar_wait(s_empty, (n_se & 1) ^ 1);         // SiLU stage has read S of the previous pair
+        if (!job_ready) wait_mma(s_empty, (n_se & 1) ^ 1);         // SiLU stage has read S of the previous pair
         if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[1 * 64 + pr] = clock64();
         ++n_se;
         tc_fence_after();
@@ -263,11 +335,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (pc == 3) job_ready = (next_kind == 1) ? probe_g1() : (next_kind == 2 ? probe_g2(next_c) : false);
           if (elect_one()) {
             const uint64_t da = umma_desc_sw128(a_addr + pc * kAtom);
-            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kSlot));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (pc | k) != 0);
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-            if (pc == 3) umma_commit(s_full);
+            for (int k = 0; k < 4; ++k) mma(tmem_base, da + 2 * k, db + 2 * k, (pc | k) != 0);
+            commit_slot(w_empty + stage);
+            if (pc == 3) commit(s_full);
           }
           __syncwarp();
           advance();
@@ -277,14 +349,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
         const int b = c & 1;
         uint32_t& n_hf = b ? n_hf1 : n_hf0;
         if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[6 * 64 + c] = clock64();
-        if (!job_ready) mbar_wait(h_full + 2 * b, n_hf & 1);         // first half of H[b] written (and fenced)
+        if (!job_ready) wait_mma(h_full + 2 * b, n_hf & 1);         // first half of H[b] written (and fenced)
         if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[7 * 64 + c] = clock64();
         tc_fence_after();
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {                             // pc = 64-wide k atom of the hidden chunk
           if (pc == 1) {                                             // second half: lands while the first atom's MMAs run
             if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[8 * 64 + c] = clock64();
-            mbar_wait(h_full + 2 * b + 1, n_hf & 1);
+            wait_mma(h_full + 2 * b + 1, n_hf & 1);
             if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[9 * 64 + c] = clock64();
           }
           if (!have) mbar_wait(w_full + stage, phase);
@@ -293,13 +365,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           if (pc == 1) job_ready = (next_kind == 1) ? probe_g1() : (next_kind == 2 ? probe_g2(next_c) : false);
           if (elect_one()) {
             const uint64_t da = umma_desc_sw128(h_addr + b * kHBytes + pc * kAtom);
-            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+            const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kSlot));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_y, da + 2 * k, db + 2 * k, idesc, (y_acc0 | c | pc | k) != 0);
-            if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
+            for (int k = 0; k < 4; ++k) mma(tmem_y, da + 2 * k, db + 2 * k, (y_acc0 | c | pc | k) != 0);
+            commit_slot(w_empty + stage);
             if (pc == 1) {
-              umma_commit(h_empty + b);
-              if (last) umma_commit(y_full);
+              commit(h_empty + b);
+              if (last) commit(y_full);
             }
           }
           __syncwarp();
@@ -316,26 +388,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       }
       do_g2(NC - 2, 2, NC - 1, false);
       do_g2(NC - 1, 0, 0, true);
+      if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[10 * 64 + 3 + sg] = clock64();
       }
       // projection tail: P_blk = y . Wp_blk^T, accumulators alternate between the S and the Y columns
       if (p.np_blocks > 0) {
-        mbar_wait(y_ready, it & 1);                       // y of the last module is in sH, the Y columns are dead
+        wait_mma(y_ready, it & 1);                       // y of the last module is in sH, the Y columns are dead
         tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[10 * 64 + 5] = clock64();
         for (int blk = 0; blk < p.np_blocks; ++blk) {
           const int ab = blk & 1;
           // accumulator `ab` is used by blocks ab, ab+2, ...: wait until the epilogue has read out block blk-2
-          if (blk >= 2) { mbar_wait(q_empty + ab, (it * ((p.np_blocks + 1 - ab) >> 1) + (blk >> 1) - 1) & 1); tc_fence_after(); }
+          if (blk >= 2) { wait_mma(q_empty + ab, (it * ((p.np_blocks + 1 - ab) >> 1) + (blk >> 1) - 1) & 1); tc_fence_after(); }
           for (int kc = 0; kc < 4; ++kc) {
             if (!have) mbar_wait(w_full + stage, phase);
             tc_fence_after();
             next_slot_probe();
             if (elect_one()) {
               const uint64_t da = umma_desc_sw128(h_addr + kc * kAtom);
-              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kPiece));
+              const uint64_t db = umma_desc_sw128(smem_u32(sW + stage * kSlot));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(ab ? tmem_y : tmem_base, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
-              if constexpr (CL == 1) umma_commit(w_empty + stage); else umma_commit_mc(w_empty + stage, kMask);
-              if (kc == 3) umma_commit(q_full + ab);
+              for (int k = 0; k < 4; ++k) mma(ab ? tmem_y : tmem_base, da + 2 * k, db + 2 * k, (kc | k) != 0);
+              commit_slot(w_empty + stage);
+              if (kc == 3) commit(q_full + ab);
             }
             __syncwarp();
             advance();
@@ -355,8 +429,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
     uint32_t ring_phase = 0;
     uint32_t n_sf = 0, n_he0 = 0, n_he1 = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {   // gridDim.x is a multiple of CL
-      const int m0 = t * BM;
+    for (int t = tile0; t < m_tiles; t += tstep, ++it) {   // gridDim.x is a multiple of CL
+      const int m0 = t * TM + m_off;
       if (it > 0 && grp >= 2) mbar_wait(tile_done, (it - 1) & 1);   // H buffers double as group 0's staging ring
       for (int sg = 0; sg < p.n_stages; ++sg) {
       const FfnStage& fs = p.st[sg];
@@ -392,7 +466,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           for (int half = 0; half < 2; ++half) tmem_ld(tmem_base + lane_base + b * HC + half * 64 + grp * kHalfCols, v[b][half]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(s_empty);
+        arrive_mma(s_empty);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           uint32_t& n_he = b ? n_he1 : n_he0;
@@ -416,7 +490,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
 #pragma unroll
             for (int j = 0; j < kHalfCols / 8; ++j) *reinterpret_cast<uint4*>(hb + sw_off(r, grp * (kHalfCols / 8) + j)) = pk[j];
             fence_proxy_async_smem();
-            mbar_arrive(h_full + 2 * b + half);
+            arrive_mma(h_full + 2 * b + half);
           }
           if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[4 * 64 + 2 * pr + b] = clock64();
         }
@@ -425,6 +499,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
       if (grp < 2) {
         mbar_wait(y_full, (it * p.n_stages + sg) & 1);
         tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[10 * 64 + 8 + sg] = clock64();
         const bool last = sg + 1 == p.n_stages;
         ResidOpts ro;
         ro.no_residual = sg > 0;                 // a chained module found X / alpha in its accumulator
@@ -435,15 +510,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
           if (elected && sg == 0) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
           if (p.np_blocks > 0) ro.y_smem = sH;             // y is only consumed by the projection tail: not stored
+          if (p.trace && blockIdx.x == 0) ro.trace = p.trace + 11 * 64 + 16;
           ResidParams rp{nullptr, p.y_row_valid, fs.alpha, p.eps, fs.ln_mode, p.M};
           resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
                                           sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
                                           reinterpret_cast<float2*>(sA + 8192), -1, -1, ro);
+          if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[10 * 64 + 10 + sg] = clock64();
           if (p.np_blocks > 0) {
             // ---- projection tail (the QKV projection of the attention block that follows): y sits in sH as the A
             //      operand; each warpgroup turns 128 of a block's 256 accumulator columns into bf16 (+ bias) and
             //      stores them through two staging tiles in the dead input tile
-            mbar_arrive(y_ready);
+            arrive_mma(y_ready);
             int sub_cnt = 0;
             for (int blk = 0; blk < p.np_blocks; ++blk) {
               const int ab = blk & 1;
@@ -481,13 +558,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
                 if (elected) { tma_store_2d(&tmP, buf, blk * 256 + sub * 64, m0); bulk_commit(); }
               }
               tc_fence_before();
-              mbar_arrive(q_empty + ab);
+              arrive_mma(q_empty + ab);
             }
             if (elected) bulk_wait_read<0>();                  // the staging tiles are free before the next tile's input lands
             named_bar_sync(bar_id, 128);
+            if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[10 * 64 + 12] = clock64();
           }
           mbar_arrive(tile_done);
-          if (t + (int)gridDim.x < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
+          if constexpr (PAIR) arrive_mma(pair_done);
+          if (t + tstep < m_tiles) mbar_wait(tile_done, it & 1);   // sA / sH are re-used by the next tile
         } else {
           // first module of a chain: X and y stay on chip.  y goes straight into the input tile sA (A operand of the
           // next module), X / alpha_next stays in the accumulator columns, nothing is stored.  The residual rows arrive
@@ -499,12 +578,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           ro.store_x = false;
           ro.y_smem = sA;
           ro.park_scale = 1.0f / p.st[sg + 1].alpha;
+          if (p.trace && blockIdx.x == 0) ro.trace = p.trace + 11 * 64;
           ResidParams rp{nullptr, nullptr, fs.alpha, p.eps, fs.ln_mode, p.M};
           resid_ln_epilogue<D, 2, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
                                           cparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
                                           reinterpret_cast<float2*>(sH + 8192), -1, -1, ro);
           // (the epilogue ends with a 256-thread barrier: both groups are done with the ring and the parameters)
-          mbar_arrive(a_ready);                  // y in sA (fenced), X / alpha parked in Y (tcgen05.wait::st done)
+          if (p.trace && blockIdx.x == 0 && et == 0 && grp == 0) p.trace[10 * 64 + 10 + sg] = clock64();
+          arrive_mma(a_ready);                  // y in sA (fenced), X / alpha parked in Y (tcgen05.wait::st done)
         }
       }
       }
@@ -514,8 +595,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();   // nobody exits while a peer may still multicast into it / signal it
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if constexpr (CL > 1 || PAIR) cluster_sync_all();   // nobody exits while a peer may still multicast into it / signal it
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 int make_2d_map(CUtensorMap* tm, bool f32, const void* base, int rows, int cols, int ld, int box_rows = 128) {
@@ -540,10 +624,16 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
                       const void* Wp = nullptr, const float* bp = nullptr, void* P = nullptr, int Np = 0) {
   // cluster size along M: the CTAs of a cluster share every weight piece through TMA multicast (CFM_B200_FFN_CLUSTER)
   static const int cl_env = env_is("CFM_B200_FFN_CLUSTER", "1") ? 1 : (env_is("CFM_B200_FFN_CLUSTER", "4") ? 4 : 2);
-  CFM_SMEM_OPT_IN(ffn_fused_kernel<1>, kSmemBytes);
-  CFM_SMEM_OPT_IN(ffn_fused_kernel<2>, kSmemBytes);
-  CFM_SMEM_OPT_IN(ffn_fused_kernel<4>, kSmemBytes);
-  const int CL = cl_env;
+  // CTA pairs (cta_group::2) by default: the main loop runs at 4.17 k cycles per chunk pair (4.10 k = tensor-pipe bound)
+  // instead of 4.66 k, the chained tile takes 101.5 k instead of 109.3 k cycles warm (tools/ffn_chain_trace.py);
+  // CFM_B200_FFN_PAIR=0 selects the single-CTA kernel (+ CFM_B200_FFN_CLUSTER multicast variants)
+  static const bool pair_off = env_is("CFM_B200_FFN_PAIR", "0");
+  const bool pair = !pair_off && M > BM;
+  CFM_SMEM_OPT_IN((ffn_fused_kernel<1, false>), kSmemBytes);
+  CFM_SMEM_OPT_IN((ffn_fused_kernel<2, false>), kSmemBytes);
+  CFM_SMEM_OPT_IN((ffn_fused_kernel<4, false>), kSmemBytes);
+  CFM_SMEM_OPT_IN((ffn_fused_kernel<1, true>), kSmemBytes);
+  const int CL = pair ? 1 : cl_env;
   const int wbox = CL == 4 ? 64 : 128;         // rows of a weight piece one CTA fetches per TMA
   CUtensorMap tmA, tmW1[2], tmW2[2], tmX, tmY;
   int rc;
@@ -573,14 +663,20 @@ static int ffn_launch(const void* y_in, int ld_in, const FfnModule* mods, int n,
   const int m_tiles = ((M + BM - 1) / BM + CL - 1) / CL * CL;
   const int max_ctas = num_sms() / CL * CL;
   const int grid = m_tiles < max_ctas ? m_tiles : max_ctas;
-  if (CL == 1)
-    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1[0], tmW2[0], tmW1[1],
+  if (pair) {
+    const int pair_tiles = ((M + BM - 1) / BM + 1) / 2, slots = num_sms() / 2;
+    const int pgrid = 2 * (pair_tiles < slots ? pair_tiles : slots);
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1, true>, dim3(pgrid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0],
+                           tmW1[1], tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
+    count_variant("ffn_fused_pair");
+  } else if (CL == 1)
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<1, false>, dim3(grid), dim3(kThreads), kSmemBytes, st, 1, tmA, tmW1[0], tmW2[0], tmW1[1],
                            tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   else if (CL == 4)
-    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<4>, dim3(grid), dim3(kThreads), kSmemBytes, st, 4, tmA, tmW1[0], tmW2[0], tmW1[1],
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<4, false>, dim3(grid), dim3(kThreads), kSmemBytes, st, 4, tmA, tmW1[0], tmW2[0], tmW1[1],
                            tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   else
-    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],
+    CFM_CUDA_OK(launch_pdl(ffn_fused_kernel<2, false>, dim3(grid), dim3(kThreads), kSmemBytes, st, 2, tmA, tmW1[0], tmW2[0], tmW1[1],
                            tmW2[1], tmX, tmX, tmY, tmWp, tmP, p));
   CFM_LAUNCHED_K("ffn_fused");
   return 0;

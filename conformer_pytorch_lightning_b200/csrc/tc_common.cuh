@@ -54,18 +54,30 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// acquire at cluster scope: for barriers that threads of the PEER CTA arrive on (release.cluster)
+// barriers that threads of the PEER CTA arrive on (see mbar_arrive_cluster for the memory-ordering argument)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (ok == 0);
+}
+
+__device__ __forceinline__ bool mbar_test_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 
 // One lane of a CONVERGED warp (returns true in exactly one lane).  tcgen05.mma / TMA operands live in uniform
@@ -137,7 +149,11 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), like CUTLASS' ClusterBarrier::arrive(cta_id): the data the waiter goes on
+  // to use is read by the async proxy of the ARRIVING CTA's own SM (tcgen05.mma cta_group::2 operands, TMEM) and was
+  // fenced there; a .release.cluster arrive costs a MEMBAR.ALL + ERRBAR + L1 invalidate per call (measured: ~1.5 k
+  // cycles, which made the first pair kernels slower than the single-CTA ones)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t accumulate) {
