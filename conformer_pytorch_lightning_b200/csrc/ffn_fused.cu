@@ -141,6 +141,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pair_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-CTA wall-clock stamps (globaltimer, ns) when tracing: [16*64 + 4*cta + {0: entry, 1: prologue done, 2: all warps done}]
+  auto gstamp = [&](int slot) {
+    if (p.trace && threadIdx.x == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      p.trace[16 * 64 + 4 * blockIdx.x + slot] = (long long)tns;
+    }
+  };
+  gstamp(0);
   // every CTA of a cluster runs the same number of tiles (phantom tiles past M are fully out of bounds: TMA
   // zero-fills their loads and clips their stores) so that the shared weight ring stays in lock-step
   // (PAIR: m_tiles counts 256-row pair tiles; the peer of the last pair may lie completely past M)
@@ -191,6 +200,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
   if constexpr (CL > 1 || PAIR) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   pdl_wait();
+  gstamp(1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
   // shared::cluster address of the LEADER's copy of a barrier = local shared::cta address + ldr_off
@@ -510,7 +520,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
           uint8_t* ring = grp == 0 ? sH : sA + kBufBytes;
           if (elected && sg == 0) resid_prefetch<D, 3, 128, 2>(ring, res_bar + grp * 4, &tmR, 0, m0, grp);
           if (p.np_blocks > 0) ro.y_smem = sH;             // y is only consumed by the projection tail: not stored
-          if (p.trace && blockIdx.x == 0) ro.trace = p.trace + 11 * 64 + 16;
+          if (p.trace && blockIdx.x == 0) ro.trace = p.trace + 11 * 64 + 32;
           ResidParams rp{nullptr, p.y_row_valid, fs.alpha, p.eps, fs.ln_mode, p.M};
           resid_ln_epilogue<D, 3, 128, 2>(tmem_y + lane_base, r, m0, 0, elected, bar_id, ring, res_bar + grp * 4, ring_phase,
                                           sparam, &tmX, &tmR, &tmY, rp, grp, 1 + kSiluGroups,
@@ -595,6 +605,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA,    // y  (M, 256) bf16
 
   tc_fence_before();
   __syncthreads();
+  gstamp(2);
   if constexpr (CL > 1 || PAIR) cluster_sync_all();   // nobody exits while a peer may still multicast into it / signal it
   if (warp == 2) {
     if constexpr (PAIR) tmem_dealloc_2sm<512>(tmem_base);

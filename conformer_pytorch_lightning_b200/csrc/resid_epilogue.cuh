@@ -115,27 +115,48 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
     uint32_t v[32];
     tmem_ld32(taddr + (ch0 + c) * 32, v);
     tmem_ld_wait();
-    const float* bs = sparam + (ch0 + c) * 32;
+    if (c == 1) RTR(13);
+    // all shared-memory reads of the chunk first (the residual cells and the bias as 16-byte loads), the arithmetic on
+    // registers, then the writes: a load -> use -> store chain per 16-byte cell serialises on the shared-memory latency
+    const float4* bs4 = reinterpret_cast<const float4*>(sparam + (ch0 + c) * 32);
+    float4 xr[8];
+    if (!o.no_residual) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xr[j] = *reinterpret_cast<const float4*>(buf + sw_off(r, j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ln 1: what stays parked is X itself (scaled for a chained module); ln 2: the pre-norm row, unscaled
+    const float ps = ln == 1 ? o.park_scale : 1.f;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;      // two independent accumulation chains
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4* cell = reinterpret_cast<float4*>(buf + sw_off(r, j));
-      float4 x = o.no_residual ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
-      x.x = fmaf(a, __uint_as_float(v[4 * j]) + bs[4 * j], x.x);
-      x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], x.y);
-      x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], x.z);
-      x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], x.w);
-      s1 += (x.x + x.y) + (x.z + x.w);
-      s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-      // ln 1: what stays parked is X itself (scaled for a chained module); ln 2: the pre-norm row, unscaled
-      const float ps = ln == 1 ? o.park_scale : 1.f;
+      const float4 bq = bs4[j];
+      float4 x = xr[j];
+      x.x = fmaf(a, __uint_as_float(v[4 * j]) + bq.x, x.x);
+      x.y = fmaf(a, __uint_as_float(v[4 * j + 1]) + bq.y, x.y);
+      x.z = fmaf(a, __uint_as_float(v[4 * j + 2]) + bq.z, x.z);
+      x.w = fmaf(a, __uint_as_float(v[4 * j + 3]) + bq.w, x.w);
+      if (j & 1) { s1b += (x.x + x.y) + (x.z + x.w); s2b += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w); }
+      else { s1a += (x.x + x.y) + (x.z + x.w); s2a += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w); }
       v[4 * j] = __float_as_uint(x.x * ps); v[4 * j + 1] = __float_as_uint(x.y * ps);
       v[4 * j + 2] = __float_as_uint(x.z * ps); v[4 * j + 3] = __float_as_uint(x.w * ps);
-      if (ln != 2) *cell = x;                    // X chunk leaves through the same buffer
+      xr[j] = x;
     }
+    s1 += s1a + s1b;
+    s2 += s2a + s2b;
+    if (ln != 2 && o.store_x) {                  // X chunk leaves through the same buffer
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(buf + sw_off(r, j)) = xr[j];
+    }
+    if (c == 1) RTR(14);
     if (ln != 0) tmem_st32(taddr + (ch0 + c) * 32, v);   // park the row in our accumulator columns
+    if (c == 1) RTR(15);
     fence_proxy_async_smem();
     RTR(2 + 2 * c);
     named_bar_sync(bar_id, 128);
+    if (c == 1) RTR(16);
     if (elected) {
       if (ln != 2 && o.store_x) {
         resid_tma_store(tmX, buf, n0 + (ch0 + c) * 32, m0, z);
@@ -179,21 +200,25 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
         uint32_t v[32];
         tmem_ld32(taddr + (ch0 + c) * 32, v);
         tmem_ld_wait();
-        const float* g = sparam + BN + (ch0 + c) * 32;
-        const float* be = sparam + 2 * BN + (ch0 + c) * 32;
+        const float4* g4 = reinterpret_cast<const float4*>(sparam + BN + (ch0 + c) * 32);
+        const float4* be4 = reinterpret_cast<const float4*>(sparam + 2 * BN + (ch0 + c) * 32);
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          const float4 gq = g4[j], bq = be4[j];
           float4 x;
-          x.x = fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g[4 * j], be[4 * j]);
-          x.y = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g[4 * j + 1], be[4 * j + 1]);
-          x.z = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g[4 * j + 2], be[4 * j + 2]);
-          x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g[4 * j + 3], be[4 * j + 3]);
-          s1 += (x.x + x.y) + (x.z + x.w);
-          s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          x.x = fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, gq.x, bq.x);
+          x.y = fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, gq.y, bq.y);
+          x.z = fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, gq.z, bq.z);
+          x.w = fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, gq.w, bq.w);
+          if (j & 1) { s1b += (x.x + x.y) + (x.z + x.w); s2b += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w); }
+          else { s1a += (x.x + x.y) + (x.z + x.w); s2a += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w); }
           v[4 * j] = __float_as_uint(x.x * o.park_scale); v[4 * j + 1] = __float_as_uint(x.y * o.park_scale);
           v[4 * j + 2] = __float_as_uint(x.z * o.park_scale); v[4 * j + 3] = __float_as_uint(x.w * o.park_scale);
           if (o.store_x) *reinterpret_cast<float4*>(buf + sw_off(r, j)) = x;
         }
+        s1 += s1a + s1b;
+        s2 += s2a + s2b;
         tmem_st32(taddr + (ch0 + c) * 32, v);
         if (o.store_x) {
           fence_proxy_async_smem();
@@ -230,13 +255,17 @@ __device__ __forceinline__ void resid_ln_epilogue(uint32_t taddr, int r, int m0,
         tmem_ld32(taddr + sub * 64 + 32, v1);
       }
       tmem_ld_wait();
+      const float4* g4 = reinterpret_cast<const float4*>(g + sub * 64);
+      const float4* be4 = reinterpret_cast<const float4*>(be + sub * 64);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const float4 ga = g4[2 * j], gb = g4[2 * j + 1], ba = be4[2 * j], bb = be4[2 * j + 1];
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bbv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int col = sub * 64 + 8 * j + e;
-          const float y = fmaf((__uint_as_float(v[8 * j + e]) * unpark - mean) * rstd, g[col], be[col]);
+          const float y = fmaf((__uint_as_float(v[8 * j + e]) * unpark - mean) * rstd, gg[e], bbv[e]);
           f[e] = ykeep ? y : 0.f;
         }
         *reinterpret_cast<uint4*>(buf + sw_off(r, j)) =

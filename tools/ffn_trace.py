@@ -3,7 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-trace = torch.zeros(12 * 64, dtype=torch.int64, device="cuda")
+trace = torch.zeros(16 * 64 + 4 * 160, dtype=torch.int64, device="cuda")
 os.environ["CFM_B200_FFN_TRACE_PTR"] = str(trace.data_ptr())
 from conformer_pytorch_lightning_b200 import _native as N, ops
 M, d, F = 15872, 256, 2048
@@ -14,7 +14,7 @@ x = torch.randn(M, d, device="cuda")
 for _ in range(3):
     ops.ffn(y, w1, b1, w2, b2, x, alpha=0.5, engine=N.ENGINE_TC)
 torch.cuda.synchronize()
-t = trace.cpu().view(12, 64)
+t = trace.cpu()[:12 * 64].view(12, 64)
 t0 = int(t[0, 0])
 NC = F // 128
 print("chunk | MMA warp: G1 start, after s_empty wait | G2 start, after h_full[0] wait, before/after h_full[1] wait |"
