@@ -119,7 +119,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rtfx(workload, sample_b, repeats):
+def cpu_port_rtfx(workload, sample_b, repeats, min_seconds=0.0):
     """The CPU port of the reference's algorithm (oracle/conformer_oracle_torch.py: the same ATen CPU
     kernels the reference's modules run, all host threads), measured path only, fp32."""
     import torch
@@ -142,7 +142,7 @@ def cpu_port_rtfx(workload, sample_b, repeats):
     sdc = OT.to_torch_sd(sd)
     best = float("inf")
     times = []
-    for _ in range(repeats):
+    while len(times) < repeats or (sum(times) < min_seconds and len(times) < 40):
         t0 = time.perf_counter()
         OT.encoder_layers(x, attn, pos, pad, sdc, cfg)
         dt = time.perf_counter() - t0
@@ -501,9 +501,11 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, best, sb, _ = cpu_port_rtfx(args.workload, args.cpu_sample, 3)
+            # bounded sample: whole batches of the same workload, repeated until ~12 s of CPU work have been timed
+            v, best, sb, tms = cpu_port_rtfx(args.workload, args.cpu_sample, 3, min_seconds=12.0)
             cpu = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"ATen-CPU port (oracle/conformer_oracle_torch.py), measured path on {sb} of {B} utterances, best of 3 ({best:.2f} s)"}
+                   "sample": f"ATen-CPU port (oracle/conformer_oracle_torch.py), measured path on {sb} of {B} utterances per pass, "
+                             f"{len(tms)} passes = {sum(tms):.1f} s of CPU work, best pass {best:.2f} s (mean {sum(tms) / len(tms):.2f} s)"}
         algo_tf = {"C2": 1.024, "C3": 3.552, "C4": 1.914}.get(args.workload)      # SURVEY 8d totals (TFLOP per pass)
         line = {"metric": "encoder audio-sec/sec (RTFx), measured path", "value": value, "unit": "audio-s/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -834,7 +836,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS) + ["C5"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per CPU-baseline pass (capped at the batch)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU bar")
     ap.add_argument("--profile", action="store_true", help="measured path only (for ncu): no e2e / probe / cpu legs")
