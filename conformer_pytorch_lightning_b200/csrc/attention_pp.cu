@@ -23,10 +23,18 @@ namespace {
 using namespace tc;
 
 constexpr int QT = 128, KT = 128, DK = 64, NQ = 2;
-constexpr int kThreads = 352;
+// SPLIT = threads per query row in the softmax groups.  1: 4 warps per group (one per scheduler); 2: 8 warps per group,
+// thread = (row, key half / output-column half): four softmax warps per scheduler instead of two hide the shared-memory,
+// TMEM and MUFU latencies of the passes (a single warp's ex2 pass is latency bound: 2.0 k cycles alone vs a 1.0 k MUFU
+// bound), the halves exchange their row maxima through shared memory once per tile.
+template <int SPLIT> struct PPCfg {
+  static constexpr int kSoftWarps = 8 * SPLIT;
+  static constexpr int kTmaWarp = kSoftWarps, kMmaWarp = kSoftWarps + 1, kAllocWarp = kSoftWarps + 2;
+  static constexpr int kThreads = (kSoftWarps + 3) * 32;
+};
 constexpr int kTile = 128 * DK * 2;            // 16 KB: one Q, K or V tile
 constexpr int kPBytes = QT * KT * 2;           // 32 KB per query tile
-constexpr int kSmemBytes = NQ * kTile + 2 * 2 * kTile + NQ * kPBytes + 1024;
+constexpr int kSmemBytes = NQ * kTile + 2 * 2 * kTile + NQ * kPBytes + 1024 + 4096;   // + row-maximum / row-sum exchange (SPLIT = 2)
 constexpr int kTmemCols = 512;                 // 2 x 128 (S) + 2 x 64 (O) = 384 -> next power of two
 
 struct AttnPPParams {
@@ -65,7 +73,11 @@ __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* p, bool aligned8)
   return bits;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// PTMEM (with SPLIT = 2): P is written into tensor memory (tcgen05.st, 64 columns per query tile: TMEM holds S 2 x 128,
+// O 2 x 64, P 2 x 64 = 512 columns) and P V takes its A operand from there: no shared-memory P tile, no
+// fence.proxy.async after the stores (measured ~500 cycles per tile on the thread that issues it).
+template <int SPLIT, bool PTMEM>
+__global__ void __launch_bounds__(PPCfg<SPLIT>::kThreads, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -79,8 +91,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* s_full = bars + 5;                          // [2] per query tile
   uint64_t* p_ready = bars + 7;                         // [2] 128 arrivals
   uint64_t* o_full = bars + 9;                          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* s_free = bars + 11;                         // [2] SPLIT = 2: S_q read out of TMEM (before P_q is complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   uint32_t* svis = tmem_slot + 1;                       // [2 groups][2 parities][4] visibility words of a (B,1,Tk) mask
+  float* sxch = reinterpret_cast<float*>(sP + NQ * kPBytes + 1024);   // [2 groups][2 parities][2 halves][128] (SPLIT = 2)
+  using PC = PPCfg<SPLIT>;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * (NQ * QT);
@@ -89,16 +104,17 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define PTR(slot) do { if (tr && lane == 0) p.trace[(slot)] = clock64(); } while (0)
 
-  if (warp == 8 && lane == 0) {
+  if (warp == PC::kTmaWarp && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1);
-      mbar_init(s_full + s, 1); mbar_init(p_ready + s, 128); mbar_init(o_full + s, 1);
+      mbar_init(s_full + s, 1); mbar_init(p_ready + s, 128 * SPLIT); mbar_init(o_full + s, 1);
+      mbar_init(s_free + s, 128 * SPLIT);
     }
     fence_barrier_init();
   }
-  if (warp == 10) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == PC::kAllocWarp) tmem_alloc<kTmemCols>(tmem_slot);
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
@@ -106,7 +122,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == PC::kTmaWarp) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(q_full, NQ * kTile);
@@ -125,7 +141,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
+  } else if (warp == PC::kMmaWarp) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DK, 1);           // B = V tile, MN-major (dk contiguous)
@@ -150,6 +166,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int s = j & 1;
 #pragma unroll 1
       for (int q = 0; q < NQ; ++q) {
+        if (SPLIT == 2 && j + 1 < n_kv) {
+          // the next score tile goes into the pipe as soon as group q has READ S_q(j) (it is still busy with the ex2 of
+          // its last chunk and the P stores): S_q(j+1) is complete when the group comes back for it
+          mbar_wait(s_free + q, j & 1);
+          if (q == 0) mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(q, j + 1);
+        }
         mbar_wait(p_ready + q, j & 1);          // P_q(j) in smem, S_q(j) read out, O_q(j-1) drained
         tc_fence_after();
         if (j < 6) PTR(16 + (j * 2 + q) * 2);
@@ -158,22 +182,208 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t pa = smem_u32(sP + q * kPBytes);
 #pragma unroll
           for (int k = 0; k < KT / 16; ++k) {
-            // A: P, K-major, two 64-key swizzle atoms (16 KB each); B: 16 keys per K step = 2048 bytes = +128 units
-            const uint64_t da = umma_desc_sw128(pa + (k >> 2) * (kPBytes / 2)) + 2 * (k & 3);
-            umma_bf16(tmem_base + NQ * KT + q * DK, da, dv + 128 * k, idesc_o, k != 0);
+            // B: 16 keys per K step = 2048 bytes = +128 units
+            if constexpr (PTMEM) {              // A: P in tensor memory, 8 columns (16 packed bf16) per K step
+              umma_bf16_ts(tmem_base + NQ * KT + q * DK, tmem_base + NQ * KT + NQ * DK + q * (KT / 2) + k * 8, dv + 128 * k,
+                           idesc_o, k != 0);
+            } else {                            // A: P in shared memory, K-major, two 64-key swizzle atoms (16 KB each)
+              const uint64_t da = umma_desc_sw128(pa + (k >> 2) * (kPBytes / 2)) + 2 * (k & 3);
+              umma_bf16(tmem_base + NQ * KT + q * DK, da, dv + 128 * k, idesc_o, k != 0);
+            }
           }
           umma_commit(o_full + q);
           if (q == NQ - 1) umma_commit(kv_empty + s);   // every MMA that reads stage s was issued before this commit
         }
         __syncwarp();
-        if (j + 1 < n_kv) {
+        if (SPLIT == 1 && j + 1 < n_kv) {
           if (q == 0) { mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1); tc_fence_after(); }
           issue_s(q, j + 1);                    // S_q is free: group q has read S_q(j) (p_ready above)
         }
         if (j < 6) PTR(16 + (j * 2 + q) * 2 + 1);
       }
     }
-  } else if (warp < 8) {
+  } else if (SPLIT == 2 && warp < PC::kSoftWarps) {
+    // ===================== softmax groups, thread = (query row, key half) =====================
+    const int g = warp >> 3;                    // group = query tile
+    const int wq = warp & 3;                    // TMEM lane quadrant (= warp % 4)
+    const int hf = (warp >> 2) & 1;             // key half of the score tile / column half of the output row
+    const int r = wq * 32 + lane;
+    const int i = i0 + g * QT + r;
+    const bool row_ok = i < p.Tq;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * KT + lane_base + hf * 64;
+    const uint32_t tmem_o = tmem_base + NQ * KT + g * DK + lane_base + hf * 32;
+    uint8_t* sPg = sP + g * kPBytes + hf * (kPBytes / 2);     // K atom `hf` of the P tile
+    const uint32_t tmem_p = tmem_base + NQ * KT + NQ * DK + g * (KT / 2) + lane_base + hf * 32;   // PTMEM: 32 packed columns
+    const uint8_t* mrow = (p.mask != nullptr && row_ok) ? p.mask + b * p.mask_bs + i * p.mask_rs : nullptr;
+    float* xch = sxch + g * 512;
+    uint32_t* sv = svis + g * 8;
+    float m_run = -CUDART_INF_F, l_run = 0.f;   // l_run: this thread's key half only (summed at the end)
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+    const bool bcast_mask = p.mask != nullptr && p.mask_rs == 0;
+    // (B,1,Tk) key-padding mask: the hf = 0 warps fetch one byte per thread and ballot it into 4 words per tile, one tile
+    // ahead; the words of tile j+1 are published by the row-maximum barrier of tile j
+    uint8_t mbyte = (bcast_mask && hf == 0 && r < p.Tk) ? __ldg(p.mask + b * p.mask_bs + r) : (uint8_t)0;
+    auto publish_vis = [&](int j) {             // visibility words of tile j -> sv[(j & 1) * 4 + ...], next byte prefetched
+      if (bcast_mask && hf == 0) {
+        const int jj = j * KT + r;
+        const bool on = (jj < p.Tk) && (mbyte != 0);
+        const int jn = jj + KT;
+        mbyte = (jn < p.Tk) ? __ldg(p.mask + b * p.mask_bs + jn) : (uint8_t)0;
+        const uint32_t w = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) sv[(j & 1) * 4 + wq] = w;
+      }
+    };
+    publish_vis(0);
+    named_bar_sync(1 + g, 256);
+    float alpha_prev = 1.f;
+#pragma unroll 1
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int j0 = j * KT + hf * 64;          // first key of this thread's half
+      uint32_t vis[2];
+      if (bcast_mask) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) vis[c] = row_ok ? sv[(j & 1) * 4 + 2 * hf + c] : 0u;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int jj = j0 + c * 32;
+          const int nvalid = p.Tk - jj;
+          uint32_t bits = !row_ok ? 0u : (nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u)));
+          if (mrow != nullptr && bits != 0u) {
+            if (nvalid >= 32) bits &= mask_bits32(mrow + jj, p.mask_aligned8 != 0);
+            else {
+              uint32_t mb = 0;
+              for (int c2 = 0; c2 < nvalid; ++c2) mb |= (__ldg(mrow + jj + c2) != 0 ? 1u : 0u) << c2;
+              bits &= mb;
+            }
+          }
+          vis[c] = bits;
+        }
+      }
+      if (j + 1 < n_kv) publish_vis(j + 1);
+      if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 0);
+      mbar_wait(s_full + g, ph);
+      tc_fence_after();
+      if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 1);
+      // ---- pass 1: masked maximum of this thread's 64 scores, halves exchanged through shared memory
+      float m_tile = -CUDART_INF_F;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + half * 32, v);
+        tmem_ld_wait();
+        const uint32_t vm = vis[half];
+        if (vm == 0xffffffffu) {
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+          for (int e = 4; e < 32; e += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[e])); m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[e + 2])); m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+          }
+          m_tile = fmaxf(m_tile, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else if (vm != 0u) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if ((vm >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+        }
+      }
+      xch[(j & 1) * 256 + hf * 128 + r] = m_tile;
+      named_bar_sync(1 + g, 256);               // (also publishes the visibility words of tile j+1)
+      m_tile = fmaxf(m_tile, xch[(j & 1) * 256 + (hf ^ 1) * 128 + r]) * p.scale_log2;
+      if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 2);
+      const float m_new = fmaxf(m_run, m_tile);
+      const bool any = m_new != -CUDART_INF_F;
+      const float alpha = any ? exp2f(m_run - m_new) : 1.f;
+      const float neg_m = any ? -m_new : 0.f;
+      // O_tile(j-1) -> registers with ITS rescale factor (this thread's 32 output columns)
+      if (j > 0) {
+        mbar_wait(o_full + g, (j - 1) & 1);
+        tc_fence_after();
+        if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 4);
+        uint32_t va[32];
+        tmem_ld32(tmem_o, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha_prev, __uint_as_float(va[e]));
+        if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 5);
+      }
+      // group 1 starts its first ex2 pass after group 0's (see the SPLIT = 1 path)
+      if (g == 1 && j == 0) asm volatile("bar.sync 3, 512;" ::: "memory");
+      // ---- pass 2: p = 2^(s * scale - m), bf16 P into K atom `hf`, partial row sum
+      float l_tile = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];                         // (one chunk at a time: 96 registers per thread at 608 threads)
+        tmem_ld32(tmem_s + c * 32, v);
+        tmem_ld_wait();
+        if (c == 1) { tc_fence_before(); mbar_arrive(s_free + g); }     // S_g(j) is out of TMEM: S_g(j+1) may overwrite it
+        if (vis[c] != 0xffffffffu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((vis[c] >> e) & 1u)) v[e] = 0xff800000u;  // -inf
+        }
+        uint32_t pk[16];
+        float la = 0.f, lb = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float p0 = ex2_fast(fmaf(__uint_as_float(v[e]), p.scale_log2, neg_m));
+          const float p1 = ex2_fast(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, neg_m));
+          const float p2 = ex2_fast(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, neg_m));
+          const float p3 = ex2_fast(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, neg_m));
+          la += p0 + p1;
+          lb += p2 + p3;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        l_tile += la + lb;
+        if constexpr (PTMEM) {
+          tmem_st16(tmem_p + c * 16, pk);
+        } else {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int cc = 4 * c + qq;            // 16-byte chunk inside this half's 128-byte row
+            uint8_t* dst = sPg + r * 128 + ((cc ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+          }
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      if constexpr (PTMEM) tmem_st_wait(); else fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready + g);
+      if (g == 0 && j == 0) asm volatile("bar.arrive 3, 512;" ::: "memory");
+      if (wq == 0 && hf == 0 && j < 6) PTR(48 + (g * 6 + j) * 6 + 3);
+      alpha_prev = alpha;
+    }
+    // the last tile's P V product, and the row sum of the other key half
+    float* lx = xch + (n_kv & 1) * 256;          // the parity slot the last tile's row-maximum exchange did NOT use
+    lx[hf * 128 + r] = l_run;
+    mbar_wait(o_full + g, (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+      uint32_t va[32];
+      tmem_ld32(tmem_o, va);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha_prev, __uint_as_float(va[e]));
+    }
+    tc_fence_before();
+    named_bar_sync(1 + g, 256);
+    l_run += lx[(hf ^ 1) * 128 + r];
+    if (row_ok) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.Tq + i) * p.H * DK + h * DK + hf * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        dst[c] = make_uint4(pack_bf16x2(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
+                            pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+    }
+  } else if (SPLIT == 1 && warp < 8) {
     // ===================== softmax groups: thread = query row =====================
     const int g = warp >> 2;                    // group = query tile
     const int wq = warp & 3;                    // TMEM lane quadrant
@@ -366,7 +576,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == PC::kAllocWarp) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 int make_tmap3(CUtensorMap* tm, const void* base, int B, int T, int H, int64_t bs, int64_t ts) {
@@ -398,8 +608,17 @@ int attention_pp(const void* q, int64_t q_bs, int64_t q_ts, const void* k, int64
   if (const char* e = getenv("CFM_B200_ATTN_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.mask_aligned8 = (mask != nullptr) && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_bs | (uintptr_t)mask_rs) % 8 == 0);
   dim3 grid((Tq + NQ * QT - 1) / (NQ * QT), H, B);
-  CFM_SMEM_OPT_IN(attention_pp_kernel, kSmemBytes);
-  CFM_CUDA_OK(launch_pdl(attention_pp_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
+  static const bool split1 = env_is("CFM_B200_ATTN_PP_SPLIT", "1"), psmem = env_is("CFM_B200_ATTN_PP_PTMEM", "0");
+  if (split1) {
+    CFM_SMEM_OPT_IN((attention_pp_kernel<1, false>), kSmemBytes);
+    CFM_CUDA_OK(launch_pdl(attention_pp_kernel<1, false>, grid, dim3(PPCfg<1>::kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
+  } else if (psmem) {
+    CFM_SMEM_OPT_IN((attention_pp_kernel<2, false>), kSmemBytes);
+    CFM_CUDA_OK(launch_pdl(attention_pp_kernel<2, false>, grid, dim3(PPCfg<2>::kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
+  } else {
+    CFM_SMEM_OPT_IN((attention_pp_kernel<2, true>), kSmemBytes);
+    CFM_CUDA_OK(launch_pdl(attention_pp_kernel<2, true>, grid, dim3(PPCfg<2>::kThreads), kSmemBytes, st, 1, tmQ, tmK, tmV, p));
+  }
   CFM_LAUNCHED_K("attention_pp");
   return 0;
 }
