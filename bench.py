@@ -667,7 +667,13 @@ def run_train(args):
     ddp.broadcast_parameters(dec)
     sync = ddp.attach(enc) if world > 1 else None
     other = [p for n, p in enc.named_parameters() if n.startswith("embed.")] + list(dec.parameters())
-    opt = torch.optim.Adam(list(enc.parameters()) + list(dec.parameters()), lr=1e-4, fused=True)
+    # module.py:140-143: torch.optim.Adam(self.parameters(), lr).  FlatAdam = the same update on flat buffers that follow the
+    # gradient buckets (one launch per layer instead of PyTorch's multi-tensor walk); CFM_BENCH_TORCH_ADAM=1 measures with
+    # torch.optim.Adam(fused=True) instead.
+    torch_adam = os.environ.get("CFM_BENCH_TORCH_ADAM", "0") == "1"
+    all_params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.Adam(all_params, lr=1e-4, fused=True) if torch_adam else C.FlatAdam(all_params, lr=1e-4)
+    opt_name = "torch.optim.Adam(fused)" if torch_adam else "FlatAdam (cfm_adam_step)"
     rs = np.random.RandomState(1234 + rank)
     feats_host = torch.from_numpy(rs.standard_normal((B, tin, 80)).astype(np.float32)).pin_memory()
     lens = torch.full((B,), tin, dtype=torch.int32, device=dev)
@@ -806,7 +812,7 @@ def run_train(args):
                         "h2d_bytes_per_step": int(feats_host.numel() * 4), "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
                         "steps": e2e_steps,
                         "api": "ConformerEncoder.forward (train mode, autograd) + CTCDecoder.forward + loss.backward() + "
-                               "ddp.GradSync per-layer all-reduce + torch.optim.Adam(fused).step(); features from pinned host "
+                               "ddp.GradSync per-layer all-reduce + " + opt_name + ".step(); features from pinned host "
                                "memory and the loss read back on the host every step"},
                 "gpu_launches": launches, "phases": phases, "kernels_total": fam,
                 "roofline": {"bound": "tensor", "kernel": "whole step (layer stack fwd+bwd + CTC head GEMMs), algorithmic FLOP of "

@@ -13,9 +13,11 @@ from .ctc import CTCDecoder, CTCGreedyHead
 from .frontend import Fbank, GlobalCMVN, load_cmvn
 from .transducer import RNNPredictor, TransducerJoint, basic_greedy_search, rnnt_loss
 from . import ddp
+from . import optim
+from .optim import FlatAdam
 from .utils import make_attn_mask, make_pad_mask, subsequent_chunk_mask
 
-__all__ = ["ConformerEncoder", "ConformerEncoderLayer", "RelativeMultiHeadSelfAttentionModule",
+__all__ = ["FlatAdam", "optim", "ConformerEncoder", "ConformerEncoderLayer", "RelativeMultiHeadSelfAttentionModule",
            "MultiHeadSelfAttentionModule", "RelativePositionalEncoding", "PositionalEncoding", "ConvolutionModule",
            "ConvolutionSubSampling", "PositionwiseFeedForwardModule", "make_pad_mask", "make_attn_mask",
            "subsequent_chunk_mask", "EncoderPipeline", "CTCGreedyHead", "CTCDecoder", "ddp", "Fbank", "GlobalCMVN", "load_cmvn", "TransducerJoint", "RNNPredictor",

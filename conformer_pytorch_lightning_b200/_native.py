@@ -24,7 +24,7 @@ EXPORTS = [
     "cfm_subsample_conv", "cfm_conv_module", "cfm_mhsa_out", "cfm_ffn_chain", "cfm_ctc_ws_bytes", "cfm_ctc_argmax", "cfm_gemm_ex", "cfm_l2_prefetch", "cfm_l2_prefetch_multi",
     "cfm_ln_fwd_train", "cfm_ln_bwd", "cfm_silu_dropout_fwd", "cfm_silu_dropout_bwd", "cfm_resid_dropout_add",
     "cfm_scale_dropout_bwd", "cfm_glu_fwd", "cfm_glu_bwd", "cfm_bn_silu_bwd", "cfm_dwconv_wgrad", "cfm_softmax_fwd",
-    "cfm_softmax_bwd", "cfm_colsum", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
+    "cfm_softmax_bwd", "cfm_colsum", "cfm_adam_step", "cfm_ctc_loss_ws_bytes", "cfm_ctc_loss_fwd", "cfm_ctc_loss_bwd",
     "cfm_fbank_frames", "cfm_fbank_power", "cfm_fbank_log_cmvn", "cfm_cmvn",
     "cfm_joint_add_tanh", "cfm_joint_tanh_bwd", "cfm_rnnt_loss_ws_bytes", "cfm_rnnt_loss_fwd", "cfm_rnnt_loss_bwd",
 ]
@@ -92,6 +92,7 @@ def _declare(lib):
     lib.cfm_softmax_fwd.argtypes = [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]
     lib.cfm_softmax_bwd.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]
     lib.cfm_colsum.argtypes = [_p, _i64, _p, _i, _i, _i, _p]
+    lib.cfm_adam_step.argtypes = [_p, _p, _p, _p, _p, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i, _f, _p]
     lib.cfm_ctc_loss_ws_bytes.argtypes = [_i, _i, _i]
     lib.cfm_ctc_loss_ws_bytes.restype = _i64
     lib.cfm_ctc_loss_fwd.argtypes = [_p, _i64, _i, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]

@@ -746,3 +746,81 @@ extern "C" int cfm_colsum(const void* x, int64_t ld, float* out, int rows, int c
   CFM_LAUNCHED_K("colsum");
   return 0;
 }
+
+// ------------------------------------------------------------------ optimizer step (module.py:140-143: torch.optim.Adam)
+namespace cfm {
+namespace {
+// One Adam update over a flat fp32 segment (torch.optim.Adam semantics, no weight decay / amsgrad):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// optionally writing the bf16 copy of the new parameter values the compute path consumes.  HBM bound: 28 B per element.
+template <bool VEC>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ p16, int64_t n, int head, float step_size,
+                                                   float b1, float omb1, float b2, float omb2, float eps, float inv_sqrt_bc2,
+                                                   float gscale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {      // omb = 1 - beta, rounded from double like PyTorch's
+    gg *= gscale;
+    mm = fmaf(b1, mm, omb1 * gg);
+    vv = fmaf(b2, vv, omb2 * gg * gg);
+    pp -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+  };
+  if (VEC) {
+    // the four fp32 pointers share their 16-byte phase: `head` scalar elements, 16-byte vectors, scalar tail
+    const int64_t n4 = (n - head) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + head);
+    float4* m4 = reinterpret_cast<float4*>(m + head);
+    float4* v4 = reinterpret_cast<float4*>(v + head);
+    const float4* g4 = reinterpret_cast<const float4*>(g + head);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 pp = p4[i], mm = m4[i], vv = v4[i];
+      const float4 gg = __ldg(g4 + i);
+      upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+      p4[i] = pp; m4[i] = mm; v4[i] = vv;
+      if (p16) reinterpret_cast<uint2*>(p16 + head)[i] = make_uint2(pack_bf16x2(pp.x, pp.y), pack_bf16x2(pp.z, pp.w));
+    }
+    const int64_t tail0 = head + (n4 << 2);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < head + (n - tail0); k += stride) {
+      const int64_t i = k < head ? k : tail0 + (k - head);
+      upd(p[i], g[i], m[i], v[i]);
+      if (p16) p16[i] = __float2bfloat16_rn(p[i]);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      upd(p[i], g[i], m[i], v[i]);
+      if (p16) p16[i] = __float2bfloat16_rn(p[i]);
+    }
+  }
+}
+}  // namespace
+}  // namespace cfm
+
+extern "C" int cfm_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr, double beta1,
+                             double beta2, double eps, int step, float grad_scale, void* stream) {
+  using namespace cfm;
+  CFM_CHECK_ARG(p && g && m && v, "cfm_adam_step: null pointer");
+  CFM_CHECK_ARG(n >= 0 && step >= 1, "cfm_adam_step: bad size / step");
+  CFM_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "cfm_adam_step: bad hyper-parameters");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+  const float step_size = (float)(lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float b1f = (float)beta1, omb1 = (float)(1.0 - beta1), b2f = (float)beta2, omb2 = (float)(1.0 - beta2), epsf = (float)eps;
+  const uintptr_t ph = reinterpret_cast<uintptr_t>(p) & 15;
+  int head = (int)(((16 - ph) & 15) / 4);
+  if (head > n) head = (int)n;
+  const bool vec = (ph & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == ph && (reinterpret_cast<uintptr_t>(m) & 15) == ph &&
+                   (reinterpret_cast<uintptr_t>(v) & 15) == ph &&
+                   (p_bf16 == nullptr || ((reinterpret_cast<uintptr_t>(p_bf16) + 2 * (uintptr_t)head) & 7) == 0);
+  const int64_t work = vec ? (n + 3) / 4 + 8 : n;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (vec)
+    adam_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, head, step_size, b1f,
+                                                                         omb1, b2f, omb2, epsf, inv_sqrt_bc2, grad_scale);
+  else
+    adam_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, 0, step_size, b1f,
+                                                                          omb1, b2f, omb2, epsf, inv_sqrt_bc2, grad_scale);
+  CFM_LAUNCHED_K("adam");
+  return 0;
+}

@@ -82,11 +82,11 @@ class _CTCLossFunction(torch.autograd.Function):
         ctx.saved = None
         B, T, d, V, Vp, has_bias, in_dtype = ctx.dims
         dev = x.device
-        # d loss / d nll_b = dloss / Lmax, folded into the logit gradient (dloss is read on the host: one scalar sync,
-        # exactly what the reference's loss.backward() entry costs)
-        scale = float(dloss) / max(lab32.shape[1], 1)
-        TO.ctc_loss_bwd(logits, B, T, V, lab32, il, ll, nll, ws, scale, logits)          # in place: logits -> dlogits
+        # d loss / d nll_b = dloss / Lmax.  1 / Lmax is folded into the logit gradient; dloss stays on the device (reading it
+        # on the host would stall the host until the whole forward has finished, and with it every launch of the backward)
+        TO.ctc_loss_bwd(logits, B, T, V, lab32, il, ll, nll, ws, 1.0 / max(lab32.shape[1], 1), logits)   # in place: logits -> dlogits
         dl = logits
+        dl.mul_(dloss.to(device=dev, dtype=dl.dtype))
         dx = torch.empty((B * T, d), dtype=x.dtype, device=dev)
         ops.gemm_ex(dl, wp.t(), dx)                                                      # dgrad
         gw = torch.zeros((Vp, d), dtype=torch.float32, device=dev)

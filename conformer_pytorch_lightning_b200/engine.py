@@ -143,13 +143,29 @@ class Derived:
             if old is not None and old.keys() == new.keys() and all(
                     old[k].shape == new[k].shape and old[k].dtype == new[k].dtype and old[k].device == new[k].device
                     for k in new):
+                # Entries that ARE module state (fp32 parameters / buffers handed through without a copy) are never written
+                # to: in train mode ``dw_b`` is the depthwise bias parameter itself, in eval mode it is the BatchNorm-folded
+                # bias -- copying the latter into the former would overwrite the parameter.  Such entries are replaced
+                # (and the generation bumped: graphs that baked in the old address are dropped); private buffers are
+                # refreshed in place so that captured graphs stay valid.
+                owned = {t.untyped_storage().data_ptr() for t in tensors}
+                replaced = False
                 for k in new:
-                    if old[k].data_ptr() != new[k].data_ptr():
+                    if old[k].data_ptr() == new[k].data_ptr():
+                        continue
+                    if old[k].untyped_storage().data_ptr() in owned or old[k].untyped_storage().data_ptr() in slot[2]:
+                        old[k] = new[k]
+                        replaced = True
+                    else:
                         old[k].copy_(new[k])
                 new = old
+                if replaced:
+                    self.generation += 1
             else:
                 self.generation += 1
-            self.slots[dtype] = (key, new)
+            # storages of the module state this slot was built from (a re-pointed parameter leaves its old storage behind:
+            # entries still aliasing it must be replaced, not refreshed, at the next rebuild)
+            self.slots[dtype] = (key, new, {t.untyped_storage().data_ptr() for t in tensors})
             return new
         return slot[1]
 

@@ -429,8 +429,11 @@ class TrainPlan:
         return self.pending is not None and self.pending() is not None
 
 
-def _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync):
-    cfg = tuple((l.training, l.conv_module.training, l.dropout.p, l.self_attn.dropout.p, l.feed_forward.dropout.p,
+def _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync, params=()):
+    # the captured graphs read the parameters through their addresses: a re-pointed parameter (p.data = ..., e.g. by
+    # optim.FlatAdam when it moves the parameters into its flat buffers) must not replay a stale plan
+    where = hash(tuple(p.data_ptr() for p in params))
+    cfg = (where,) + tuple((l.training, l.conv_module.training, l.dropout.p, l.self_attn.dropout.p, l.feed_forward.dropout.p,
                  l.feed_forward_macaron.dropout.p, l.conv_module.norm.momentum) for l in layers)
     return (tuple(x_emb.shape), x_emb.device, dtype, None if attn_mask is None else tuple(attn_mask.shape),
             None if pad_mask is None else tuple(pad_mask.shape), cfg, after_norm is not None, grad_sync is not None)
@@ -603,7 +606,7 @@ def run_stack(x_emb, layers, after_norm, attn_mask, pos_embed, pad_mask, dtype, 
             and (pad_mask is None or pad_mask.dim() != 3 or pad_mask.size(2) == 0 or tuple(pad_mask.shape) == (B, 1, T))
             and all(l.conv_module.norm.momentum is not None for l in layers)):
         plans = owner.__dict__.setdefault("_train_plans", {})
-        key = _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync)
+        key = _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync, params)
         cand = plans.get(key)
         if cand is None:
             while len(plans) >= 4:

@@ -169,13 +169,14 @@ class _RnntLossFunction(torch.autograd.Function):
         B, T, U1, V, ld, blank, reduction = ctx.cfg
         if reduction == "none":
             raise NotImplementedError("rnnt_loss backward with reduction='none' (per-utterance upstream gradients)")
-        scale = float(dloss) / (B if reduction == "mean" else 1)
+        scale = 1.0 / (B if reduction == "mean" else 1)      # the upstream gradient stays on the device (no host sync)
         rows = B * T * U1
         Vp = ld if ld >= V else V
         buf = torch.empty((rows, ld), dtype=logits.dtype, device=logits.device)
         N.check(N.lib().cfm_rnnt_loss_bwd(logits.data_ptr(), ld, B, T, U1, V, Vp, blank, tg.data_ptr(), tg.shape[1], tl.data_ptr(),
                                           ul.data_ptr(), nll.data_ptr(), ws.data_ptr(), scale, buf.data_ptr(),
                                           ops._DT[logits.dtype], ops._stream(logits)))
+        buf.mul_(dloss.to(device=buf.device, dtype=buf.dtype))
         g = buf.view(B, T, U1, ld)[..., :V]
         g._cfm_padded = buf                     # lets the joint's backward use the zero-padded buffer without a copy
         return g, None, None, None, None, None

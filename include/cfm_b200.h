@@ -323,6 +323,12 @@ int cfm_softmax_bwd(const void* P, const float* dPd, void* dS, int B, int H, int
                     const uint64_t* seed, int site, void* stream);
 /* out (cols) += column sums of x (rows, ld) -- bias gradients. */
 int cfm_colsum(const void* x, int64_t ld, float* out, int rows, int cols, int dtype, void* stream);
+/* Optimizer step of the training loop (module.py:140-143: torch.optim.Adam(self.parameters(), lr), default betas / eps, no
+ * weight decay): one Adam update over a flat fp32 segment of n elements, torch.optim.Adam arithmetic,
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1-b1^step) * m / (sqrt(v) / sqrt(1-b2^step) + eps)
+ * with g = grad_scale * grad.  `step` counts from 1.  p_bf16 (may be NULL) receives the bf16 copy of the updated values. */
+int cfm_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int step, float grad_scale, void* stream);
 
 /* CTC loss (decoder.py:18-23: log_softmax + nn.CTCLoss(reduction='sum'), blank = 0) on logits (B*T, ld), V valid
  * columns.  fwd: nll[b]; bwd: dlogits = scale * (softmax - occupancy) for valid frames, 0 elsewhere (may alias logits).

@@ -263,3 +263,123 @@ def test_training_plan_is_released_by_a_dropped_forward_and_survives_accumulatio
     (o1.square().mean() + o2.square().mean()).backward()
     g_ref = enc.encoders[0].feed_forward.w_1.weight.grad
     assert float((g_acc - g_ref).abs().max()) < 2e-2 * float(g_ref.abs().max())
+
+
+# ----------------------------------------------------------------------------------------------- optimizer step
+@pytest.mark.gpu
+def test_flat_adam_matches_torch_adam_on_plain_tensors():
+    """cfm_adam_step vs torch.optim.Adam (module.py:141 configuration) on stand-alone gradients, odd sizes, several steps and
+    a changing learning rate (the WarmupLR scheduler writes param_groups[0]['lr'])."""
+    import conformer_pytorch_lightning_b200 as C
+    torch.manual_seed(0)
+    shapes = [(257, 33), (5,), (1024, 256), (3, 1, 15), (1,)]
+    ref = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2)
+    o_new = C.FlatAdam(ours, lr=1e-2)
+    for it in range(5):
+        for g in (o_ref.param_groups[0], o_new.param_groups[0]):
+            g["lr"] = 1e-2 * (it + 1) / 5
+        for a, b in zip(ref, ours):
+            g = torch.randn_like(a)
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step()
+        o_new.step()
+    for a, b in zip(ref, ours):
+        assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
+    sd_ref, sd_new = o_ref.state_dict(), o_new.state_dict()
+    for k in sd_ref["state"]:
+        assert int(sd_new["state"][k]["step"]) == int(sd_ref["state"][k]["step"]) == 5
+        assert torch.allclose(sd_new["state"][k]["exp_avg"], sd_ref["state"][k]["exp_avg"], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(sd_new["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+    # resume: a torch.optim.Adam checkpoint loads into FlatAdam and the next step agrees
+    o_res = C.FlatAdam([torch.nn.Parameter(p.detach().clone()) for p in ref], lr=1e-2)
+    o_res.load_state_dict(sd_ref)                          # (FlatAdam takes private copies of the loaded moments)
+    res = o_res.param_groups[0]["params"]
+    for a, b in zip(ref, res):
+        g = torch.randn_like(a)
+        a.grad, b.grad = g.clone(), g.clone()
+    o_ref.step()
+    o_res.step()
+    for a, b in zip(ref, res):
+        assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
+
+
+@pytest.mark.gpu
+def test_flat_adam_training_steps_match_torch_adam():
+    """Three optimizer steps of a 2-layer encoder + CTC head: FlatAdam on the live parameters vs torch.optim.Adam on shadow
+    copies fed the SAME gradients (two separate training runs diverge by +-lr wherever a gradient is rounding noise: Adam
+    normalises the magnitude away).  The layer gradients arrive as views of the per-layer buckets, so FlatAdam updates a
+    bucket with one launch; the derived bf16 / re-laid-out weights the next forward uses must follow the update."""
+    import conformer_pytorch_lightning_b200 as C
+    from conformer_pytorch_lightning_b200 import _native
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, static_chunk_size=16, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0)
+    rs = np.random.RandomState(3)
+    feats = torch.from_numpy(rs.standard_normal((4, 200, 80)).astype(np.float32)).cuda()
+    lens = torch.tensor([200, 180, 160, 120], dtype=torch.int32, device="cuda")
+    labels = torch.from_numpy(rs.randint(1, 50, size=(4, 8)).astype(np.int64)).cuda()
+    lab_len = torch.full((4,), 8, dtype=torch.int64, device="cuda")
+    for dtype in (torch.float32, torch.bfloat16):
+        enc = build_encoder(cfg, 0, compute_dtype=dtype).train()
+        torch.manual_seed(1)
+        dec = C.CTCDecoder(60, cfg["encoder_dim"], 0.0).cuda()
+        dec.compute_dtype = dtype
+        ps = list(enc.parameters()) + list(dec.parameters())
+        shadow = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        opt, opt_ref = C.FlatAdam(ps, lr=1e-3), torch.optim.Adam(shadow, lr=1e-3)
+        launches0 = _native.kernel_launches("adam")
+        losses = []
+        for it in range(4):                                  # eager, eager (re-pointed parameters), capture, replay
+            opt.zero_grad(set_to_none=True)
+            out, mask = enc(feats, lens)
+            loss = dec(out.float(), mask.squeeze(1).sum(1), labels, lab_len)
+            loss.backward()
+            for p, s_ in zip(ps, shadow):
+                s_.grad = None if p.grad is None else p.grad.detach().clone()
+            opt.step()
+            opt_ref.step()
+            losses.append(float(loss))
+            worst = max(float((p.detach() - s_.detach()).abs().max()) / max(1.0, float(s_.detach().abs().max())) for p, s_ in zip(ps, shadow))
+            assert worst <= 2e-6, (it, worst)
+        n_launch = (_native.kernel_launches("adam") - launches0) // 4
+        print(f"{dtype}: adam launches per step {n_launch} for {len(ps)} parameter tensors; losses {losses}")
+        assert n_launch < len(ps) // 2                        # buckets, not tensors
+        assert losses[-1] < losses[0]                         # and it trains
+        # the updated parameters are what the next forward computes with (derived-weight caches invalidated)
+        enc2 = build_encoder(cfg, 0, compute_dtype=dtype)
+        enc2.load_state_dict(enc.state_dict())
+        enc.eval(); enc2.eval()
+        with torch.no_grad():
+            a, _ = enc(feats, lens)
+            b, _ = enc2(feats, lens)
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_train_eval_switch_leaves_parameters_untouched(dtype):
+    """Derived weights that ARE parameters in train mode (the depthwise bias) become BatchNorm-folded copies in eval mode:
+    refreshing the cache must never write the eval-mode value into the parameter (validation passes inside a training run)."""
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, static_chunk_size=16, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0)
+    rs = np.random.RandomState(5)
+    feats = torch.from_numpy(rs.standard_normal((3, 160, 80)).astype(np.float32)).cuda()
+    lens = torch.tensor([160, 140, 100], dtype=torch.int32, device="cuda")
+    enc = build_encoder(cfg, 0, compute_dtype=dtype).train()
+    out, _ = enc(feats, lens)
+    out.float().square().mean().backward()
+    before = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    enc.eval()
+    with torch.no_grad():
+        for _ in range(3):                                    # eager, capture, replay
+            enc(feats, lens)
+    enc.train()
+    out, _ = enc(feats, lens)
+    after = enc.state_dict()
+    for k, v in before.items():
+        if "running_" in k or "num_batches" in k:
+            continue                                          # the second training forward updates the running statistics
+        assert torch.equal(v, after[k]), k
