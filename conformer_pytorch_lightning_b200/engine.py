@@ -149,11 +149,16 @@ class Derived:
                 # (and the generation bumped: graphs that baked in the old address are dropped); private buffers are
                 # refreshed in place so that captured graphs stay valid.
                 owned = {t.untyped_storage().data_ptr() for t in tensors}
+                # persistent sources: module state and the optimizer's low-precision mirrors of it (see mirror_valid): a new
+                # entry that is a view of one of those is adopted as it is (it tracks its source without any copy)
+                persistent = owned | {t._cfm_mirror.untyped_storage().data_ptr() for t in tensors
+                                      if getattr(t, "_cfm_mirror", None) is not None}
                 replaced = False
                 for k in new:
                     if old[k].data_ptr() == new[k].data_ptr():
                         continue
-                    if old[k].untyped_storage().data_ptr() in owned or old[k].untyped_storage().data_ptr() in slot[2]:
+                    if (old[k].untyped_storage().data_ptr() in owned or old[k].untyped_storage().data_ptr() in slot[2]
+                            or new[k].untyped_storage().data_ptr() in persistent):
                         old[k] = new[k]
                         replaced = True
                     else:
@@ -179,9 +184,38 @@ def _f32(w):
     return w.detach().float().contiguous()
 
 
+# ---- low-precision mirrors of the parameters (optim.FlatAdam): the optimizer kernel writes the bf16 copy of every updated
+# parameter into a flat mirror buffer laid out like its flat fp32 buffer; ``p._cfm_mirror`` is the view that belongs to p and
+# ``p._cfm_mirror_version`` the parameter version it was written for.  While the two agree the mirror IS the compute-dtype
+# copy: no cast kernel, and a captured graph that reads it sees every optimizer step.
+def mirror_valid(p):
+    return getattr(p, "_cfm_mirror", None) is not None and p._version == getattr(p, "_cfm_mirror_version", -1)
+
+
+def _actp(p, dtype, shape=None):
+    """Compute-dtype copy of parameter ``p`` (optionally reshaped): its mirror when that is current, else a cast."""
+    if mirror_valid(p) and p._cfm_mirror.dtype == dtype:
+        return p._cfm_mirror if shape is None else p._cfm_mirror.view(shape)
+    return _act(p if shape is None else p.detach().reshape(shape), dtype)
+
+
+def _actp_cat(ps, dtype):
+    """cat(ps, 0) in the compute dtype; free when the parameters' mirrors are adjacent in memory (bucket layout)."""
+    if all(mirror_valid(p) and p._cfm_mirror.dtype == dtype for p in ps):
+        ms = [p._cfm_mirror for p in ps]
+        es = ms[0].element_size()
+        if all(m.is_contiguous() and m.shape[1:] == ms[0].shape[1:] for m in ms) and all(
+                ms[i + 1].untyped_storage().data_ptr() == ms[0].untyped_storage().data_ptr() and
+                ms[i + 1].data_ptr() == ms[i].data_ptr() + ms[i].numel() * es for i in range(len(ms) - 1)):
+            rows = sum(m.shape[0] for m in ms)
+            shape = (rows,) + tuple(ms[0].shape[1:])
+            return torch.as_strided(ms[0], shape, ms[0].stride())
+    return _act(torch.cat([p.detach() for p in ps], 0), dtype)
+
+
 def ffn_weights(m, dtype):
-    return {"w1": _act(m.w_1.weight, dtype), "b1": _f32(m.w_1.bias),
-            "w2": _act(m.w_2.weight, dtype), "b2": _f32(m.w_2.bias)}
+    return {"w1": _actp(m.w_1.weight, dtype), "b1": _f32(m.w_1.bias),
+            "w2": _actp(m.w_2.weight, dtype), "b2": _f32(m.w_2.bias)}
 
 
 def mhsa_weights(m, dtype):
@@ -189,11 +223,11 @@ def mhsa_weights(m, dtype):
     bq = m.linear_q.bias.detach().float()
     if rel:
         bq = bq + m.pos_bias_u.detach().float().reshape(-1)     # (q + u) folded into the q bias
-    d = {"wqkv": _act(torch.cat([m.linear_q.weight, m.linear_k.weight, m.linear_v.weight], 0), dtype),
+    d = {"wqkv": _actp_cat([m.linear_q.weight, m.linear_k.weight, m.linear_v.weight], dtype),
          "bqkv": torch.cat([bq, m.linear_k.bias.detach().float(), m.linear_v.bias.detach().float()]).contiguous(),
-         "wo": _act(m.linear_out.weight, dtype), "bo": _f32(m.linear_out.bias)}
+         "wo": _actp(m.linear_out.weight, dtype), "bo": _f32(m.linear_out.bias)}
     if rel:
-        d["wpos"] = _act(m.linear_pos.weight, dtype)
+        d["wpos"] = _actp(m.linear_pos.weight, dtype)
         d["u"] = _f32(m.pos_bias_u)
         d["vb"] = _f32(m.pos_bias_v)
     return d
@@ -213,8 +247,8 @@ def conv_weights(m, dtype):
         scale = m.norm.weight.detach().float() * torch.rsqrt(m.norm.running_var.float() + m.norm.eps)
         dw = dw * scale[:, None]
         db = (db - m.norm.running_mean.float()) * scale + m.norm.bias.detach().float()
-    return {"w1": _act(w1, dtype), "b1": b1, "dw_w": dw.t().contiguous(), "dw_b": db.contiguous(),
-            "w2": _act(m.pointwise_conv2.weight.detach().reshape(dd, dd), dtype), "b2": _f32(m.pointwise_conv2.bias),
+    return {"w1": _actp(m.pointwise_conv1.weight, dtype, (2 * dd, dd)), "b1": b1, "dw_w": dw.t().contiguous(), "dw_b": db.contiguous(),
+            "w2": _actp(m.pointwise_conv2.weight, dtype, (dd, dd)), "b2": _f32(m.pointwise_conv2.bias),
             "gamma": _f32(m.norm.weight), "beta": _f32(m.norm.bias)}
 
 

@@ -36,18 +36,22 @@ def _bump_versions(tensors):
 
 class _Segment:
     """A run of parameters updated by one launch: flat views of p / exp_avg / exp_avg_sq and the expected gradient layout."""
-    __slots__ = ("params", "rel", "p", "m", "v", "span")
+    __slots__ = ("params", "rel", "p", "m", "v", "span", "mirror")
 
-    def __init__(self, params, rel, p, m, v, span):
-        self.params, self.rel, self.p, self.m, self.v, self.span = params, rel, p, m, v, span
+    def __init__(self, params, rel, p, m, v, span, mirror=None):
+        self.params, self.rel, self.p, self.m, self.v, self.span, self.mirror = params, rel, p, m, v, span, mirror
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, bf16_mirror=True):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
             raise ValueError("FlatAdam: bad hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
         self.grad_scale = float(grad_scale)
+        # bf16_mirror: the kernel also writes the bf16 copy of every updated parameter into a flat mirror (laid out like the
+        # fp32 buffer); the bf16 compute path takes its weights from there (engine._actp) instead of re-casting the fp32
+        # masters at every step (~0.4 ms of cast / copy kernels per C5 step)
+        self.bf16_mirror = bool(bf16_mirror)
         self._segments = {}          # id(group) -> list of _Segment (built at the first step from the gradient layout)
         self._steps = {}             # id(group) -> python int (the kernel takes the step count by value)
         self._step_tensor = {}
@@ -101,6 +105,7 @@ class FlatAdam(torch.optim.Optimizer):
         def flat():
             return torch.zeros(span + 4, dtype=torch.float32, device=dev)[pad:pad + span]
         fp, fm, fv = flat(), flat(), flat()
+        mirror = torch.zeros(span + 4, dtype=torch.bfloat16, device=dev)[pad:pad + span] if self.bf16_mirror else None
         for p, r in zip(params, rel):
             n = p.numel()
             view = fp[r:r + n].view(p.shape)
@@ -114,7 +119,11 @@ class FlatAdam(torch.optim.Optimizer):
                 st["exp_avg"].copy_(old_m)
                 st["exp_avg_sq"].copy_(old_v)
             st.setdefault("step", torch.zeros((), dtype=torch.float32))
-        return _Segment(params, rel, fp, fm, fv, span)
+            if mirror is not None:
+                p._cfm_mirror = mirror[r:r + n].view(p.shape)
+                p._cfm_mirror.copy_(p.data)
+                p._cfm_mirror_version = -1             # becomes current with the first update written by the kernel
+        return _Segment(params, rel, fp, fm, fv, span, mirror)
 
     # ---------------------------------------------------------------- step
     @torch.no_grad()
@@ -154,7 +163,8 @@ class FlatAdam(torch.optim.Optimizer):
                     for p, r in zip(seg.params, seg.rel))
                 if ok:
                     stream = torch.cuda.current_stream(p0.device).cuda_stream
-                    N.check(lib.cfm_adam_step(seg.p.data_ptr(), base, seg.m.data_ptr(), seg.v.data_ptr(), None, seg.span, lr, b1, b2,
+                    N.check(lib.cfm_adam_step(seg.p.data_ptr(), base, seg.m.data_ptr(), seg.v.data_ptr(),
+                                              None if seg.mirror is None else seg.mirror.data_ptr(), seg.span, lr, b1, b2,
                                               eps, step, self.grad_scale, stream))
                 else:
                     self._step_params(lib, seg, group, step)
@@ -167,6 +177,9 @@ class FlatAdam(torch.optim.Optimizer):
                 if self.state[p].get("step") is not shared:
                     self.state[p]["step"] = shared       # one host tensor per group (state_dict still lists it per parameter)
             _bump_versions(touched)
+            if self.bf16_mirror:
+                for p in touched:                        # the mirrors hold exactly these parameter versions
+                    p._cfm_mirror_version = p._version
         return loss
 
     def _step_params(self, lib, seg, group, step):
@@ -178,8 +191,10 @@ class FlatAdam(torch.optim.Optimizer):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             st = self.state[p]
             stream = torch.cuda.current_stream(p.device).cuda_stream
-            N.check(lib.cfm_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), None,
-                                      p.numel(), lr, b1, b2, eps, step, self.grad_scale, stream))
+            mir = getattr(p, "_cfm_mirror", None) if self.bf16_mirror else None
+            N.check(lib.cfm_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                      None if mir is None else mir.data_ptr(), p.numel(), lr, b1, b2, eps, step, self.grad_scale,
+                                      stream))
 
     @torch.no_grad()
     def _build_late(self, group):

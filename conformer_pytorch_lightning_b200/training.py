@@ -432,7 +432,9 @@ class TrainPlan:
 def _plan_key(x_emb, layers, after_norm, attn_mask, pad_mask, dtype, grad_sync, params=()):
     # the captured graphs read the parameters through their addresses: a re-pointed parameter (p.data = ..., e.g. by
     # optim.FlatAdam when it moves the parameters into its flat buffers) must not replay a stale plan
-    where = hash(tuple(p.data_ptr() for p in params))
+    # ... and a plan captured while the bf16 mirrors of the parameters were current (no cast kernels inside) is only valid
+    # while they are: any other in-place update of a parameter flips its bit and selects a plan that re-derives its weights
+    where = hash(tuple((p.data_ptr(), engine.mirror_valid(p)) for p in params))
     cfg = (where,) + tuple((l.training, l.conv_module.training, l.dropout.p, l.self_attn.dropout.p, l.feed_forward.dropout.p,
                  l.feed_forward_macaron.dropout.p, l.conv_module.norm.momentum) for l in layers)
     return (tuple(x_emb.shape), x_emb.device, dtype, None if attn_mask is None else tuple(attn_mask.shape),

@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import conformer_pytorch_lightning_b200 as C
-from conformer_pytorch_lightning_b200 import _native
+from conformer_pytorch_lightning_b200 import _native, engine
 from oracle import conformer_oracle as O
 from oracle import conformer_oracle_torch as OT
 from _util import build_encoder, load_golden, max_rel
@@ -347,6 +347,19 @@ def test_flat_adam_training_steps_match_torch_adam():
         print(f"{dtype}: adam launches per step {n_launch} for {len(ps)} parameter tensors; losses {losses}")
         assert n_launch < len(ps) // 2                        # buckets, not tensors
         assert losses[-1] < losses[0]                         # and it trains
+        if dtype == torch.bfloat16:
+            # the bf16 weights of the compute path ARE the optimizer's mirrors (no cast kernels per step) ...
+            l0 = enc.encoders[0]
+            W = l0.derived_weights(dtype)
+            assert W["ff"]["w1"].data_ptr() == l0.feed_forward.w_1.weight._cfm_mirror.data_ptr()
+            assert W["mha"]["wqkv"].data_ptr() == l0.self_attn.linear_q.weight._cfm_mirror.data_ptr()
+            assert W["conv"]["w2"].data_ptr() == l0.conv_module.pointwise_conv2.weight._cfm_mirror.data_ptr()
+            # ... until something else touches a parameter: then the weights are re-derived from the fp32 master
+            with torch.no_grad():
+                l0.feed_forward.w_1.weight.mul_(1.0)
+            assert not engine.mirror_valid(l0.feed_forward.w_1.weight)
+            W = l0.derived_weights(dtype)
+            assert torch.equal(W["ff"]["w1"], l0.feed_forward.w_1.weight.detach().to(dtype))
         # the updated parameters are what the next forward computes with (derived-weight caches invalidated)
         enc2 = build_encoder(cfg, 0, compute_dtype=dtype)
         enc2.load_state_dict(enc.state_dict())

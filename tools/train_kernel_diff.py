@@ -44,3 +44,6 @@ print("total us/step: torch %.0f  flat %.0f" % (sum(v[0] for v in res["torch"].v
 for k in keys[:22]:
     a, b = res["torch"].get(k, (0, 0)), res["flat"].get(k, (0, 0))
     print(f"{b[0] - a[0]:+9.1f} us  torch {a[0]:8.1f} ({a[1]:.0f}x)  flat {b[0]:8.1f} ({b[1]:.0f}x)  {k[:100]}")
+print("---- FlatAdam step, kernels by device time")
+for k, v in sorted(res["flat"].items(), key=lambda kv: -kv[1][0])[:32]:
+    print(f"{v[0]:9.1f} us ({v[1]:4.0f}x, {v[0] / max(v[1], 1):6.1f} us each)  {k[:110]}")
