@@ -113,6 +113,14 @@ def test_training_on_cpu_raises_too():
         dec(torch.randn(1, 10, 256), torch.tensor([10]), torch.ones(1, 3, dtype=torch.long), torch.tensor([3]))
 
 
+def test_flat_adam_refuses_cpu_parameters():
+    """The optimizer step is native too (cfm_adam_step): CPU / non-fp32 parameters raise instead of falling back."""
+    with pytest.raises(NotImplementedError, match="CUDA fp32"):
+        C.FlatAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
+    with pytest.raises(ValueError):
+        C.FlatAdam([torch.nn.Parameter(torch.zeros(4))], lr=-1.0)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "conformer_pytorch_lightning_b200")
     for fn in os.listdir(pkg):
