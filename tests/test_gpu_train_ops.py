@@ -178,7 +178,8 @@ def test_residual_dropout_pair(dtype):
     df, dbias = torch.empty((rows, cols), dtype=dtype, device="cuda"), torch.zeros(cols, device="cuda")
     TO.scale_dropout_bwd(dx, df, dbias, alpha=0.5, row_valid=valid, p=0.25, seed=_seed(7), site=3)
     ref = 0.5 * dx * torch.where(mult.abs() < 1e-3, 0.0, 1 / 0.75) * valid[:, None]
-    assert _rel(df.float(), ref) < _tol(dtype)
+    known = f.float().abs() > 1e-4                            # where f ~ 0 the forward does not reveal the mask (x - x0 underflows)
+    assert _rel(df.float() * known, ref * known) < _tol(dtype)
     assert _rel(dbias, df.float().sum(0)) < 1e-5
 
 
