@@ -139,29 +139,35 @@ int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, 
 }
 
 // ------------------------------------------------------------------ BatchNorm (training) pieces
-__global__ void __launch_bounds__(256)
+// Deterministic (no atomics: the training forward repeats bit for bit under the same seed): one block owns 16 channels and
+// reduces ALL rows itself -- 64 row lanes per channel, fixed-order tree in shared memory.  d / 16 blocks (16 at d = 256)
+// stream 256 KB each; the first version used 64-channel slabs + atomicAdd (order dependent sums, and 15.7 us at the C5 shard
+// because only 64 blocks were launched).
+__global__ void __launch_bounds__(1024)
 bn_stats_kernel(const float* __restrict__ x, int rows, int d, float* __restrict__ sum,
                 float* __restrict__ sumsq) {
-  // block = 64 channels x 4 row-lanes; grid.x over channel groups, grid.y over row slabs
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int rl = threadIdx.x >> 6;
-  float s = 0.f, q = 0.f;
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;       // 16 channels x 64 row lanes
+  const int c = blockIdx.x * 16 + cl;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   if (c < d) {
-    for (int r = blockIdx.y * 4 + rl; r < rows; r += gridDim.y * 4) {
-      const float v = x[(size_t)r * d + c];
-      s += v;
-      q = fmaf(v, v, q);
+    int r = rl;
+    for (; r + 64 < rows; r += 128) {                             // two independent chains / loads in flight
+      const float a = x[(size_t)r * d + c], b = x[(size_t)(r + 64) * d + c];
+      s0 += a; q0 = fmaf(a, a, q0);
+      s1 += b; q1 = fmaf(b, b, q1);
     }
+    if (r < rows) { const float a = x[(size_t)r * d + c]; s0 += a; q0 = fmaf(a, a, q0); }
   }
-  __shared__ float ss[4][64], sq[4][64];
-  ss[rl][threadIdx.x & 63] = s;
-  sq[rl][threadIdx.x & 63] = q;
+  __shared__ float ss[64][17], sq[64][17];
+  ss[rl][cl] = s0 + s1;
+  sq[rl][cl] = q0 + q1;
   __syncthreads();
-  if (rl == 0 && c < d) {
-    const int i = threadIdx.x & 63;
-    atomicAdd(sum + c, (ss[0][i] + ss[1][i]) + (ss[2][i] + ss[3][i]));
-    atomicAdd(sumsq + c, (sq[0][i] + sq[1][i]) + (sq[2][i] + sq[3][i]));
+#pragma unroll
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (rl < w) { ss[rl][cl] += ss[rl + w][cl]; sq[rl][cl] += sq[rl + w][cl]; }
+    __syncthreads();
   }
+  if (rl == 0 && c < d) { sum[c] += ss[0][cl]; sumsq[c] += sq[0][cl]; }
 }
 
 template <typename T>
@@ -234,8 +240,7 @@ extern "C" int cfm_bn_stats(const float* x, int rows, int d, float* sum, float* 
   using namespace cfm;
   CFM_CHECK_ARG(x && sum && sumsq, "cfm_bn_stats: null pointer");
   if (rows <= 0) return 0;
-  dim3 grid((d + 63) / 64, max(1, min((rows + 255) / 256, 4 * num_sms())));
-  bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, d, sum, sumsq);
+  bn_stats_kernel<<<(d + 15) / 16, 1024, 0, (cudaStream_t)stream>>>(x, rows, d, sum, sumsq);
   CFM_LAUNCHED_K("bn_stats");
   return 0;
 }

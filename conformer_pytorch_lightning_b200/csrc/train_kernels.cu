@@ -448,18 +448,27 @@ dwconv_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ u, float* __
   float acc[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; ++j) acc[j] = 0.f;
-  const int t0 = blockIdx.y * seg, t1 = min(t0 + seg, Tlen);
-  if (c < d) {
+  // each of the 4 time lanes owns SEG/4 = 16 CONSECUTIVE frames of the block's segment: 16 dy values and the 16 + K - 1 u
+  // values around them are loaded once into registers (all loads independent, issued back to back) and the K tap sums are
+  // fully unrolled FMAs -- the first version re-read u through L1 K times per frame with the loads in the dependent chain
+  constexpr int TL = 16;
+  const int t0 = blockIdx.y * seg + tl * TL;
+  if (c < d && t0 < Tlen) {
     const T* dyb = dy + (size_t)b * Tlen * d + c;
     const T* ub = u + (size_t)b * Tlen * d + c;
-    for (int t = t0 + tl; t < t1; t += 4) {
-      const float g = to_f32(dyb[(size_t)t * d]);
-      acc[K] += g;
+    float g[TL], w[TL + K - 1];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const int s = t + j - pad;
-        if (s >= 0 && s < Tlen) acc[j] = fmaf(g, to_f32(ub[(size_t)s * d]), acc[j]);
-      }
+    for (int i = 0; i < TL; ++i) g[i] = (t0 + i < Tlen) ? to_f32(dyb[(size_t)(t0 + i) * d]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < TL + K - 1; ++i) {
+      const int sidx = t0 + i - pad;
+      w[i] = (sidx >= 0 && sidx < Tlen) ? to_f32(ub[(size_t)sidx * d]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TL; ++i) {
+      acc[K] += g[i];
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc[j] = fmaf(g[i], w[i + j], acc[j]);
     }
   }
   __shared__ float red[4][64];
@@ -476,6 +485,12 @@ dwconv_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ u, float* __
   }
 }
 
+// eight consecutive elements (row offsets are multiples of 8): 16 bytes of bf16 or 2 x 16 bytes of fp32
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) { Vec<__nv_bfloat16>::store(p, f); }
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) { store_f32<8>(p, f); }
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) { Vec<__nv_bfloat16>::load(p, f); }
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) { load_f32<8>(p, f); }
+
 // ================================================================== masked softmax + dropout (attention.py:88-95)
 // one warp per (b, h, i) row of S (fp32, row stride Tp); mask semantics of the reference: masked -> -inf, softmax,
 // masked -> 0 (a fully masked row gives zeros).  P (and the dropped copy Pd) are written with zeros in columns [T, Tp).
@@ -490,6 +505,44 @@ softmax_fwd_kernel(const float* __restrict__ S, T* __restrict__ P, T* __restrict
   const int b = (int)(row / ((long long)H * Tq));
   const float* s = S + row * Tp;
   const uint8_t* m = mask ? mask + b * mask_bs + i * mask_rs : nullptr;
+  if (Tp <= 256) {
+    // one pass with the row in registers (8 columns per lane): two 16-byte loads of S, the 8 mask bytes, one 16-byte store
+    // of P (and of Pd) per lane, instead of three passes of scalar loads
+    const int j0 = lane * 8;
+    float v[8];
+    bool on[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[e] = 0.f; on[e] = false; }
+    if (j0 < Tp) {
+      const float4 a = *reinterpret_cast<const float4*>(s + j0), c4 = *reinterpret_cast<const float4*>(s + j0 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) on[e] = (j0 + e < Tk) && (m == nullptr || m[j0 + e] != 0);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (on[e]) mx = fmaxf(mx, v[e]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[e] = on[e] ? act_exp<T>(v[e] - mx) : 0.f; sum += v[e]; }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    if (j0 < Tp) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rounded<T>(v[e] * inv);
+      store8(P + row * Tp + j0, v);
+      if (Pd != nullptr) {
+        float m0[4], m1[4];
+        drop_mult<4>(drop, (unsigned long long)row * Tp + j0, m0);
+        drop_mult<4>(drop, (unsigned long long)row * Tp + j0 + 4, m1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[e] *= m0[e]; v[4 + e] *= m1[e]; }
+        store8(Pd + row * Tp + j0, v);
+      }
+    }
+    return;
+  }
   float mx = -INFINITY;
   for (int j = lane; j < Tk; j += 32)
     if (m == nullptr || m[j]) mx = fmaxf(mx, s[j]);
@@ -525,6 +578,34 @@ softmax_bwd_kernel(const T* __restrict__ P, const float* __restrict__ dPd, T* __
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
+  if (Tp <= 256) {
+    const int j0 = lane * 8;
+    float pv[8], dp[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { pv[e] = 0.f; dp[e] = 0.f; }
+    if (j0 < Tp) {
+      float m0[4], m1[4];
+      drop_mult<4>(drop, (unsigned long long)row * Tp + j0, m0);
+      drop_mult<4>(drop, (unsigned long long)row * Tp + j0 + 4, m1);
+      const float4 a = *reinterpret_cast<const float4*>(dPd + row * Tp + j0), c4 = *reinterpret_cast<const float4*>(dPd + row * Tp + j0 + 4);
+      const float dd[8] = {a.x * m0[0], a.y * m0[1], a.z * m0[2], a.w * m0[3], c4.x * m1[0], c4.y * m1[1], c4.z * m1[2], c4.w * m1[3]};
+      float pl[8];
+      load8(P + row * Tp + j0, pl);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (j0 + e < Tk) { pv[e] = pl[e]; dp[e] = dd[e]; }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dot = fmaf(pv[e], dp[e], dot);
+    dot = warp_sum(dot);
+    if (j0 < Tp) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pv[e] *= dp[e] - dot;
+      store8(dS + row * Tp + j0, pv);
+    }
+    return;
+  }
   float dot = 0.f;
   for (int j0 = lane * 4; j0 < Tp; j0 += 128) {
     float mult[4];
