@@ -363,7 +363,14 @@ bool gemm_gen_tc_supported(const void* A, long long lda, long long a_hs, long lo
 int gemm_gen(const void* A, int a_mn, long long lda, long long a_hs, long long a_bs, const void* B, int b_mn, long long ldb,
              long long b_hs, long long b_bs, void* C, int c_dtype, long long ldc, long long c_hs, long long c_bs,
              int accumulate, int M, int N, int K, int nH, int nB, float alpha, int splits, cudaStream_t st) {
-  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  if (!(c_dtype == CFM_F32 && accumulate)) {
+    // no split-K for a bf16 / overwritten output: narrower tiles instead when 256-wide ones leave most SMs idle (input
+    // gradients at the C5 shard: 3968 x 256 with K = 2048 is 31 tiles of 128 x 256 -- 8.5 us of MMA time on 31 SMs -- or
+    // 124 tiles of 128 x 64)
+    const long long mt = (long long)nB * nH * ((M + BM - 1) / BM);
+    while (bn > 64 && mt * ((N + bn - 1) / bn) * 2 <= num_sms()) bn /= 2;
+  }
   GenParams p{};
   p.M = M; p.N = N; p.K = K; p.nH = nH; p.nB = nB;
   p.m_tiles = (M + BM - 1) / BM;
