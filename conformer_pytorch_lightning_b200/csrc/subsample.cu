@@ -291,6 +291,11 @@ struct FusedParams {
   int B, Tin, idim, T2, F2, TL, tiles_per_utt;
 };
 
+// ATMEM: relu(conv1) goes straight back into tensor memory (tcgen05.st of the packed bf16 row, 32 columns per k-step, two
+// slots in the 128 columns the accumulators leave free) and conv2 reads its A operand from there (tcgen05.mma with A in
+// TMEM): no shared-memory A tile, no st.shared + fence.proxy.async per k-step in the converter warps, and one operand
+// less on the shared-memory port.
+template <bool ATMEM>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C) K-major, box (64, 256)
                        const __grid_constant__ CUtensorMap tmO,   // O as (C, F2, T2, B), box (64, F2, TL, 1)
@@ -303,9 +308,12 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
   uint8_t* ring = sW1 + kW1Bytes;                       // 2 output staging tiles
   float* sb1 = reinterpret_cast<float*>(ring + 2 * kBuf);
   float* sb2 = sb1 + BN;
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(sb2 + BN);   // [kBSt] W2 tile landed
-  uint64_t* b_empty = b_full + kBSt;                    // [kBSt] conv2 MMAs that read the slot retired
-  uint64_t* a_full = b_empty + kBSt;                    // [kASt] A tile written by converter group g & 1 (128 arrivals)
+  // ATMEM: the two shared-memory A slots (32 KB, directly behind the W2 ring) are not needed: a fifth W2 stage lives there
+  constexpr int NB = ATMEM ? kBSt + 1 : kBSt;
+  static_assert(kASt * kABytes == kBBytes, "the fifth W2 stage takes exactly the A slots");
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(sb2 + BN);   // [NB] W2 tile landed
+  uint64_t* b_empty = b_full + (kBSt + 1);              // [NB] conv2 MMAs that read the slot retired
+  uint64_t* a_full = b_empty + (kBSt + 1);              // [kASt] A tile written by converter group g & 1 (128 arrivals)
   uint64_t* a_empty = a_full + kASt;                    // [kASt]
   uint64_t* im_full = a_empty + kASt;                   // [4] im2col slot written (128 arrivals)
   uint64_t* im_empty = im_full + 4;                     // [4] conv1 MMAs of the tap retired
@@ -323,9 +331,9 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmW); prefetch_tmap(&tmO); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kBSt; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
     for (int s = 0; s < kASt; ++s) { mbar_init(a_full + s, 128); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(im_full + s, 128); mbar_init(im_empty + s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(im_full + s, 64); mbar_init(im_empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc1_full + s, 1); mbar_init(acc1_empty + s, 128); }
     mbar_init(tfull, 1); mbar_init(tempty, 128);
     fence_barrier_init();
@@ -352,13 +360,14 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc1 = tmem_base + BN;            // 2 x 64 columns
+  const uint32_t tmem_a = tmem_base + BN + 128;         // ATMEM: 2 x 32 columns (A operand of conv2, 64 packed bf16 per row)
 
   if (warp == 0) {
     // ===================== TMA producer: W2 tiles =====================
     for (int g = 0; g < n_ks; ++g) {
       const int ks = g % 36, tap = ks >> 2, kc = ks & 3;
-      const int bs = g % kBSt;
-      mbar_wait(b_empty + bs, ((g / kBSt) & 1) ^ 1);
+      const int bs = g % NB;
+      mbar_wait(b_empty + bs, ((g / NB) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(b_full + bs, kBBytes);
         tma_load_2d(sB + bs * kBBytes, &tmW, b_full + bs, tap * BN + kc * BK, 0);
@@ -386,21 +395,69 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
     if (n_ks > 0) { conv1(0); conv1(1); }
     for (int g = 0; g < n_ks; ++g) {
       const int ks = g % 36, tl = g / 36;
-      const int as = g & 1, bs = g % kBSt;
+      const int as = g & 1, bs = g % NB;
+      // conv1 of k-step g+2 first: its TMEM buffer was released as soon as the converter had LOADED conv1(g), so it runs while
+      // the converter is still turning conv1(g) into the A operand of conv2(g) (issued after conv2(g) it used to sit behind
+      // that whole conversion: the converter chain, not the tensor pipe, set the pace)
+      if (g + 2 < n_ks) conv1(g + 2);
       if (ks == 0) { mbar_wait(tempty, (tl & 1) ^ 1); }  // the epilogue has drained the previous tile's accumulator
       mbar_wait(a_full + as, (g >> 1) & 1);
-      mbar_wait(b_full + bs, (g / kBSt) & 1);
+      mbar_wait(b_full + bs, (g / NB) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t da = umma_desc_sw128(smem_u32(sAt + as * kABytes)), db = umma_desc_sw128(smem_u32(sB + bs * kBBytes));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc2, (ks | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) {
+          if constexpr (ATMEM) umma_bf16_ts(tmem_base, tmem_a + as * 32 + k * 8, db + 2 * k, idesc2, (ks | k) != 0);
+          else umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc2, (ks | k) != 0);
+        }
         umma_commit(a_empty + as);
         umma_commit(b_empty + bs);
         if (ks == 35) umma_commit(tfull);
       }
       __syncwarp();
-      if (g + 2 < n_ks) conv1(g + 2);
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== im2col producers (64 threads, two tile rows each): the 3 x 3 fp32 patch of every position for
+    //                       tap `tapg` -> bf16 K-step slot tapg & 3 of the [128 x 16 x 4] im2col tile.  They run up to four taps
+    //                       ahead of conv1 (im_empty), so the global-load latency of the patches is off the converters'
+    //                       critical path (it used to cost them ~1.5 k cycles per tap) =====================
+    const int n_taps = n_my * 9;
+    const int tid = threadIdx.x - 64;
+    for (int tapg = 0; tapg < n_taps; ++tapg) {
+      const int tl = tapg / 9, tap = tapg - tl * 9;
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+      const int b = t / p.tiles_per_utt, t20 = (t % p.tiles_per_utt) * p.TL;
+      const int i = tap / 3, j = tap - i * 3;
+      const int slot = tapg & 3;
+      float v[2][9];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = tid + 64 * h;
+        const int dt2 = r / p.F2, f2 = r - dt2 * p.F2;
+        const int t2 = t20 + dt2;
+        if (r < rows_used && t2 < p.T2) {
+          const float* xin = p.x + ((size_t)b * p.Tin + 4 * t2 + 2 * i) * p.idim + 4 * f2 + 2 * j;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[h][a * 3 + c] = __ldg(xin + a * p.idim + c);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) v[h][k] = 0.f;
+        }
+      }
+      mbar_wait(im_empty + slot, ((tapg >> 2) & 1) ^ 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = tid + 64 * h;
+        uint8_t* rowp = sIm + r * 128;
+        *reinterpret_cast<uint4*>(rowp + ((((2 * slot) ^ r) & 7) << 4)) =
+            make_uint4(pack_bf16x2(v[h][0], v[h][1]), pack_bf16x2(v[h][2], v[h][3]), pack_bf16x2(v[h][4], v[h][5]), pack_bf16x2(v[h][6], v[h][7]));
+        *reinterpret_cast<uint4*>(rowp + ((((2 * slot + 1) ^ r) & 7) << 4)) = make_uint4(pack_bf16x2(v[h][8], 0.f), 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(im_full + slot);
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== converter warps: thread = tile row (position); warpgroup cg takes the k-steps g = cg mod 2
@@ -408,40 +465,8 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
     const int cg = (warp - 4) >> 2;
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const int dt2 = r / p.F2, f2 = r - dt2 * p.F2;
-    // im2col of tap `tapg` (global counter) into K-step slot tapg & 3
-    auto build_im = [&](int tapg) {
-      const int tl = tapg / 9, tap = tapg - tl * 9;
-      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
-      const int b = t / p.tiles_per_utt, t20 = (t % p.tiles_per_utt) * p.TL;
-      const int i = tap / 3, j = tap - i * 3;
-      const int slot = tapg & 3;
-      mbar_wait(im_empty + slot, ((tapg >> 2) & 1) ^ 1);
-      const int t2 = t20 + dt2;
-      float v[9];
-      if (r < rows_used && t2 < p.T2) {
-        const float* xin = p.x + ((size_t)b * p.Tin + 4 * t2 + 2 * i) * p.idim + 4 * f2 + 2 * j;
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) v[a * 3 + c] = __ldg(xin + a * p.idim + c);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) v[k] = 0.f;
-      }
-      uint8_t* rowp = sIm + r * 128;
-      *reinterpret_cast<uint4*>(rowp + ((((2 * slot) ^ r) & 7) << 4)) =
-          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(rowp + ((((2 * slot + 1) ^ r) & 7) << 4)) = make_uint4(pack_bf16x2(v[8], 0.f), 0u, 0u, 0u);
-      fence_proxy_async_smem();
-      mbar_arrive(im_full + slot);
-    };
-    const int n_taps = n_my * 9;
-    for (int tg = cg; tg < 3 && tg < n_taps; tg += 2) build_im(tg);
     for (int g = cg; g < n_ks; g += 2) {
       const int kc = g & 3, ab = g & 1;
-      // stay three taps ahead of conv1: at this group's first k-step of tap tg, build tap tg+3 if it is ours
-      if ((kc >> 1) == 0 && (((g >> 2) + 3) & 1) == cg && (g >> 2) + 3 < n_taps) build_im((g >> 2) + 3);
       mbar_wait(acc1_full + ab, (g >> 1) & 1);
       tc_fence_after();
       uint32_t v[64];
@@ -464,10 +489,20 @@ subsample_fused_kernel(const __grid_constant__ CUtensorMap tmW,   // W2 (C, 9*C)
         pk[jj] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
       }
       mbar_wait(a_empty + cg, ((g >> 1) & 1) ^ 1);       // conv2 has finished with the A tile that lived here (slot g & 1 = cg)
-      uint8_t* a = sAt + cg * kABytes;
+      if constexpr (ATMEM) {
+        tc_fence_after();
+        uint32_t pr[32];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(a + r * 128 + (((jj ^ r) & 7) << 4)) = pk[jj];
-      fence_proxy_async_smem();
+        for (int jj = 0; jj < 8; ++jj) { pr[4 * jj] = pk[jj].x; pr[4 * jj + 1] = pk[jj].y; pr[4 * jj + 2] = pk[jj].z; pr[4 * jj + 3] = pk[jj].w; }
+        tmem_st32(tmem_a + lane_base + cg * 32, pr);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        uint8_t* a = sAt + cg * kABytes;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint4*>(a + r * 128 + (((jj ^ r) & 7) << 4)) = pk[jj];
+        fence_proxy_async_smem();
+      }
       mbar_arrive(a_full + cg);
     }
   } else if (warp >= 12) {
@@ -577,10 +612,13 @@ extern "C" int cfm_subsample_conv(const float* x, int B, int Tin, int idim, cons
       if ((rc = make_map_nd(&tmO, out, 4, dims, str, box)) != 0) return rc;
     }
     FusedParams fp{x, w1, b1, b2, B, Tin, idim, T2, F2, TL, (T2 + TL - 1) / TL};
-    CFM_SMEM_OPT_IN(subsample_fused_kernel, kFusedSmem);
+    static const bool a_smem = env_is("CFM_B200_SUBSAMPLE_ATMEM", "0");
+    CFM_SMEM_OPT_IN(subsample_fused_kernel<true>, kFusedSmem);
+    CFM_SMEM_OPT_IN(subsample_fused_kernel<false>, kFusedSmem);
     const int total = B * fp.tiles_per_utt;
     const int grid = total < num_sms() ? total : num_sms();
-    CFM_CUDA_OK(launch_pdl(subsample_fused_kernel, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
+    if (a_smem) CFM_CUDA_OK(launch_pdl(subsample_fused_kernel<false>, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
+    else CFM_CUDA_OK(launch_pdl(subsample_fused_kernel<true>, dim3(grid), dim3(kFusedThreads), (size_t)kFusedSmem, st, 1, tmW, tmO, fp));
     CFM_LAUNCHED_K("subsample_fused");
     return 0;
   }
