@@ -396,3 +396,52 @@ def test_train_eval_switch_leaves_parameters_untouched(dtype):
         if "running_" in k or "num_batches" in k:
             continue                                          # the second training forward updates the running statistics
         assert torch.equal(v, after[k]), k
+
+
+@pytest.mark.gpu
+def test_eval_graph_follows_further_training():
+    """train -> eval (the inference CUDA graph is captured, its bf16 weights are the optimizer's mirrors) -> train more ->
+    eval again (graph replay): the replayed graph must compute with the NEW weights, bit-identical to a fresh encoder."""
+    import conformer_pytorch_lightning_b200 as C
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, static_chunk_size=16, dropout=0.0, attention_dropout=0.0, pos_enc_dropout=0.0)
+    rs = np.random.RandomState(9)
+    feats = torch.from_numpy(rs.standard_normal((4, 300, 80)).astype(np.float32)).cuda()
+    lens = torch.tensor([300, 280, 200, 150], dtype=torch.int32, device="cuda")
+    labels = torch.from_numpy(rs.randint(1, 50, size=(4, 8)).astype(np.int64)).cuda()
+    lab_len = torch.full((4,), 8, dtype=torch.int64, device="cuda")
+    enc = build_encoder(cfg, 0, compute_dtype=torch.bfloat16)
+    dec = C.CTCDecoder(60, cfg["encoder_dim"], 0.0).cuda()
+    dec.compute_dtype = torch.bfloat16
+    opt = C.FlatAdam(list(enc.parameters()) + list(dec.parameters()), lr=1e-3)
+
+    def train(n):
+        enc.train()
+        for _ in range(n):
+            opt.zero_grad(set_to_none=True)
+            out, mask = enc(feats, lens)
+            dec(out.float(), mask.squeeze(1).sum(1), labels, lab_len).backward()
+            opt.step()
+
+    def evaluate(n):
+        enc.eval()
+        with torch.no_grad():
+            return [enc(feats, lens)[0].clone() for _ in range(n)]
+
+    def fresh():
+        e2 = build_encoder(cfg, 0, compute_dtype=torch.bfloat16)
+        e2.load_state_dict(enc.state_dict())
+        e2.eval()
+        with torch.no_grad():
+            return e2(feats, lens)[0]
+
+    train(3)
+    a = evaluate(3)                      # eager, capture, replay
+    ref_a = fresh()
+    assert all(torch.equal(x, ref_a) for x in a)
+    train(2)
+    b = evaluate(2)                      # replays of the graph captured above (or a rebuilt plan): new weights either way
+    ref_b = fresh()
+    assert not torch.equal(ref_a, ref_b)
+    assert all(torch.equal(x, ref_b) for x in b)
