@@ -23,6 +23,7 @@
 #include "tc_common.cuh"
 #include "resid_epilogue.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -83,13 +84,17 @@ constexpr int kMaxSmem = 232448;
 // 128 A rows and only HALF of the W rows, so the shared-memory fill and the B-operand reads per SM are halved (the
 // single-CTA kernel reads 96 B/clk of operands and fills 96 B/clk by TMA against the 128 B/clk one SM's shared memory
 // serves) and the smaller stage buys a deeper ring.
-template <int BN, bool RESID, bool PAIR = false> struct Cfg {
+template <int BN, bool RESID, bool PAIR = false, int NG = 2> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // epilogue warps: every epilogue is latency bound with one warp per scheduler, so two warpgroups split the tile's
   // columns (2 warps / SMSP); the residual/LN epilogue exchanges its partial row sums through shared memory
-  static constexpr int kEpiThreads = 256;
+  // NG = 4 for the plain activation epilogues of 256-wide tiles: bias + SiLU of a 128 x 256 tile takes two warpgroups 4.1 k
+  // cycles (tanh.approx on 2 warps per scheduler), as long as the tile's MMAs at K = 512; four warpgroups own one 64-column
+  // sub-tile each
+  static constexpr int kGroups = NG;
+  static constexpr int kEpiThreads = 128 * NG;
   static constexpr int kThreads = 128 + kEpiThreads;
   static constexpr int kBufs = 4;                                  // staging ring (2 per warpgroup)
   static constexpr int kParamFloats = RESID ? 5 * BN + 1024 : BN;  // bias (+ LN gammas/betas + row-sum exchange)
@@ -113,13 +118,18 @@ struct GemmParams {
   unsigned long long* keys;     // ARGMAX epilogue: per-row packed (ordered logit, ~column), combined with atomicMax
   int n_valid;                  // ARGMAX: columns >= n_valid are padding (W rows zero-filled by TMA)
   int pair;                     // host-side: launch the cta_group::2 kernel (W tensor map holds half-tile boxes)
+  long long* trace;             // optional cycle accounting of CTA 0 (tools/gemm_trace.py); nullptr in production
 };
 constexpr int EPI_ARGMAX = 100; // internal epilogue of cfm_ctc_argmax: no C tile at all
 
 
 
+template <int BN, int EPI> constexpr int epi_groups() {
+  return (BN == 256 && (EPI == CFM_EPI_BIAS || EPI == CFM_EPI_BIAS_SILU || EPI == CFM_EPI_BIAS_RELU)) ? 4 : 2;
+}
+
 template <int BN, int EPI, bool PAIR>
-__global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR>::kThreads), 1)
+__global__ void __launch_bounds__((Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR, epi_groups<BN, EPI>()>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC,   // F1: bf16 output; RESIDUAL: fp32 X store
                const __grid_constant__ CUtensorMap tmR,   // RESIDUAL: fp32 residual load
@@ -127,7 +137,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const GemmParams p) {
   constexpr bool GLU = (EPI == CFM_EPI_BIAS_GLU);
   constexpr bool RESID = (EPI == CFM_EPI_RESIDUAL);
-  using C = Cfg<BN, RESID, PAIR>;
+  using C = Cfg<BN, RESID, PAIR, epi_groups<BN, EPI>()>;
+  constexpr int NG = C::kGroups;
   constexpr int OUT_BN = GLU ? BN / 2 : BN;      // output columns per tile
   // 1024-byte alignment is what SWIZZLE_128B tiles need; keeping `smem` a plain shared-space array (no integer
   // round-up) lets ptxas emit LDS/STS instead of generic LD.E/ST.E for every epilogue access
@@ -218,14 +229,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = umma_idesc_bf16(TM, BN);
     int stage = 0, phase = 0, it = 0;
     bool have = false;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
+    long long w_acc = 0, w_full = 0, t_begin = tr ? clock64() : 0;
     for (int t = tile0; t < total; t += tstep, ++it) {
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      long long c0 = tr ? clock64() : 0;
       if constexpr (PAIR) mbar_wait_cluster(tempty_bar + acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
       else mbar_wait(tempty_bar + acc, acc_phase ^ 1);     // epilogue has drained this accumulator
+      if (tr) w_acc += clock64() - c0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < kb_count; ++kb) {
-        if (!have) mbar_wait(full_bar + stage, phase);
+        if (!have) { long long c1 = tr ? clock64() : 0; mbar_wait(full_bar + stage, phase); if (tr) w_full += clock64() - c1; }
         tc_fence_after();
         {   // probe the next slot; consumed after this stage's MMAs have been issued
           const int ns = (stage + 1 == C::kStages) ? 0 : stage + 1;
@@ -252,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
+    if (tr && lane == 0) { p.trace[0] = clock64() - t_begin; p.trace[1] = w_acc; p.trace[2] = w_full; p.trace[3] = it; }
   } else if (warp >= 4) {
     // ===================== epilogue (thread = output row; two warpgroups split the columns) ==============
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
@@ -278,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (RESID) {
         resid_stage_params<BN, 256>(sparam, threadIdx.x - 128, p.bias, n0, p.ln_mode, p.g1, p.b1, p.g2, p.b2);
       } else {
-        constexpr int GCOLS = OUT_BN / 2;
+        constexpr int GCOLS = OUT_BN / NG;
         for (int ii = et; ii < GCOLS; ii += 128) {
           const int i = grp * GCOLS + ii;
           if constexpr (EPI == EPI_ARGMAX) sparam[i] = (p.bias && n0 + i < p.n_valid) ? p.bias[n0 + i] : 0.f;
@@ -290,7 +306,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (!RESID) {
         // ---------------- bf16 activations: 64-column sub-tiles through a 2-deep staging ring + TMA store
+        const bool tre = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+        long long e0 = tre ? clock64() : 0;
         mbar_wait(tfull_bar + acc, acc_phase);
+        if (tre) { p.trace[4] += clock64() - e0; e0 = clock64(); }
         tc_fence_after();
         if constexpr (EPI == EPI_ARGMAX) {
           // row-wise (max, argmax) of this warpgroup's columns; tiles of the same rows on other CTAs are combined
@@ -328,10 +347,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           named_bar_sync(bar_id, 128);                 // sparam may be restaged for the next tile
         } else {
 #pragma unroll 1
-        for (int ss = 0; ss < OUT_BN / 128; ++ss, ++sub_cnt) {
-          const int sub = grp * (OUT_BN / 128) + ss;   // 64-column sub-tile owned by this warpgroup
-          uint8_t* buf = ring + (grp * 2 + (sub_cnt & 1)) * kBufBytes;
-          if (elected) bulk_wait_read<1>();            // the store issued two sub-tiles ago has left this buffer
+        for (int ss = 0; ss < OUT_BN / (64 * NG); ++ss, ++sub_cnt) {
+          const int sub = grp * (OUT_BN / (64 * NG)) + ss;   // 64-column sub-tile owned by this warpgroup
+          // staging buffers: two per warpgroup (NG = 2) or one (NG = 4: its previous store must have left it)
+          uint8_t* buf = ring + (NG == 2 ? grp * 2 + (sub_cnt & 1) : grp) * kBufBytes;
+          if (elected) {
+            long long e1 = tre ? clock64() : 0;
+            if constexpr (NG == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            if (tre) p.trace[5] += clock64() - e1;
+          }
           named_bar_sync(bar_id, 128);                 // (also publishes sparam on the first sub-tile)
           uint32_t v[64];
           {
@@ -372,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         release_acc(acc);
+        if (tre) p.trace[6] += clock64() - e0;
         }
       } else {
         // ---------------- fp32 residual stream (+ fused LayerNorms): resid_epilogue.cuh
@@ -403,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int EPI, bool PAIR>
 int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, const CUtensorMap& tmR,
                    const CUtensorMap& tmY, const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR>;
+  using C = Cfg<BN, EPI == CFM_EPI_RESIDUAL, PAIR, epi_groups<BN, EPI>()>;
   CFM_SMEM_OPT_IN((gemm_tc_kernel<BN, EPI, PAIR>), C::kSmemBytes);
   constexpr int OUT_BN = (EPI == CFM_EPI_BIAS_GLU) ? BN / 2 : BN;
   constexpr int TM = PAIR ? 2 * BM : BM;
@@ -421,12 +446,16 @@ int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtenso
 // L2 flushed) K=2048/N=512 54.3 -> 50.2 us, K=2048/N=256 37.9 -> 35.8, K=512/N=1536 35.8 -> 33.8; short-K tiles with a
 // heavy epilogue lose (K=256/N=2048 + SiLU 29.6 -> 35.7, K=512/N=512 + residual 29.7 -> 31.7: the cluster-scope
 // accumulator hand-back and the 2-CTA launch granularity cost more than the halved operand traffic saves).
+// Warm cycle accounting of one CTA (tools/gemm_trace.py): K=512/N=2048 + SiLU 6.8 k -> 5.1 k cycles per 128 x 256 tile (the
+// single-CTA MMA warp waits 28 % of its time for operands: 384 KB per tile against the ~70 B/clk a single SM's TMA
+// delivers; the SiLU epilogue itself is 4.1 k cycles per tile, as long as the 4.1 k of MMAs), K=512/N=1536 6.6 k -> 4.8 k,
+// K=2048/N=512 23.3 k -> 18.0 k (ideal 16.4 k).
 // CFM_B200_GEMM_PAIR=0/1 forces the choice (measurement switch).
 inline bool use_pair(int M, int N, int K, int epilogue) {
   static const bool off = env_is("CFM_B200_GEMM_PAIR", "0"), on = env_is("CFM_B200_GEMM_PAIR", "1");
   if (off || M <= BM) return false;
   if (on) return true;
-  return K >= 1024 || (K >= 512 && N >= 1024 && epilogue == CFM_EPI_BIAS);
+  return K >= 1024 || (K >= 512 && N >= 1024 && epilogue != CFM_EPI_BIAS_GLU);
 }
 
 template <int BN, int EPI>
@@ -486,6 +515,7 @@ int gemm_tc_ln(const void* A, int lda, const void* W, const float* bias, float* 
   if ((rc = make_2d(&tmW, false, W, w_rows, K, K, (epilogue == CFM_EPI_BIAS_GLU) ? 128 : (pair ? bn / 2 : bn))) != 0) return rc;
   GemmParams p{};
   p.pair = pair ? 1 : 0;
+  if (const char* e = getenv("CFM_B200_GEMM_TRACE_PTR")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   p.bias = bias; p.row_valid = row_valid; p.y_row_valid = y_row_valid;
   p.g1 = g1; p.b1 = b1; p.g2 = g2; p.b2 = b2;
   p.alpha = alpha; p.eps = eps; p.M = M; p.N = N; p.K = K; p.ln_mode = ln_mode;
