@@ -90,7 +90,8 @@ def _train_worker(rank, world, port, q):
         out, _ = enc(torch.from_numpy(feats[rank::world]).cuda(), torch.from_numpy(lens[rank::world]).cuda())
         out.square().mean().backward()
         ddp.sync_grads([p for n, p in enc.named_parameters() if n.startswith("embed.")])
-        grads.append({k: p.grad.detach().float().cpu() for k, p in enc.named_parameters() if p.grad is not None})
+        # numpy arrays: plain pickling through the queue (torch tensors travel as shared-memory handles that die with this process)
+        grads.append({k: p.grad.detach().float().cpu().numpy() for k, p in enc.named_parameters() if p.grad is not None})
     q.put((rank, grads, sync.buckets_sent))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,6 +112,7 @@ def test_two_gpu_gradient_allreduce_equals_mean_of_shard_gradients():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda r: r[0])
+    res = [(r, [{k: torch.from_numpy(v) for k, v in g.items()} for g in grads], n) for r, grads, n in res]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
