@@ -55,10 +55,12 @@ class FlatAdam(torch.optim.Optimizer):
         self._segments = {}          # id(group) -> list of _Segment (built at the first step from the gradient layout)
         self._steps = {}             # id(group) -> python int (the kernel takes the step count by value)
         self._step_tensor = {}
-        for g in self.param_groups:
-            for p in g["params"]:
-                if not p.is_cuda or p.dtype != torch.float32:
-                    raise NotImplementedError("FlatAdam: CUDA fp32 parameters only (no CPU fallback)")
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)          # (also called by Optimizer.__init__ for the initial groups)
+        for p in self.param_groups[-1]["params"]:
+            if not p.is_cuda or p.dtype != torch.float32:
+                raise NotImplementedError("FlatAdam: CUDA fp32 parameters only (no CPU fallback)")
 
     # ---------------------------------------------------------------- layout
     @torch.no_grad()
