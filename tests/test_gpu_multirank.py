@@ -137,3 +137,56 @@ def test_two_gpu_gradient_allreduce_equals_mean_of_shard_gradients():
                 assert float((step_grads[k] - v).abs().max()) < tol * scale, (rank, k)
     for k in ref:                                            # and the two ranks agree
         assert torch.allclose(res[0][1][-1][k], res[1][1][-1][k], rtol=0, atol=0)
+
+
+def _adam_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import conformer_oracle as O
+    from _util import build_encoder
+    import conformer_pytorch_lightning_b200 as C
+    from conformer_pytorch_lightning_b200 import ddp
+    cfg = O.conformer_cfg("M", encoder_num_layers=2, dropout=0.1, attention_dropout=0.1, pos_enc_dropout=0.0,
+                          static_chunk_size=16)
+    enc = build_encoder(cfg, 2 + rank, device=f"cuda:{rank}", compute_dtype=torch.bfloat16).train()   # different init per rank
+    ddp.broadcast_parameters(enc)                                                                    # ... until the broadcast
+    sync = ddp.attach(enc)
+    opt = C.FlatAdam(enc.parameters(), lr=1e-3)
+    feats, lens = _inputs()
+    losses = []
+    for step in range(4):                                    # eager, eager (re-pointed parameters), capture, replay
+        opt.zero_grad(set_to_none=True)
+        out, _ = enc(torch.from_numpy(feats[rank::world]).cuda(), torch.from_numpy(lens[rank::world]).cuda())
+        loss = out.square().mean()
+        loss.backward()
+        ddp.sync_grads([p for n, p in enc.named_parameters() if n.startswith("embed.")])
+        opt.step()
+        losses.append(float(loss))
+    sd = {k: v.detach().float().cpu().numpy() for k, v in enc.state_dict().items() if v.dtype.is_floating_point and "running_" not in k}
+    q.put((rank, sd, losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_flat_adam_keeps_ranks_in_sync():
+    """Data-parallel training with the native optimizer: both ranks start from rank 0's weights, see different shards (and
+    different dropout masks), all-reduce their gradients and apply FlatAdam -- after four steps the parameters are bit-identical
+    on the two ranks (BatchNorm running statistics are per rank, like the reference's non-Sync BatchNorm)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_adam_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    a, b = res[0][1], res[1][1]
+    assert a.keys() == b.keys() and len(a) > 50
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert all(np.isfinite(res[r][2]).all() for r in range(world))
